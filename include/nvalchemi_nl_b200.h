@@ -1,0 +1,110 @@
+/*
+ * nvalchemi_nl_b200.h — C ABI of the B200-native cell-list neighbor-list library
+ * (libnvalchemi_nl_b200.so, sm_100a).  Plain pointers and sizes only: no torch, no Warp.
+ *
+ * The reference (NVIDIA/nvalchemi-toolkit-ops v0.2.0) has no FFI: its "operator ABI" for this path
+ * is four torch.library custom ops that mutate pre-allocated tensors
+ *   nvalchemiops::build_cell_list        nvalchemiops/neighborlist/cell_list.py:725-889
+ *   nvalchemiops::query_cell_list        nvalchemiops/neighborlist/cell_list.py:892-1034
+ *   nvalchemiops::batch_build_cell_list  nvalchemiops/neighborlist/batch_cell_list.py:739-912
+ *   nvalchemiops::batch_query_cell_list  nvalchemiops/neighborlist/batch_cell_list.py:915-1067
+ * plus the COO conversion  neighbor_utils.py:362-441.  Each entry point below names the reference
+ * interface it stands in for.  All pointers are DEVICE pointers unless stated otherwise; `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns 0 on
+ * success and a negative code on failure (message via nvnl_last_error()).
+ *
+ * dtype: 0 = float32 positions/cell, 1 = float64.
+ * A "workspace" is an opaque device buffer of nvnl_workspace_bytes() bytes (256-byte aligned)
+ * that plays the role of the reference's 7-tensor cell-list cache (neighbor_utils.py:494-539).
+ */
+#ifndef NVALCHEMI_NL_B200_H
+#define NVALCHEMI_NL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVNL_ABI_VERSION 1
+#define NVNL_F32 0
+#define NVNL_F64 1
+
+/* error bits reported by nvnl_status() */
+#define NVNL_ERR_IMAGE_RANGE 1   /* atom more than 1e6 periodic images away, or search radius >= 64 cells */
+#define NVNL_ERR_BAD_BATCH_IDX 2 /* batch_idx outside [0, num_systems) */
+#define NVNL_ERR_SINGULAR_CELL 4 /* cell matrix not invertible */
+
+int nvnl_abi_version(void);
+const char* nvnl_last_error(void);
+
+/* Size of the opaque cell-list cache for n_atoms atoms in n_systems systems.
+ * Stands in for estimate_cell_list_sizes + allocate_cell_list
+ * (cell_list.py:639-722, neighbor_utils.py:494-539) — but needs no device->host sync: the number
+ * of cells is bounded by n_atoms + n_systems by construction. */
+size_t nvnl_workspace_bytes(int64_t n_atoms, int64_t n_systems, int dtype);
+
+/* build_cell_list / batch_build_cell_list (cell_list.py:725-889, batch_cell_list.py:739-912):
+ * grid selection, atom->cell hash, counting sort of positions into per-cell float4 runs.
+ *   positions [n_atoms,3], cell [n_systems,3,3] (rows = lattice vectors), pbc [n_systems,3] (bytes),
+ *   batch_idx [n_atoms] int32 or NULL (single system), batch_ptr [n_systems+1] int32 or NULL. */
+int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* First half of the COO path: per-atom neighbor counts and their exclusive scan.
+ * Replaces the num_neighbors side of query_cell_list and the cumsum of
+ * get_neighbor_list_from_neighbor_matrix (neighbor_utils.py:432-435).
+ *   cutoff_sq: the squared cutoff already rounded to the input precision
+ *   num_neighbors [n_atoms] out, neighbor_ptr [n_atoms+1] out (may be NULL to skip the scan).
+ *   fma: 1 = mul+fma-chain distance arithmetic (Warp/NVRTC default), 0 = separately rounded. */
+int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+               double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
+               void* stream);
+
+/* Device->host read of the control block (synchronizes `stream`): total number of directed pairs
+ * found by the last nvnl_count, the largest per-atom count (what assert_max_neighbors checks,
+ * neighbor_utils.py:352-359), number of cells, error bits, and whether any atom was outside the
+ * primary periodic image.  The one sync of the COO path (the reference has three). Host pointers. */
+int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
+                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, void* stream);
+
+/* Second half of the COO path: writes edge_index [2,num_pairs] (row 0 = source atoms, sorted),
+ * shifts [num_pairs,3].  Output identical in content to cell_list(..., return_neighbor_list=True)
+ * (cell_list.py:1432-1441) without materialising the padded matrix.
+ *   index_offset is added to every atom index written (rank-sharded batches, 0 otherwise). */
+int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                  double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
+                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, void* stream);
+
+/* query_cell_list / batch_query_cell_list (cell_list.py:892-1034, batch_cell_list.py:915-1067)
+ * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of
+ * neighbor_matrix [n_atoms,max_neighbors], neighbor_matrix_shifts [n_atoms,max_neighbors,3] and
+ * num_neighbors [n_atoms] is written exactly once.  num_neighbors keeps counting past
+ * max_neighbors (neighbor_utils.py:139-147). */
+int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                     double cutoff_sq, int half_fill, int fma, int32_t* neighbor_matrix,
+                     int32_t* neighbor_matrix_shifts, int32_t* num_neighbors, int32_t max_neighbors,
+                     int32_t fill_value, void* stream);
+
+/* Introspection for tests / rebuild detection: copies the per-system grid (cells per dimension and
+ * stencil radius, int32 [n_systems,3] each, device pointers, either may be NULL). */
+int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int32_t* cells_per_dimension,
+                  int32_t* neighbor_search_radius, void* stream);
+
+/* Multi-GPU re-assembly (north_star: batch_ptr-sharded ranks + ONE NCCL all-gather; the reference has
+ * no distributed code).  Each rank fills a block [ src(stride) | dst(stride) | shifts(3*stride) ] with
+ * nvnl_fill_coo (edge_index = block, shifts = block + 2*stride, num_pairs = stride); after the
+ * all-gather `recv` holds n_ranks such blocks and this kernel writes the global edge_index
+ * [2,total_pairs] and shifts [total_pairs,3].  counts_host: pairs per rank (HOST pointer). */
+int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, const int64_t* counts_host,
+                         int32_t* edge_index, int64_t total_pairs, int32_t* shifts, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t nvnl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVALCHEMI_NL_B200_H */

@@ -1,0 +1,340 @@
+// nvnl_api.cu — C ABI (include/nvalchemi_nl_b200.h) over the sm_100a kernels.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/nvalchemi_nl_b200.h"
+#include "nvnl_sweep.cuh"
+
+using namespace nvnl;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess)
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define NVNL_CHECK_LAUNCH(what)                                   \
+    do {                                                          \
+        g_launches.fetch_add(1, std::memory_order_relaxed);       \
+        cudaError_t e__ = cudaGetLastError();                     \
+        if (e__ != cudaSuccess) return fail(-2, what, e__);       \
+    } while (0)
+
+int rec_bytes(int dtype) { return dtype == NVNL_F64 ? (int)sizeof(Rec<double>) : (int)sizeof(Rec<float>); }
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+constexpr size_t kSweepSmemBytes = (size_t)kCandBytes + (size_t)kSweepWarps * kRowCap * 4 * sizeof(int) + sizeof(SweepSmem);
+
+template <typename T, int MODE, bool HALF, bool FMA>
+int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
+    auto kern = k_sweep<T, MODE, HALF, FMA>;
+    static int blocks_per_sm = 0;  // one static per instantiation
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemBytes);
+        if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_sweep)", e);
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kSweepThreads, kSweepSmemBytes);
+        if (e != cudaSuccess) return fail(-2, "occupancy(k_sweep)", e);
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    long long grid = (long long)sm_count() * blocks_per_sm;
+    const long long max_items = a.L.max_cells;
+    if (grid > max_items) grid = max_items > 0 ? max_items : 1;
+    kern<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(a);
+    NVNL_CHECK_LAUNCH("k_sweep");
+    return 0;
+}
+
+template <typename T, int MODE>
+int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st) {
+    if (half_fill) {
+        return fma ? launch_sweep_t<T, MODE, true, true>(a, st) : launch_sweep_t<T, MODE, true, false>(a, st);
+    }
+    return fma ? launch_sweep_t<T, MODE, false, true>(a, st) : launch_sweep_t<T, MODE, false, false>(a, st);
+}
+
+template <typename T>
+int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const int* batch_idx, const int* batch_ptr,
+            int ns, double cutoff, unsigned char* ws, cudaStream_t st) {
+    const WsLayout L = make_layout(n, ns, (int)sizeof(Rec<T>));
+    const int sms = sm_count();
+    {
+        long long work = L.max_cells + 2 > n ? L.max_cells + 2 : n;
+        long long blocks = (work + 255) / 256;
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+        if (blocks < 1) blocks = 1;
+        k_init<T><<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, ns, cell, pbc, batch_ptr, nullptr);
+        NVNL_CHECK_LAUNCH("k_init");
+    }
+    {
+        const int need_counts = (batch_ptr == nullptr && ns > 1) ? 1 : 0;
+        long long blocks = (n + 2047) / 2048;
+        if (blocks > (long long)sms * 4) blocks = (long long)sms * 4;
+        if (blocks < 1) blocks = 1;
+        k_bbox<T><<<(unsigned)blocks, kScanThreads, 0, st>>>(ws, L, n, ns, pos, batch_idx, need_counts);
+        NVNL_CHECK_LAUNCH("k_bbox");
+    }
+    k_grid<<<1, kScanThreads, 0, st>>>(ws, L, ns, cutoff);
+    NVNL_CHECK_LAUNCH("k_grid");
+    const bool vec = (reinterpret_cast<uintptr_t>(pos) % 16) == 0;
+    {
+        const long long threads = (n + 3) / 4;
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+        if (vec)
+            k_hash<T, true><<<blocks, 256, 0, st>>>(ws, L, n, ns, pos, batch_idx);
+        else
+            k_hash<T, false><<<blocks, 256, 0, st>>>(ws, L, n, ns, pos, batch_idx);
+        NVNL_CHECK_LAUNCH("k_hash");
+    }
+    {
+        Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
+        const long long cnt = L.max_cells + 1;  // out has cnt + 1 entries
+        const unsigned blocks = (unsigned)((cnt + 1 + kScanTile - 1) / kScanTile);
+        k_scan<<<blocks, kScanThreads, 0, st>>>(reinterpret_cast<const int*>(ws + L.cell_count),
+                                               reinterpret_cast<int*>(ws + L.cell_start), cnt,
+                                               reinterpret_cast<unsigned long long*>(ws + L.scan_status0),
+                                               &ctrl->scan_tile[0], nullptr, nullptr);
+        NVNL_CHECK_LAUNCH("k_scan(cells)");
+    }
+    {
+        const long long threads = (n + 3) / 4;
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+        if (vec)
+            k_scatter<T, true><<<blocks, 256, 0, st>>>(ws, L, n, pos);
+        else
+            k_scatter<T, false><<<blocks, 256, 0, st>>>(ws, L, n, pos);
+        NVNL_CHECK_LAUNCH("k_scatter");
+    }
+    return 0;
+}
+
+template <typename T>
+SweepArgs<T> base_args(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq) {
+    SweepArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.ws = ws;
+    a.L = make_layout(n, ns, (int)sizeof(Rec<T>));
+    a.batch_idx = batch_idx;
+    a.num_systems = ns;
+    a.n = n;
+    a.cutoff_sq = (T)cutoff_sq;
+    return a;
+}
+
+template <typename T>
+int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, int half_fill, int fma,
+            int* num_neighbors, int* neighbor_ptr, cudaStream_t st) {
+    SweepArgs<T> a = base_args<T>(ws, n, ns, batch_idx, cutoff_sq);
+    a.num_neighbors = num_neighbors;
+    a.queue = 0;
+    int rc = launch_sweep<T, MODE_COUNT>(a, half_fill, fma, st);
+    if (rc) return rc;
+    if (neighbor_ptr) {
+        Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
+        const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
+        k_scan<<<blocks, kScanThreads, 0, st>>>(num_neighbors, neighbor_ptr, n,
+                                               reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
+                                               &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count);
+        NVNL_CHECK_LAUNCH("k_scan(neighbors)");
+    }
+    return 0;
+}
+
+__global__ void k_get_grid(const unsigned char* __restrict__ ws, WsLayout L, int ns, int* __restrict__ cpd,
+                           int* __restrict__ radius) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const SysParams* sys = reinterpret_cast<const SysParams*>(ws + L.sys);
+    for (int d = 0; d < 3; ++d) {
+        if (cpd) cpd[3 * s + d] = sys[s].cpd[d];
+        if (radius) radius[3 * s + d] = sys[s].R[d];
+    }
+}
+
+struct RankOffsets {
+    long long off[65];  // off[g] = first global pair of rank g, off[n_ranks] = total
+};
+
+// Re-assemble the global COO arrays from the all-gathered per-rank blocks
+//   recv[g] = [ src (stride) | dst (stride) | shifts (3*stride) ]  (int32, stride = padded pair count)
+__global__ void k_unpack_gathered(const int* __restrict__ recv, int n_ranks, long long stride, RankOffsets ro,
+                                  int* __restrict__ edge_index, long long total, int* __restrict__ shifts) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += nthreads) {
+        int g = 0;
+        while (g + 1 < n_ranks && p >= ro.off[g + 1]) ++g;
+        const long long q = p - ro.off[g];
+        const int* blk = recv + (long long)g * 5 * stride;
+        edge_index[p] = blk[q];
+        edge_index[total + p] = blk[stride + q];
+        shifts[3 * p] = blk[2 * stride + 3 * q];
+        shifts[3 * p + 1] = blk[2 * stride + 3 * q + 1];
+        shifts[3 * p + 2] = blk[2 * stride + 3 * q + 2];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvnl_abi_version(void) { return NVNL_ABI_VERSION; }
+const char* nvnl_last_error(void) { return g_err; }
+int64_t nvnl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t nvnl_workspace_bytes(int64_t n_atoms, int64_t n_systems, int dtype) {
+    if (n_atoms < 0 || n_systems < 0) return 0;
+    return make_layout(n_atoms, n_systems > 0 ? n_systems : 1, rec_bytes(dtype)).total;
+}
+
+int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff, void* workspace,
+               size_t workspace_bytes, void* stream) {
+    if (n_atoms <= 0 || n_systems <= 0) return fail(-1, "nvnl_build: n_atoms and n_systems must be positive");
+    if (n_atoms > 2000000000LL) return fail(-1, "nvnl_build: n_atoms exceeds the int32 index range");
+    if (!(cutoff > 0.0)) return fail(-1, "nvnl_build: cutoff must be positive");
+    if (!positions || !cell || !pbc || !workspace) return fail(-1, "nvnl_build: null pointer");
+    if (n_systems > 1 && !batch_idx) return fail(-1, "nvnl_build: batch_idx is required for n_systems > 1");
+    if (dtype != NVNL_F32 && dtype != NVNL_F64) return fail(-1, "nvnl_build: unsupported dtype");
+    if (workspace_bytes < nvnl_workspace_bytes(n_atoms, n_systems, dtype))
+        return fail(-1, "nvnl_build: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(-1, "nvnl_build: workspace must be 256-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32)
+        return build_t<float>(static_cast<const float*>(positions), n_atoms, static_cast<const float*>(cell), pbc,
+                              batch_idx, batch_ptr, n_systems, cutoff, ws, st);
+    return build_t<double>(static_cast<const double*>(positions), n_atoms, static_cast<const double*>(cell), pbc,
+                           batch_idx, batch_ptr, n_systems, cutoff, ws, st);
+}
+
+int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+               double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr, void* stream) {
+    if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32)
+        return count_t<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, half_fill, fma, num_neighbors, neighbor_ptr, st);
+    if (dtype == NVNL_F64)
+        return count_t<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, half_fill, fma, num_neighbors, neighbor_ptr, st);
+    return fail(-1, "nvnl_count: unsupported dtype");
+}
+
+int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
+                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, void* stream) {
+    if (!workspace) return fail(-1, "nvnl_status: null workspace");
+    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    Ctrl h;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(&h, static_cast<unsigned char*>(workspace) + L.ctrl, sizeof(Ctrl),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_status: memcpy", e);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_status: sync", e);
+    if (total_pairs) *total_pairs = (int64_t)h.total_pairs;
+    if (max_count) *max_count = h.max_count;
+    if (total_cells) *total_cells = h.total_cells;
+    if (error_bits) *error_bits = h.error;
+    if (unwrapped) *unwrapped = h.unwrapped;
+    return 0;
+}
+
+int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                  double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
+                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, void* stream) {
+    if (!workspace || !neighbor_ptr || n_atoms <= 0) return fail(-1, "nvnl_fill_coo: bad arguments");
+    if (num_pairs < 0 || num_pairs > 2147483647LL) return fail(-1, "nvnl_fill_coo: num_pairs outside int32 range");
+    if (num_pairs == 0) return 0;
+    if (!edge_index || !shifts) return fail(-1, "nvnl_fill_coo: null output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32) {
+        SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
+        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+        a.index_offset = index_offset; a.queue = 1;
+        return launch_sweep<float, MODE_FILL_COO>(a, half_fill, fma, st);
+    }
+    if (dtype == NVNL_F64) {
+        SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
+        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+        a.index_offset = index_offset; a.queue = 1;
+        return launch_sweep<double, MODE_FILL_COO>(a, half_fill, fma, st);
+    }
+    return fail(-1, "nvnl_fill_coo: unsupported dtype");
+}
+
+int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                     double cutoff_sq, int half_fill, int fma, int32_t* neighbor_matrix, int32_t* neighbor_matrix_shifts,
+                     int32_t* num_neighbors, int32_t max_neighbors, int32_t fill_value, void* stream) {
+    if (!workspace || !num_neighbors || n_atoms <= 0 || max_neighbors < 0)
+        return fail(-1, "nvnl_fill_matrix: bad arguments");
+    if (max_neighbors > 0 && (!neighbor_matrix || !neighbor_matrix_shifts))
+        return fail(-1, "nvnl_fill_matrix: null output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32) {
+        SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
+        a.neighbor_matrix = neighbor_matrix; a.out_shifts = neighbor_matrix_shifts; a.num_neighbors = num_neighbors;
+        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2;
+        return launch_sweep<float, MODE_FILL_MATRIX>(a, half_fill, fma, st);
+    }
+    if (dtype == NVNL_F64) {
+        SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
+        a.neighbor_matrix = neighbor_matrix; a.out_shifts = neighbor_matrix_shifts; a.num_neighbors = num_neighbors;
+        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2;
+        return launch_sweep<double, MODE_FILL_MATRIX>(a, half_fill, fma, st);
+    }
+    return fail(-1, "nvnl_fill_matrix: unsupported dtype");
+}
+
+int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int32_t* cells_per_dimension,
+                  int32_t* neighbor_search_radius, void* stream) {
+    if (!workspace || n_systems <= 0) return fail(-1, "nvnl_get_grid: bad arguments");
+    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    k_get_grid<<<(n_systems + 127) / 128, 128, 0, st>>>(static_cast<const unsigned char*>(workspace), L, n_systems,
+                                                       cells_per_dimension, neighbor_search_radius);
+    NVNL_CHECK_LAUNCH("k_get_grid");
+    return 0;
+}
+
+int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, const int64_t* counts_host,
+                         int32_t* edge_index, int64_t total_pairs, int32_t* shifts, void* stream) {
+    if (n_ranks <= 0 || n_ranks > 64) return fail(-1, "nvnl_unpack_gathered: n_ranks must be in [1, 64]");
+    if (!counts_host) return fail(-1, "nvnl_unpack_gathered: null counts");
+    RankOffsets ro;
+    ro.off[0] = 0;
+    for (int g = 0; g < n_ranks; ++g) {
+        if (counts_host[g] < 0 || counts_host[g] > stride_pairs) return fail(-1, "nvnl_unpack_gathered: bad count");
+        ro.off[g + 1] = ro.off[g] + counts_host[g];
+    }
+    if (ro.off[n_ranks] != total_pairs) return fail(-1, "nvnl_unpack_gathered: counts do not sum to total_pairs");
+    if (total_pairs == 0) return 0;
+    if (!recv || !edge_index || !shifts) return fail(-1, "nvnl_unpack_gathered: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long blocks = (total_pairs + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_unpack_gathered<<<(unsigned)blocks, 256, 0, st>>>(recv, n_ranks, stride_pairs, ro, edge_index, total_pairs, shifts);
+    NVNL_CHECK_LAUNCH("k_unpack_gathered");
+    return 0;
+}
+
+}  // extern "C"

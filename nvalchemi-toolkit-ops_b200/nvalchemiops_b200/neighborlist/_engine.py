@@ -1,0 +1,202 @@
+"""Thin driver of the C ABI: tensor checks, workspace, stream, and the two output paths.
+
+This is the only module that touches ``libnvalchemi_nl_b200.so``.  There is no other
+implementation behind it: CPU tensors are rejected, a missing library is an ImportError.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib, config
+from .neighbor_utils import NeighborOverflowError
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+ERR_MESSAGES = {
+    1: "an atom lies more than 1e6 periodic images from the cell, or the search radius exceeds 63 cells",
+    2: "batch_idx contains a system index outside [0, num_systems)",
+    4: "a cell matrix is singular",
+}
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    if dtype not in _DTYPES:
+        # same error class/message family as nvalchemiops/types.py:29
+        raise ValueError(f"Unsupported dtype: {dtype}")
+    return _DTYPES[dtype]
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"nvalchemiops_b200: `{name}` is on {t.device}; this package runs on CUDA (sm_100a) only "
+            "and has no CPU fallback."
+        )
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def cutoff_sq_in_dtype(cutoff: float, dtype: torch.dtype, python_double: bool = False) -> float:
+    """rc^2 as the reference kernels see it: squared in the kernel precision (cell_list.py:444), or squared
+    in Python double and then cast (naive.py:290) when ``python_double``."""
+    if dtype == torch.float32:
+        if python_double:
+            return float(np.float32(cutoff * cutoff))
+        c = np.float32(cutoff)
+        return float(np.float32(c * c))
+    return float(cutoff) * float(cutoff)
+
+
+class CellListHandle:
+    """Result of ``build``: the opaque device workspace plus what the queries need."""
+
+    __slots__ = ("ws", "dtype_code", "n", "ns", "batch_idx", "dtype", "device", "cutoff")
+
+    def __init__(self, ws, dtype_code, n, ns, batch_idx, dtype, device, cutoff):
+        self.ws, self.dtype_code, self.n, self.ns = ws, dtype_code, n, ns
+        self.batch_idx, self.dtype, self.device, self.cutoff = batch_idx, dtype, device, cutoff
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def build(positions, cutoff, cell, pbc, batch_idx=None, batch_ptr=None, workspace=None) -> CellListHandle:
+    """Grid + hash + counting sort (nvnl_build).  ``cell`` [S,3,3], ``pbc`` [S,3] bool."""
+    _require_cuda(positions, "positions")
+    code = _dtype_code(positions.dtype)
+    if positions.ndim != 2 or positions.shape[1] != 3:
+        raise ValueError("positions must have shape (total_atoms, 3)")
+    n = positions.shape[0]
+    dev = positions.device
+    positions = positions.contiguous()
+    cell = cell.to(device=dev, dtype=positions.dtype).reshape(-1, 3, 3).contiguous()
+    ns = cell.shape[0]
+    pbc_u8 = pbc.to(device=dev).reshape(-1, 3).to(torch.uint8).contiguous()
+    if pbc_u8.shape[0] != ns:
+        raise ValueError(f"pbc has {pbc_u8.shape[0]} systems but cell has {ns}")
+    if batch_idx is not None:
+        batch_idx = batch_idx.to(device=dev, dtype=torch.int32).contiguous()
+        if batch_idx.shape[0] != n:
+            raise ValueError("batch_idx must have one entry per atom")
+    elif ns > 1:
+        raise ValueError("batch_idx is required when more than one cell is given")
+    if batch_ptr is not None:
+        batch_ptr = batch_ptr.to(device=dev, dtype=torch.int32).contiguous()
+        if batch_ptr.shape[0] != ns + 1:
+            raise ValueError("batch_ptr must have num_systems + 1 entries")
+    L = _lib.lib()
+    nbytes = int(L.nvnl_workspace_bytes(n, ns, code))
+    if workspace is None or workspace.numel() < nbytes or workspace.device != dev:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            L.nvnl_build(_ptr(positions), code, n, _ptr(cell), _ptr(pbc_u8), _ptr(batch_idx), _ptr(batch_ptr), ns,
+                         float(cutoff), _ptr(workspace), workspace.numel(), _stream(dev)),
+            "nvnl_build",
+        )
+    # keep the inputs alive until the stream has consumed them
+    workspace._nvnl_keepalive = (positions, cell, pbc_u8, batch_idx, batch_ptr)
+    return CellListHandle(workspace, code, n, ns, batch_idx, positions.dtype, dev, float(cutoff))
+
+
+def _raise_on_error_bits(bits: int):
+    if bits:
+        msgs = [m for b, m in ERR_MESSAGES.items() if bits & b]
+        raise ValueError("nvalchemiops_b200: invalid input: " + "; ".join(msgs))
+
+
+def status(h: CellListHandle):
+    """(total_pairs, max_count, total_cells, error_bits, unwrapped) — synchronizes the stream."""
+    L = _lib.lib()
+    tp, mc, tc, eb, uw = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_status(_ptr(h.ws), h.dtype_code, h.n, h.ns, ctypes.byref(tp), ctypes.byref(mc), ctypes.byref(tc),
+                          ctypes.byref(eb), ctypes.byref(uw), _stream(h.device)),
+            "nvnl_status",
+        )
+    return tp.value, mc.value, tc.value, eb.value, uw.value
+
+
+def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, fill_value,
+                 half_fill=False):
+    """Fill the three padded outputs in place (nvnl_fill_matrix): no host sync, graph-capturable."""
+    for t, nm in ((neighbor_matrix, "neighbor_matrix"), (neighbor_matrix_shifts, "neighbor_matrix_shifts"),
+                  (num_neighbors, "num_neighbors")):
+        _require_cuda(t, nm)
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError(f"{nm} must be a contiguous int32 tensor")
+    M = neighbor_matrix.shape[1]
+    if neighbor_matrix.shape[0] != h.n or neighbor_matrix_shifts.shape[:2] != (h.n, M) or num_neighbors.shape[0] != h.n:
+        raise ValueError("output tensors do not match (total_atoms, max_neighbors)")
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_fill_matrix(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
+                               int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_matrix),
+                               _ptr(neighbor_matrix_shifts), _ptr(num_neighbors), M, int(fill_value),
+                               _stream(h.device)),
+            "nvnl_fill_matrix",
+        )
+
+
+def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True):
+    """num_neighbors [N] and (optionally) neighbor_ptr [N+1] (nvnl_count); asynchronous."""
+    num = torch.empty(h.n, dtype=torch.int32, device=h.device)
+    ptr = torch.empty(h.n + 1, dtype=torch.int32, device=h.device) if want_ptr else None
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_count(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq), int(bool(half_fill)),
+                         int(bool(config.fma)), _ptr(num), _ptr(ptr), _stream(h.device)),
+            "nvnl_count",
+        )
+    return num, ptr
+
+
+def fill_coo(h: CellListHandle, cutoff_sq, neighbor_ptr, edge_index, shifts, num_pairs, half_fill=False,
+             index_offset=0):
+    """Write COO rows at neighbor_ptr (nvnl_fill_coo).  ``edge_index`` is [2, num_pairs] (or a block laid out
+    as such with row stride ``num_pairs``), ``shifts`` [num_pairs, 3]."""
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_fill_coo(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
+                            int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_ptr), _ptr(edge_index),
+                            int(num_pairs), _ptr(shifts), int(index_offset), _stream(h.device)),
+            "nvnl_fill_coo",
+        )
+
+
+def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None):
+    """COO outputs ``(neighbor_list [2,P], neighbor_ptr [N+1], shifts [P,3])``: count -> scan -> one sync for the
+    size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
+    ``max_neighbors`` (neighbor_utils.py:352-359)."""
+    num, ptr = count(h, cutoff_sq, half_fill)
+    total, max_count, _cells, err, _uw = status(h)
+    _raise_on_error_bits(err)
+    if max_neighbors is not None and max_count > max_neighbors:
+        raise NeighborOverflowError(max_neighbors, max_count)
+    if total > 2**31 - 1:
+        raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
+    edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
+    shifts = torch.empty((total, 3), dtype=torch.int32, device=h.device)
+    if total > 0:
+        fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill)
+    return edge_index, ptr, shifts, num
+
+
+def get_grid(h: CellListHandle):
+    cpd = torch.empty((h.ns, 3), dtype=torch.int32, device=h.device)
+    rad = torch.empty((h.ns, 3), dtype=torch.int32, device=h.device)
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(L.nvnl_get_grid(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(cpd), _ptr(rad), _stream(h.device)),
+                   "nvnl_get_grid")
+    return cpd, rad

@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+
+Bar: neighbor sets bit-exact after sorting (i, j, sx, sy, sz) records — integer outputs, so no tolerance.
+Modelled on the reference's own tests (test/neighborlist/test_cell_list.py, test_batch_cell_list.py,
+test_neighborlist.py); the oracle plays the role the optional `vesin` comparison plays there.
+"""
+import numpy as np
+import pytest
+import torch
+
+import reference_oracle as ro
+from systems import (bench_batch, bench_box, kat_structure, load_kat, random_system, triclinic_system)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _nl():
+    from nvalchemiops_b200 import neighborlist
+
+    return neighborlist
+
+
+def _records_gpu_matrix(nm, num, sh):
+    return ro.records_from_matrix(nm.cpu(), num.cpu(), sh.cpu())
+
+
+def _check_matrix_padding(nm, num, sh, fill_value):
+    nm, num, sh = nm.cpu(), num.cpu(), sh.cpu()
+    M = nm.shape[1]
+    cols = torch.arange(M)[None, :]
+    pad = cols >= num.clamp(max=M)[:, None]
+    assert (nm[pad] == fill_value).all(), "padding must be fill_value"
+    assert (sh[pad] == 0).all(), "padding shifts must be zero"
+
+
+# ----------------------------------------------------------------------------------------------
+# known-answer tests of the reference (test_cell_list.py:391-419, test_batch_cell_list.py:516-542)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["HoTlPd", "SiCu"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_known_answer_counts(name, dtype):
+    pos, cell, pbc, expected = kat_structure(name, dtype, DEV)
+    for k, rc in enumerate(load_kat()["cutoffs"]):
+        nm, num, sh = _nl().cell_list(positions=pos, cutoff=rc, pbc=pbc, cell=cell)
+        assert num.cpu().tolist() == expected[k]
+        assert nm.dtype == torch.int32 and num.dtype == torch.int32 and sh.dtype == torch.int32
+        assert nm.device == pos.device
+        o = ro.cell_list(pos, rc, cell, pbc)
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), ro.records_from_matrix(*o))
+        nl, ptr, s = _nl().cell_list(pos, rc, cell, pbc, return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(nl.cpu(), s.cpu()), ro.records_from_matrix(*o))
+        assert ptr.cpu().tolist() == [0] + np.cumsum(expected[k]).tolist()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_known_answer_counts_batched(dtype):
+    p1, c1, b1, e1 = kat_structure("HoTlPd", dtype, DEV)
+    p2, c2, b2, e2 = kat_structure("SiCu", dtype, DEV)
+    pos = torch.cat([p1, p2])
+    cell = torch.stack([c1, c2])
+    pbc = torch.stack([b1, b2])
+    bidx = torch.tensor([0] * len(p1) + [1] * len(p2), dtype=torch.int32, device=DEV)
+    for k, rc in enumerate(load_kat()["cutoffs"]):
+        nm, num, sh = _nl().batch_cell_list(pos, rc, cell, pbc, bidx)
+        assert num.cpu().tolist() == e1[k] + e2[k]
+        o = ro.batch_cell_list(pos, rc, cell, pbc, bidx)
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), ro.records_from_matrix(*o))
+
+
+# ----------------------------------------------------------------------------------------------
+# full (i, j, shift) set parity on random systems — the sweep of test_cell_list.py:316-389
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pbc_flag", [[True, True, True], [True, False, True], [False, False, True],
+                                      [False, False, False]])
+@pytest.mark.parametrize("num_atoms", [10, 20, 50, 100])
+@pytest.mark.parametrize("cutoff", [1.0, 3.0, 5.0])
+@pytest.mark.parametrize("kind", ["cubic", "triclinic"])
+def test_set_parity_small_systems(pbc_flag, num_atoms, cutoff, kind):
+    for dtype in (torch.float32, torch.float64):
+        if kind == "cubic":
+            pos, cell, pbc = random_system(num_atoms, 3.0, dtype, seed=42, pbc_flag=pbc_flag)
+        else:
+            scale = (1 / 720.88) ** (1 / 3) * 3.0
+            pos, cell, pbc = triclinic_system(num_atoms, 8.57 * scale, 12.9645 * scale, 7.2203 * scale, 90.74, 115.944,
+                                              87.663, dtype, seed=42, pbc_flag=pbc_flag)
+        o = ro.cell_list(pos, cutoff, cell, pbc, max_neighbors=8192)
+        assert o[1].max() <= 8192
+        want = ro.records_from_matrix(*o)
+        nl, ptr, s = _nl().cell_list(pos.to(DEV), cutoff, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+        got = ro.records_from_coo(nl.cpu(), s.cpu())
+        assert np.array_equal(got, want), f"{kind} {dtype} n={num_atoms} rc={cutoff} pbc={pbc_flag}"
+        src = nl[0].cpu().numpy()
+        assert (np.diff(src) >= 0).all(), "COO source atoms must be sorted"
+        assert np.array_equal(np.bincount(src, minlength=num_atoms), np.diff(ptr.cpu().numpy()))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_set_parity_random_geometry(seed):
+    """Random box sizes / cutoffs / mixed PBC / unwrapped atoms, both fma modes."""
+    from nvalchemiops_b200 import config
+
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(30, 400))
+    L = float(rng.uniform(3.0, 14.0))
+    rc = float(rng.uniform(1.0, 5.5))
+    pbc_flag = [bool(x) for x in rng.integers(0, 2, 3)]
+    dtype = torch.float32 if seed % 2 == 0 else torch.float64
+    if seed % 3 == 0:
+        pos, cell, pbc = triclinic_system(n, L, 1.3 * L, 0.8 * L, 70.0, 105.0, 60.0, dtype, seed=seed, pbc_flag=pbc_flag,
+                                          spread=(-1.4, 2.3))
+    else:
+        pos, cell, pbc = random_system(n, L, dtype, seed=seed, pbc_flag=pbc_flag)
+        if seed % 3 == 1:
+            pos = pos * 3.0 - L  # atoms up to one box outside on either side
+    try:
+        for fma in (True, False):
+            config.fma = fma
+            o = ro.cell_list(pos, rc, cell, pbc, max_neighbors=16384, fma_mode=int(fma))
+            assert o[1].max() <= 16384
+            want = ro.records_from_matrix(*o)
+            nl, ptr, s = _nl().cell_list(pos.to(DEV), rc, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+            assert np.array_equal(ro.records_from_coo(nl.cpu(), s.cpu()), want), f"seed {seed} fma {fma}"
+    finally:
+        config.fma = True
+
+
+def test_matrix_output_padding_overflow_and_buffers():
+    pos, cell, pbc = random_system(300, 9.0, torch.float32, seed=7)
+    pos, cell, pbc = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    nl = _nl()
+    nm, num, sh = nl.cell_list(pos, 3.0, cell, pbc, max_neighbors=96)
+    assert nm.shape == (300, 96) and sh.shape == (300, 96, 3) and num.shape == (300,)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 3.0, cell, pbc, max_neighbors=96))
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 300)
+    # explicit fill value
+    nm2, num2, sh2 = nl.cell_list(pos, 3.0, cell, pbc, max_neighbors=96, fill_value=-1)
+    _check_matrix_padding(nm2, num2, sh2, -1)
+    # pre-allocated outputs are reused in place (test_neighborlist.py:817-855)
+    bm = torch.full((300, 96), 12345, dtype=torch.int32, device=DEV)
+    bs = torch.full((300, 96, 3), 7, dtype=torch.int32, device=DEV)
+    bn = torch.full((300,), 9, dtype=torch.int32, device=DEV)
+    r = nl.cell_list(pos, 3.0, cell, pbc, neighbor_matrix=bm, neighbor_matrix_shifts=bs, num_neighbors=bn)
+    assert r[0] is bm and r[1] is bn and r[2] is bs
+    assert torch.equal(bm, nm) or np.array_equal(_records_gpu_matrix(bm, bn, bs), want)
+    _check_matrix_padding(bm, bn, bs, 300)
+    # overflow: counts keep counting, stored entries are a subset of the true row (neighbor_utils.py:139-147)
+    nm3, num3, sh3 = nl.cell_list(pos, 3.0, cell, pbc, max_neighbors=8)
+    assert torch.equal(num3, num)
+    assert num3.max().item() > 8
+    got = ro.records_from_matrix(nm3.cpu(), num3.cpu(), sh3.cpu())
+    want_set = {tuple(r) for r in want.tolist()}
+    assert all(tuple(r) in want_set for r in got.tolist())
+    assert got.shape[0] == int(num3.clamp(max=8).sum())
+    with pytest.raises(nl.NeighborOverflowError):
+        nl.cell_list(pos, 3.0, cell, pbc, max_neighbors=8, return_neighbor_list=True)
+
+
+def test_half_fill_canonical_set():
+    pos, cell, pbc = random_system(200, 5.0, torch.float32, seed=11)  # box < 2 rc: multi-image, self images
+    full = ro.records_from_matrix(*ro.cell_list(pos, 3.5, cell, pbc, max_neighbors=4096))
+    nl, ptr, s = _nl().cell_list(pos.to(DEV), 3.5, cell.to(DEV), pbc.to(DEV), half_fill=True,
+                                 return_neighbor_list=True)
+    half = ro.records_from_coo(nl.cpu(), s.cpu())
+    assert 2 * half.shape[0] == full.shape[0]
+    assert np.array_equal(ro.canonical_undirected(half), np.unique(ro.canonical_undirected(full), axis=0))
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 3.5, cell.to(DEV), pbc.to(DEV), half_fill=True, max_neighbors=2048)
+    assert np.array_equal(ro.canonical_undirected(_records_gpu_matrix(nm, num, sh)), ro.canonical_undirected(half))
+
+
+def test_no_pbc_shifts_zero_and_mixed_pbc_components():
+    pos, cell, pbc = random_system(150, 8.0, torch.float32, seed=3, pbc_flag=[False, False, False])
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 4.0, cell.to(DEV), pbc.to(DEV))
+    assert (sh == 0).all()
+    pos, cell, pbc = random_system(150, 4.0, torch.float32, seed=3, pbc_flag=[True, True, False])
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 4.5, cell.to(DEV), pbc.to(DEV))
+    assert (sh[..., 2] == 0).all() and (sh[..., 0] != 0).any()
+
+
+def test_empty_and_zero_cutoff_shapes():
+    nl = _nl()
+    cell = torch.eye(3, device=DEV).reshape(1, 3, 3)
+    pbc = torch.tensor([True, True, True], device=DEV)
+    pos = torch.rand(10, 3, device=DEV)
+    nm, num, sh = nl.cell_list(pos, 0.0, cell, pbc)
+    assert nm.shape == (10, 0) and num.shape == (10,) and sh.shape == (10, 0, 3)
+    e, p, s = nl.cell_list(pos, 0.0, cell, pbc, return_neighbor_list=True)
+    assert e.shape == (2, 0) and p.shape == (11,) and s.shape == (0, 3)
+    empty = torch.zeros((0, 3), device=DEV)
+    nm, num, sh = nl.cell_list(empty, 1.0, cell, pbc)
+    assert nm.shape == (0, 0) and num.shape == (0,) and sh.shape == (0, 0, 3)
+    e, p, s = nl.cell_list(empty, 1.0, cell, pbc, return_neighbor_list=True)
+    assert e.shape == (2, 0) and p.shape == (1,) and s.shape == (0, 3)
+    one = torch.zeros((1, 3), device=DEV)
+    nm, num, sh = nl.cell_list(one, 0.5, cell, pbc)
+    assert num.tolist() == [0]
+    nm, num, sh = nl.cell_list(one, 1.5, cell, pbc)  # self images
+    assert num.tolist() == [6]
+
+
+# ----------------------------------------------------------------------------------------------
+# batches (BASELINE config 3 shape) and the dispatcher
+# ----------------------------------------------------------------------------------------------
+def test_batch_mixed_pbc_parity_and_no_cross_system_pairs():
+    pos, cell, pbc, bidx, bptr = bench_batch(24, 150, 250, seed=3, mixed_pbc=True)
+    want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1024))
+    nl = _nl()
+    e, p, s = nl.batch_cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), bidx.to(DEV), return_neighbor_list=True)
+    got = ro.records_from_coo(e.cpu(), s.cpu())
+    assert np.array_equal(got, want)
+    b = bidx.numpy()
+    assert (b[got[:, 0]] == b[got[:, 1]]).all()
+    # through the dispatcher with batch_ptr only, and with shuffled (non-contiguous) batch_idx
+    e2, p2, s2 = nl.neighbor_list(pos.to(DEV), 6.0, cell=cell.to(DEV), pbc=pbc.to(DEV), batch_ptr=bptr.to(DEV),
+                                  return_neighbor_list=True, method=None if pos.shape[0] >= 5000 else "batch_cell_list",
+                                  batch_idx=bidx.to(DEV))
+    assert np.array_equal(ro.records_from_coo(e2.cpu(), s2.cpu()), want)
+    perm = torch.randperm(pos.shape[0], generator=torch.Generator().manual_seed(0))
+    e3, p3, s3 = nl.batch_cell_list(pos[perm].to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), bidx[perm].to(DEV),
+                                    return_neighbor_list=True)
+    inv = perm.numpy()
+    got3 = ro.records_from_coo(e3.cpu(), s3.cpu())
+    got3[:, 0] = inv[got3[:, 0]]
+    got3[:, 1] = inv[got3[:, 1]]
+    assert np.array_equal(ro.sort_records(got3), want)
+
+
+def test_dispatcher_naive_route_and_auto_selection():
+    """BASELINE config 1 (256 atoms, no cell/pbc -> 2-tuple) and auto cell_list without a cell (>= 5000 atoms,
+    test_neighborlist.py:91-114)."""
+    nl = _nl()
+    pos = random_system(256, 13.68, torch.float32, seed=1)[0]
+    out = nl.neighbor_list(pos.to(DEV), 6.0)
+    assert len(out) == 2
+    nm, num = out
+    o = ro.neighbor_list(pos, 6.0)
+    assert np.array_equal(ro.records_from_matrix(nm.cpu(), num.cpu()), ro.records_from_matrix(*o))
+    e, p = nl.neighbor_list(pos.to(DEV), 6.0, return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(e.cpu()), ro.records_from_matrix(*o))
+    big = random_system(6000, 40.0, torch.float32, seed=2)[0]
+    out = nl.neighbor_list(big.to(DEV), 3.0, max_neighbors=64)
+    assert len(out) == 3
+    o = ro.neighbor_list(big, 3.0, max_neighbors=64)
+    assert np.array_equal(_records_gpu_matrix(*out[:1], out[1], out[2]), ro.records_from_matrix(*o))
+    with pytest.raises(TypeError):
+        nl.neighbor_list(big.to(DEV), 3.0, not_a_kwarg=1)
+    with pytest.raises(ValueError):
+        nl.neighbor_list(big.to(DEV), 3.0, method="nope")
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs at (near) full size
+# ----------------------------------------------------------------------------------------------
+def test_config2_50k_matrix_parity():
+    pos, cell, pbc = bench_box(50_000, seed=2)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=160, nthreads=8))
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=160)
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 50_000)
+    # default max_neighbors = 1584: same set, 1.27 GB of mostly padding written once
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV))
+    assert nm.shape[1] == 1584
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+
+
+def _keys(i, j, s, n):
+    """Total-order key of a directed pair record for |s_d| <= 3."""
+    code = ((s[:, 0] + 3) * 7 + (s[:, 1] + 3)) * 7 + (s[:, 2] + 3)
+    return (i.to(torch.int64) * n + j.to(torch.int64)) * 343 + code.to(torch.int64)
+
+
+def test_config4_1m_atoms_properties_and_full_parity():
+    """1 M atoms, rc = 6, periodic: size-independent properties on the full output, then full-set parity with
+    the oracle run on the reference algorithm with max_nbins raised (same neighbor set, tractable on CPU)."""
+    n = 1_000_000
+    pos, cell, pbc = bench_box(n, seed=4)
+    e, ptr, s = _nl().neighbor_list(pos.to(DEV), 6.0, cell=cell.to(DEV), pbc=pbc.to(DEV), return_neighbor_list=True)
+    P = e.shape[1]
+    assert ptr[-1].item() == P and ptr[0].item() == 0
+    assert (ptr[1:] >= ptr[:-1]).all()
+    assert (e[0, 1:] >= e[0, :-1]).all(), "source atoms sorted"
+    counts = torch.bincount(e[0].long(), minlength=n)
+    assert torch.equal(counts.to(torch.int32), ptr[1:] - ptr[:-1])
+    assert s.abs().max().item() <= 1
+    # symmetry: {(i,j,s)} == {(j,i,-s)}
+    k_fwd = torch.sort(_keys(e[0], e[1], s, n)).values
+    k_rev = torch.sort(_keys(e[1], e[0], -s, n)).values
+    assert torch.equal(k_fwd, k_rev)
+    assert (k_fwd[1:] != k_fwd[:-1]).all(), "no duplicate records"
+    # geometry: every stored pair is inside the cutoff (fp64 re-evaluation, 1e-5 slack like the reference tests)
+    p64 = pos.to(DEV).double()
+    L = cell[0, 0, 0].double().item()
+    d = p64[e[1].long()] - p64[e[0].long()] + s.double() * L
+    assert (d.pow(2).sum(1).sqrt() < 6.0 + 1e-5).all()
+    del d, p64, k_rev
+    # expected density: 90.5 neighbors per atom
+    assert abs(P / n - 90.48) < 0.2
+    # full-set parity
+    nm, num, sh = ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=160, nthreads=8, max_nbins=1 << 20)
+    assert num.max() <= 160
+    assert np.array_equal(num, (ptr[1:] - ptr[:-1]).cpu().numpy())
+    mask = np.arange(160)[None, :] < num[:, None]
+    oi = torch.from_numpy(np.nonzero(mask)[0]).to(DEV)
+    oj = torch.from_numpy(nm[mask]).to(DEV)
+    os_ = torch.from_numpy(sh[mask]).to(DEV)
+    k_or = torch.sort(_keys(oi, oj, os_, n)).values
+    assert torch.equal(k_fwd, k_or)
+
+
+def test_large_cells_multi_tile_path():
+    """Few huge cells (cutoff ~ box/2): candidates exceed one shared-memory tile, rows exceed the staging row."""
+    pos, cell, pbc = random_system(3000, 12.0, torch.float32, seed=9)
+    for fl, mode in (([True, True, True], "pbc"), ([False, False, False], "open")):
+        pbc = torch.tensor(fl).reshape(1, 3)
+        o = ro.cell_list(pos, 5.5, cell, pbc, max_neighbors=4096, nthreads=8)
+        assert o[1].max() <= 4096
+        want = ro.records_from_matrix(*o)
+        e, p, s = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), mode
+        nm, num, sh = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), max_neighbors=2048)
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), mode
+        _check_matrix_padding(nm, num, sh, 3000)

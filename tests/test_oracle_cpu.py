@@ -1,0 +1,170 @@
+"""CPU tests (no GPU): the oracle against the reference's golden vectors and an independent brute force,
+the reference-side host helpers, and the C-ABI library surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import reference_oracle as ro
+from systems import kat_structure, load_kat, random_system, triclinic_system
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["HoTlPd", "SiCu"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("fma", [0, 1])
+def test_oracle_reproduces_reference_known_answers(name, dtype, fma):
+    """test/neighborlist/test_cell_list.py:391-419 — per-atom counts at rc = 1, 4, 6."""
+    pos, cell, pbc, expected = kat_structure(name, dtype)
+    for k, rc in enumerate(load_kat()["cutoffs"]):
+        _, num, _ = ro.cell_list(pos, rc, cell, pbc, fma_mode=fma)
+        assert num.tolist() == expected[k]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_oracle_batch_known_answers(dtype):
+    """test/neighborlist/test_batch_cell_list.py:516-542 — both structures in one batch."""
+    p1, c1, b1, e1 = kat_structure("HoTlPd", dtype)
+    p2, c2, b2, e2 = kat_structure("SiCu", dtype)
+    pos = torch.cat([p1, p2])
+    cell = torch.stack([c1, c2])
+    pbc = torch.stack([b1, b2])
+    bidx = torch.tensor([0] * len(p1) + [1] * len(p2), dtype=torch.int32)
+    for k, rc in enumerate(load_kat()["cutoffs"]):
+        _, num, _ = ro.batch_cell_list(pos, rc, cell, pbc, bidx)
+        assert num.tolist() == e1[k] + e2[k]
+
+
+def test_oracle_matches_independent_brute_force():
+    """Random small systems, mixed PBC, cubic and triclinic, partly unwrapped — restatement == brute force."""
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(5, 60))
+        L = float(rng.uniform(2.0, 9.0))
+        rc = float(rng.uniform(0.8, 5.0))
+        pbc = [bool(x) for x in rng.integers(0, 2, 3)]
+        dtype = torch.float32 if trial % 2 == 0 else torch.float64
+        if trial % 3 == 0:
+            pos, cell, pb = triclinic_system(n, L, L * 1.2, L * 0.9, 75.0, 100.0, 65.0, dtype, seed=trial, pbc_flag=pbc,
+                                             spread=(-0.3, 1.3))
+        else:
+            pos, cell, pb = random_system(n, L, dtype, seed=trial, pbc_flag=pbc)
+            if trial % 3 == 1:
+                pos = pos * 1.6 - 0.3 * L  # unwrapped
+        for fma in (0, 1):
+            nm, num, sh = ro.cell_list(pos, rc, cell, pb, max_neighbors=4096, fma_mode=fma)
+            assert num.max() <= 4096
+            rec = ro.records_from_matrix(nm, num, sh)
+            bf = ro.brute_force(pos, rc, cell, pb, fma_mode=fma)
+            assert np.array_equal(rec, bf), f"trial {trial} fma {fma}"
+
+
+def test_oracle_half_fill_is_half_of_full():
+    pos, cell, pbc = random_system(40, 6.0, torch.float32, seed=5)
+    nm, num, sh = ro.cell_list(pos, 3.0, cell, pbc)
+    nmh, numh, shh = ro.cell_list(pos, 3.0, cell, pbc, half_fill=True)
+    full = ro.canonical_undirected(ro.records_from_matrix(nm, num, sh))
+    half = ro.canonical_undirected(ro.records_from_matrix(nmh, numh, shh))
+    assert num.sum() == 2 * numh.sum()
+    assert np.array_equal(np.unique(full, axis=0), half)
+
+
+def test_oracle_naive_no_pbc_equals_cell_list():
+    """BASELINE config 1 plumbing: naive (2-tuple) == cell-list set without PBC."""
+    pos = random_system(256, 13.68, torch.float32, seed=1)[0]
+    nm, num = ro.neighbor_list(pos, 6.0)
+    cell = torch.eye(3).reshape(1, 3, 3)
+    nm2, num2, sh2 = ro.cell_list(pos, 6.0, cell, torch.tensor([False] * 3))
+    assert np.array_equal(ro.records_from_matrix(nm, num), ro.records_from_matrix(nm2, num2, sh2))
+    assert (sh2 == 0).all()
+
+
+def test_prefix_sum_and_coo_conversion_known_answers():
+    g = load_kat()
+    assert np.concatenate([[0], np.cumsum(g["prefix_sum"]["counts"][:-1])]).tolist() == g["prefix_sum"]["starts"]
+    c = g["coo_conversion"]
+    nm = np.array(c["neighbor_matrix"], dtype=np.int32)
+    num = np.array(c["num_neighbors"], dtype=np.int32)
+    nl, ptr = ro.get_neighbor_list_from_neighbor_matrix(nm, num, fill_value=c["fill_value"])
+    assert nl.shape == (2, c["num_pairs"]) and ptr.tolist() == [0, 2, 4, 6, 6]
+    with pytest.raises(ro.NeighborOverflowError):
+        ro.get_neighbor_list_from_neighbor_matrix(nm, np.array(c["overflow_num_neighbors"], dtype=np.int32),
+                                                  fill_value=c["fill_value"])
+    e = g["estimate_max_neighbors"]
+    assert ro.estimate_max_neighbors(6.0) == e["cutoff_6_default"]
+    assert ro.estimate_max_neighbors(5.0, 0.35, 1.0) == e["cutoff_5_density_035_sf_1"]
+
+
+# ---- host-side mirror of the reference API (pure torch plumbing, runs on CPU) ----
+def test_host_helpers_match_reference_contract():
+    from nvalchemiops_b200.neighborlist import (NeighborOverflowError, estimate_max_neighbors,
+                                                get_neighbor_list_from_neighbor_matrix)
+    from nvalchemiops_b200.neighborlist.neighbor_utils import _prepare_batch_idx_ptr
+
+    g = load_kat()
+    assert estimate_max_neighbors(6.0) == 1584 and estimate_max_neighbors(0.0) == 0
+    c = g["coo_conversion"]
+    nm = torch.tensor(c["neighbor_matrix"], dtype=torch.int32)
+    num = torch.tensor(c["num_neighbors"], dtype=torch.int32)
+    nl, ptr = get_neighbor_list_from_neighbor_matrix(nm, num, fill_value=-1)
+    assert nl.shape == (2, 6) and nl.dtype == torch.int32 and ptr.tolist() == [0, 2, 4, 6, 6]
+    shm = torch.zeros((4, 4, 3), dtype=torch.int32)
+    nl, ptr, sh = get_neighbor_list_from_neighbor_matrix(nm, num, shm, fill_value=-1)
+    assert sh.shape == (6, 3)
+    with pytest.raises(NeighborOverflowError):
+        get_neighbor_list_from_neighbor_matrix(nm, torch.tensor([8, 8, 8, 8], dtype=torch.int32), shm, fill_value=-1)
+    bi, bp = _prepare_batch_idx_ptr(None, torch.tensor([0, 3, 5], dtype=torch.int32), 5, "cpu")
+    assert bi.tolist() == [0, 0, 0, 1, 1]
+    bi, bp = _prepare_batch_idx_ptr(torch.tensor([0, 0, 1, 1, 1], dtype=torch.int32), None, 5, "cpu")
+    assert bp.tolist() == [0, 2, 5]
+    with pytest.raises(ValueError):
+        _prepare_batch_idx_ptr(None, None, 5, "cpu")
+
+
+def test_product_path_has_no_cpu_fallback():
+    from nvalchemiops_b200.neighborlist import batch_cell_list, cell_list, neighbor_list
+
+    pos, cell, pbc = random_system(20, 5.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cell_list(pos, 2.0, cell, pbc)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        neighbor_list(pos, 2.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        batch_cell_list(pos, 2.0, cell, pbc, torch.zeros(20, dtype=torch.int32))
+    with pytest.raises(ValueError, match="Invalid method"):
+        neighbor_list(pos, 2.0, method="bogus")
+    with pytest.raises(ValueError, match="Unsupported dtype"):
+        cell_list(pos.half(), 2.0, cell.half(), pbc)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/nvalchemi_nl_b200.h <-> libnvalchemi_nl_b200.so <-> the ctypes binding (no compute calls)."""
+    from nvalchemiops_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "nvalchemi_nl_b200.h")).read()
+    declared = set(re.findall(r"\b(nvnl_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.library_path())
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.declared_symbols())
+    lib = _lib.lib()
+    assert lib.nvnl_abi_version() == 1
+    assert lib.nvnl_workspace_bytes(1000, 1, 0) > 1000 * 16
+    assert lib.nvnl_workspace_bytes(1000, 4, 1) > lib.nvnl_workspace_bytes(1000, 4, 0)
+    # argument validation happens before any CUDA call
+    assert lib.nvnl_build(None, 0, 0, None, None, None, None, 1, 1.0, None, 0, None) != 0
+    assert b"positive" in lib.nvnl_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nvalchemi-toolkit-ops_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "reference_oracle" not in src and "nl_oracle" not in src, f
