@@ -3,7 +3,8 @@ import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.pa
 from systems import bench_box
 from nvalchemiops_b200.neighborlist import _engine, neighbor_list
 dev='cuda:0'
-for n in (50_000, 1_000_000):
+sizes = [int(a) for a in sys.argv[1:]] or [50_000, 1_000_000]
+for n in sizes:
     pos, cell, pbc = bench_box(n, seed=4)
     pos, cell, pbc = pos.to(dev), cell.to(dev), pbc.to(dev)
     csq = 36.0

@@ -88,7 +88,8 @@ def test_set_parity_small_systems(pbc_flag, num_atoms, cutoff, kind):
         o = ro.cell_list(pos, cutoff, cell, pbc, max_neighbors=8192)
         assert o[1].max() <= 8192
         want = ro.records_from_matrix(*o)
-        nl, ptr, s = _nl().cell_list(pos.to(DEV), cutoff, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+        nl, ptr, s = _nl().cell_list(pos.to(DEV), cutoff, cell.to(DEV), pbc.to(DEV), max_neighbors=8192,
+                                     return_neighbor_list=True)
         got = ro.records_from_coo(nl.cpu(), s.cpu())
         assert np.array_equal(got, want), f"{kind} {dtype} n={num_atoms} rc={cutoff} pbc={pbc_flag}"
         src = nl[0].cpu().numpy()
@@ -120,7 +121,8 @@ def test_set_parity_random_geometry(seed):
             o = ro.cell_list(pos, rc, cell, pbc, max_neighbors=16384, fma_mode=int(fma))
             assert o[1].max() <= 16384
             want = ro.records_from_matrix(*o)
-            nl, ptr, s = _nl().cell_list(pos.to(DEV), rc, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+            nl, ptr, s = _nl().cell_list(pos.to(DEV), rc, cell.to(DEV), pbc.to(DEV), max_neighbors=16384,
+                                         return_neighbor_list=True)
             assert np.array_equal(ro.records_from_coo(nl.cpu(), s.cpu()), want), f"seed {seed} fma {fma}"
     finally:
         config.fma = True
@@ -161,7 +163,7 @@ def test_matrix_output_padding_overflow_and_buffers():
 def test_half_fill_canonical_set():
     pos, cell, pbc = random_system(200, 5.0, torch.float32, seed=11)  # box < 2 rc: multi-image, self images
     full = ro.records_from_matrix(*ro.cell_list(pos, 3.5, cell, pbc, max_neighbors=4096))
-    nl, ptr, s = _nl().cell_list(pos.to(DEV), 3.5, cell.to(DEV), pbc.to(DEV), half_fill=True,
+    nl, ptr, s = _nl().cell_list(pos.to(DEV), 3.5, cell.to(DEV), pbc.to(DEV), half_fill=True, max_neighbors=4096,
                                  return_neighbor_list=True)
     half = ro.records_from_coo(nl.cpu(), s.cpu())
     assert 2 * half.shape[0] == full.shape[0]
@@ -196,7 +198,9 @@ def test_empty_and_zero_cutoff_shapes():
     one = torch.zeros((1, 3), device=DEV)
     nm, num, sh = nl.cell_list(one, 0.5, cell, pbc)
     assert num.tolist() == [0]
-    nm, num, sh = nl.cell_list(one, 1.5, cell, pbc)  # self images
+    nm, num, sh = nl.cell_list(one, 1.5, cell, pbc)  # self images: 6 at distance 1 + 12 at sqrt(2)
+    assert num.tolist() == [18]
+    nm, num, sh = nl.cell_list(one, 1.2, cell, pbc)
     assert num.tolist() == [6]
 
 
@@ -207,7 +211,7 @@ def test_batch_mixed_pbc_parity_and_no_cross_system_pairs():
     pos, cell, pbc, bidx, bptr = bench_batch(24, 150, 250, seed=3, mixed_pbc=True)
     want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1024))
     nl = _nl()
-    e, p, s = nl.batch_cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), bidx.to(DEV), return_neighbor_list=True)
+    e, p, s = nl.batch_cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), bidx.to(DEV), return_neighbor_list=True)  # default max_neighbors 1584
     got = ro.records_from_coo(e.cpu(), s.cpu())
     assert np.array_equal(got, want)
     b = bidx.numpy()
@@ -317,7 +321,8 @@ def test_large_cells_multi_tile_path():
         o = ro.cell_list(pos, 5.5, cell, pbc, max_neighbors=4096, nthreads=8)
         assert o[1].max() <= 4096
         want = ro.records_from_matrix(*o)
-        e, p, s = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+        e, p, s = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), max_neighbors=4096,
+                                  return_neighbor_list=True)
         assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), mode
         nm, num, sh = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), max_neighbors=2048)
         assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), mode
