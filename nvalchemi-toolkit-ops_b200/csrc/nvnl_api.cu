@@ -4,7 +4,7 @@
 #include <cstring>
 
 #include "../../include/nvalchemi_nl_b200.h"
-#include "nvnl_sweep.cuh"
+#include "nvnl_fast.cuh"
 
 using namespace nvnl;
 
@@ -63,12 +63,44 @@ int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
+template <typename T, int MODE, bool HALF, bool FMA>
+int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
+    auto kern = k_fast<T, MODE, HALF, FMA>;
+    constexpr size_t smem = fast_smem_bytes<T>();
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_fast)", e);
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kFastThreads, smem);
+        if (e != cudaSuccess) return fail(-2, "occupancy(k_fast)", e);
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    long long grid = (long long)sm_count() * blocks_per_sm;
+    const long long max_items = a.L.max_cells;
+    if (grid > max_items) grid = max_items > 0 ? max_items : 1;
+    kern<<<(unsigned)grid, kFastThreads, smem, st>>>(a);
+    NVNL_CHECK_LAUNCH("k_fast");
+    return 0;
+}
+
+// Every query is two launches: the lean kernel takes the cells it can (and lists the rest), the general
+// kernel takes the listed cells — or all of them when atoms lie outside the primary periodic image.
+template <typename T, int MODE, bool HALF, bool FMA>
+int launch_pair(SweepArgs<T> a, cudaStream_t st) {
+    a.queue = MODE;  // fast: queues 0..2
+    int rc = launch_fast_t<T, MODE, HALF, FMA>(a, st);
+    if (rc) return rc;
+    a.queue = 3;     // general
+    return launch_sweep_t<T, MODE, HALF, FMA>(a, st);
+}
+
 template <typename T, int MODE>
 int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st) {
     if (half_fill) {
-        return fma ? launch_sweep_t<T, MODE, true, true>(a, st) : launch_sweep_t<T, MODE, true, false>(a, st);
+        return fma ? launch_pair<T, MODE, true, true>(a, st) : launch_pair<T, MODE, true, false>(a, st);
     }
-    return fma ? launch_sweep_t<T, MODE, false, true>(a, st) : launch_sweep_t<T, MODE, false, false>(a, st);
+    return fma ? launch_pair<T, MODE, false, true>(a, st) : launch_pair<T, MODE, false, false>(a, st);
 }
 
 template <typename T>

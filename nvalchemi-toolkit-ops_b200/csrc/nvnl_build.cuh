@@ -19,7 +19,7 @@ namespace nvnl {
 // ------------------------------------------------------------------------------------------------
 struct WsLayout {
     size_t ctrl, sys, bbox, cell_count, cell_start, atom_cell, atom_rank, atom_ashift, sorted, sorted_ashift,
-        cursor, scan_status0, scan_status1, total;
+        cursor, scan_status0, scan_status1, masks, deferred, total;
     long long max_cells;  // N + S (upper bound on the number of cells, see k_grid)
 };
 
@@ -47,6 +47,8 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     L.cursor = take(sizeof(int) * (size_t)n);
     L.scan_status0 = take(sizeof(unsigned long long) * (size_t)((L.max_cells + 2) / kScanTile + 2));
     L.scan_status1 = take(sizeof(unsigned long long) * (size_t)((n + 1) / kScanTile + 2));
+    L.masks = take(sizeof(unsigned) * 32 * (size_t)n);   // one hit mask per (atom, 32-candidate chunk)
+    L.deferred = take(sizeof(int) * (size_t)(L.max_cells + 2));
     L.total = o;
     return L;
 }
@@ -78,6 +80,7 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
         ctrl->scan_tile[0] = ctrl->scan_tile[1] = 0;
         ctrl->total_pairs = 0ull;
         ctrl->max_count = 0;
+        ctrl->n_deferred = 0;
     }
     int* cell_count = reinterpret_cast<int*>(ws + L.cell_count);
     for (long long i = gid; i < L.max_cells + 2; i += stride) cell_count[i] = 0;

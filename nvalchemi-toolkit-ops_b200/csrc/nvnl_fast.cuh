@@ -1,0 +1,407 @@
+// nvnl_fast.cuh — the lean sweep for the common case (atoms inside the primary image, <= 32 cell
+// images per stencil, <= one shared-memory tile of candidates).  Everything else is appended to a
+// deferred-cell list and handled by the general kernel in nvnl_sweep.cuh.
+//
+// Why a second kernel: ncu on the first implementation (profiles/r1_baseline_*.txt) showed both
+// sweeps issue-bound at 588 / 1351 warp-instructions per atom.  This version
+//   * does all per-cell work (image enumeration, shift sort, segment table, TMA issue) in warp 0 only;
+//   * addresses shared memory with 32-bit shared-space pointers and immediate offsets;
+//   * specialises the inner loop for zero-shift segments (interior cells: 3 FADD + FMUL + 2 FFMA +
+//     FSETP + VOTE per 32 candidates);
+//   * computes every distance ONCE: the count pass stores one 32-bit hit mask per (atom, 32-candidate
+//     chunk) — 128 B per atom — and the COO fill pass only expands masks (popc prefix) into rows.
+//   * the matrix pass fuses mask computation, row write and padding (no global masks).
+#pragma once
+#include "nvnl_sweep.cuh"
+
+namespace nvnl {
+
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastSlackBytes = 1024;  // the tail chunk of the last segment may read past the staged data
+
+enum FastMode { FAST_COUNT = 0, FAST_FILL_COO = 1, FAST_MATRIX = 2 };
+
+template <typename T>
+struct FastSmem {
+    T segS[32 * 3];
+    int seg_begin[33], seg_key[32], seg_cb[33];
+    int chunk_cand[32], chunk_seg[32];
+    int e_st[32], e_cn[32], e_key[32], e_tag[32];
+    unsigned maskbuf[kFastWarps][32];
+    int item, ntarget, home_off, home_start, nseg, total, nchunks;
+    unsigned long long mbar;
+};
+
+template <typename T>
+constexpr size_t fast_smem_bytes() {
+    return (size_t)kCandBytes + kFastSlackBytes + sizeof(FastSmem<T>);
+}
+
+// ---- shared-memory accessors on 32-bit shared-space addresses -----------------------------------
+__device__ __forceinline__ void lds_rec(uint32_t addr, float& x, float& y, float& z, int& j) {
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=r"(j) : "r"(addr));
+}
+__device__ __forceinline__ void lds_rec(uint32_t addr, double& x, double& y, double& z, int& j) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+    asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(z) : "r"(addr));
+    asm volatile("ld.shared.b32 %0, [%1+24];" : "=r"(j) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ int lds_rec_j(uint32_t addr) {
+    int j;
+    if (sizeof(T) == 4)
+        asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(j) : "r"(addr));
+    else
+        asm volatile("ld.shared.b32 %0, [%1+24];" : "=r"(j) : "r"(addr));
+    return j;
+}
+
+// one 32-candidate chunk: returns the hit ballot
+template <typename T, bool HALF, bool FMA, bool SHIFTED, bool TAIL>
+__device__ __forceinline__ unsigned chunk_mask(uint32_t addr, T xi, T yi, T zi, int i, T Sx, T Sy, T Sz, T rc2,
+                                               bool seg_lexpos, bool valid) {
+    using A = Arith<T>;
+    T x, y, z;
+    int j;
+    lds_rec(addr, x, y, z, j);
+    T dx = A::sub(x, xi), dy = A::sub(y, yi), dz = A::sub(z, zi);
+    if (SHIFTED) {
+        dx = A::add(dx, Sx);
+        dy = A::add(dy, Sy);
+        dz = A::add(dz, Sz);
+    }
+    const T d2 = dist2<T, FMA>(dx, dy, dz);
+    bool hit = d2 < rc2;
+    if (TAIL) hit = hit && valid;
+    if (HALF) hit = hit && (i < j || (i == j && seg_lexpos));
+    return __ballot_sync(0xffffffffu, hit);
+}
+
+// Phase 1: hit masks of one target atom against the staged stencil; chunk ck's ballot -> mb[ck].
+template <typename T, bool HALF, bool FMA>
+__device__ __forceinline__ void fast_masks(const FastSmem<T>& sm, uint32_t cand_addr, T xi, T yi, T zi, int i, T rc2,
+                                           int lane, unsigned* __restrict__ mb) {
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    const int nseg = sm.nseg;
+    const bool l0 = lane == 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int b = sm.seg_begin[sg], e = sm.seg_begin[sg + 1];
+        const int key = sm.seg_key[sg];
+        int ck = sm.seg_cb[sg];
+        uint32_t addr = cand_addr + (uint32_t)(b + lane) * RS;
+        const int nfull = (e - b) >> 5, rem = (e - b) & 31;
+        if (key == 0) {
+            int k = 0;
+#pragma unroll 1
+            for (; k + 4 <= nfull; k += 4) {
+                const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+                const unsigned m1 = chunk_mask<T, HALF, FMA, false, false>(addr + 32 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+                const unsigned m2 = chunk_mask<T, HALF, FMA, false, false>(addr + 64 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+                const unsigned m3 = chunk_mask<T, HALF, FMA, false, false>(addr + 96 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+                if (l0) { mb[ck] = m0; mb[ck + 1] = m1; mb[ck + 2] = m2; mb[ck + 3] = m3; }
+                ck += 4;
+                addr += 128 * RS;
+            }
+#pragma unroll 1
+            for (; k < nfull; ++k) {
+                const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+                if (l0) mb[ck] = m0;
+                ++ck;
+                addr += 32 * RS;
+            }
+            if (rem) {
+                const unsigned m0 = chunk_mask<T, HALF, FMA, false, true>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, lane < rem);
+                if (l0) mb[ck] = m0;
+            }
+        } else {
+            const T Sx = sm.segS[3 * sg], Sy = sm.segS[3 * sg + 1], Sz = sm.segS[3 * sg + 2];
+            int csx, csy, csz;
+            unpack_key(key, csx, csy, csz);
+            const bool lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
+#pragma unroll 2
+            for (int k = 0; k < nfull; ++k) {
+                const unsigned m0 = chunk_mask<T, HALF, FMA, true, false>(addr, xi, yi, zi, i, Sx, Sy, Sz, rc2, lexpos, true);
+                if (l0) mb[ck] = m0;
+                ++ck;
+                addr += 32 * RS;
+            }
+            if (rem) {
+                const unsigned m0 = chunk_mask<T, HALF, FMA, true, true>(addr, xi, yi, zi, i, Sx, Sy, Sz, rc2, lexpos, lane < rem);
+                if (l0) mb[ck] = m0;
+            }
+        }
+    }
+}
+
+// Phase 2: expand the hit masks of one atom into an output row.
+//   COO:    out_i[p0+k] = i, out_j[p0+pos] = j, shifts[3(p0+pos)..] = s
+//   MATRIX: neighbor_matrix[p0+pos] = j (pos < limit), shifts likewise
+template <typename T, bool COO>
+__device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastSmem<T>& sm, uint32_t cand_addr,
+                                           unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
+                                           int* __restrict__ out_sh) {
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int pc = __popc(mymask);
+    const int incl = warp_incl_scan(pc, lane);
+    const int excl = incl - pc;
+    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
+    const int nstore = cnt < limit ? cnt : limit;
+    const int off_idx = COO ? a.index_offset : 0;
+    if (COO) {
+        const int iv = i + off_idx;
+        for (int k = lane; k < nstore; k += 32) a.out_i[p0 + k] = iv;
+    }
+    // hits of a leading zero-shift segment occupy the first nzero row slots: their shifts are zero
+    int nzero = 0;
+    if (sm.seg_key[0] == 0) {
+        const int c1 = sm.seg_cb[1];
+        nzero = c1 > 0 ? __shfl_sync(0xffffffffu, incl, c1 - 1) : 0;
+        nzero = nzero < limit ? nzero : limit;
+    }
+    int* sh = out_sh + 3 * p0;
+    for (int e = lane; e < 3 * nzero; e += 32) sh[e] = 0;
+    const int nchunks = sm.nchunks;
+    for (int ck = 0; ck < nchunks; ++ck) {
+        const unsigned m = __shfl_sync(0xffffffffu, mymask, ck);
+        if (m == 0u) continue;
+        const int off = __shfl_sync(0xffffffffu, excl, ck);
+        if ((m >> lane) & 1u) {
+            const int pos = off + __popc(m & ltmask);
+            if (pos < limit) {
+                const int c = sm.chunk_cand[ck] + lane;
+                const int j = lds_rec_j<T>(cand_addr + (uint32_t)c * RS);
+                out_j[p0 + pos] = j + off_idx;
+                const int key = sm.seg_key[sm.chunk_seg[ck]];
+                if (key != 0) {
+                    int csx, csy, csz;
+                    unpack_key(key, csx, csy, csz);
+                    sh[3 * pos] = csx;
+                    sh[3 * pos + 1] = csy;
+                    sh[3 * pos + 2] = csz;
+                }
+            }
+        }
+    }
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool HALF, bool FMA>
+__global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FastSmem<T>& sm = *reinterpret_cast<FastSmem<T>*>(smem_raw + kCandBytes + kFastSlackBytes);
+    Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw);
+    const uint32_t cand_addr = smem_u32(smem_raw);
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    constexpr int cap = kCandBytes / (int)RS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(a.ws + a.L.ctrl);
+    const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
+    const int* cell_count = reinterpret_cast<const int*>(a.ws + a.L.cell_count);
+    const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
+    const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
+    unsigned* masks = reinterpret_cast<unsigned*>(a.ws + a.L.masks);
+    int* deferred = reinterpret_cast<int*>(a.ws + a.L.deferred);
+
+    if (MODE == FAST_COUNT) {
+        // re-arm the look-back scan that turns the counts into neighbor_ptr (runs after the count kernels)
+        unsigned long long* st1 = reinterpret_cast<unsigned long long*>(a.ws + a.L.scan_status1);
+        const long long nst = (a.n + 1) / kScanTile + 2;
+        for (long long k = (long long)blockIdx.x * blockDim.x + tid; k < nst; k += (long long)gridDim.x * blockDim.x)
+            st1[k] = 0ull;
+        if (blockIdx.x == 0 && tid == 0) {
+            ctrl->scan_tile[1] = 0;
+            ctrl->total_pairs = 0ull;
+            ctrl->max_count = 0;
+        }
+    }
+    const bool unwrapped = ctrl->unwrapped != 0;  // then every cell belongs to the general kernel
+    const int total_cells = ctrl->total_cells;
+    if (tid == 0) {
+        mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    unsigned* mb = sm.maskbuf[warp];
+
+    while (!unwrapped) {
+        // ---------------- warp 0: find the next cell this kernel can take, stage its stencil ----------------
+        if (warp == 0) {
+            for (;;) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&ctrl->work_counter[a.queue], 1);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= total_cells) {
+                    if (lane == 0) sm.item = -1;
+                    break;
+                }
+                const int ntarget = cell_count[g];
+                if (ntarget == 0) continue;
+                const int home_start = cell_start[g];
+                const int j0 = sorted[home_start].j;
+                const int s = a.batch_idx ? a.batch_idx[j0] : 0;
+                const SysParams& sp = sys[s];
+                const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
+                const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];
+                const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
+                const int nimg = nx * ny * nzz;
+                bool ok = nimg <= 32;
+                int st = 0, cn = 0, key = kKeyEmpty, tag = 0;
+                const int coff = sp.cell_offset;
+                if (ok && lane < nimg) {
+                    const int local = g - coff;
+                    const int cx = local % cpd0, cy = (local / cpd0) % cpd1, cz = local / (cpd0 * cpd1);
+                    const int dx = lane % nx - R0, dy = (lane / nx) % ny - R1, dz = lane / (nx * ny) - R2;
+                    int tx = cx + dx, ty = cy + dy, tz = cz + dz;
+                    bool in = true;
+                    int csx = 0, csy = 0, csz = 0;
+                    if (sp.pbc[0]) divmod_floor(tx, cpd0, csx, tx); else in = in && tx >= 0 && tx < cpd0;
+                    if (sp.pbc[1]) divmod_floor(ty, cpd1, csy, ty); else in = in && ty >= 0 && ty < cpd1;
+                    if (sp.pbc[2]) divmod_floor(tz, cpd2, csz, tz); else in = in && tz >= 0 && tz < cpd2;
+                    if (in) {
+                        const int gc = coff + tx + cpd0 * (ty + cpd1 * tz);
+                        cn = cell_count[gc];
+                        st = cell_start[gc];
+                        if (cn > 0) key = pack_key(csx, csy, csz);
+                    }
+                    tag = (dx == 0 && dy == 0 && dz == 0) ? 1 : 0;
+                }
+                const unsigned shiftmask = __ballot_sync(0xffffffffu, key != 0 && key != kKeyEmpty);
+                if (ok && shiftmask) {
+                    // order the images by shift: equal shifts become one contiguous segment, zero shift first
+                    int rank = 0;
+                    for (int t = 0; t < 32; ++t) {
+                        const int kt = __shfl_sync(0xffffffffu, key, t);
+                        rank += (kt < key || (kt == key && t < lane)) ? 1 : 0;
+                    }
+                    sm.e_st[rank] = st; sm.e_cn[rank] = cn; sm.e_key[rank] = key; sm.e_tag[rank] = tag;
+                    __syncwarp();
+                    st = sm.e_st[lane]; cn = sm.e_cn[lane]; key = sm.e_key[lane]; tag = sm.e_tag[lane];
+                    __syncwarp();
+                }
+                const int incl = warp_incl_scan(cn, lane);
+                const int off = incl - cn;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                ok = ok && total <= cap;
+                // segments
+                int nseg = 1;
+                int nch = 0;
+                if (ok) {
+                    if (shiftmask) {
+                        const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+                        const bool head = cn > 0 && (lane == 0 || pk != key);
+                        const unsigned hm = __ballot_sync(0xffffffffu, head);
+                        nseg = __popc(hm);
+                        if (head) {
+                            const int si = __popc(hm & ((1u << lane) - 1u));
+                            sm.seg_begin[si] = off;
+                            sm.seg_key[si] = key;
+                            int csx, csy, csz;
+                            unpack_key(key, csx, csy, csz);
+                            T cm[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
+                            T Sx, Sy, Sz;
+                            shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
+                            sm.segS[3 * si] = Sx; sm.segS[3 * si + 1] = Sy; sm.segS[3 * si + 2] = Sz;
+                        }
+                        if (lane == 0) sm.seg_begin[nseg] = total;
+                    } else if (lane == 0) {
+                        sm.seg_begin[0] = 0; sm.seg_begin[1] = total; sm.seg_key[0] = 0;
+                    }
+                    __syncwarp();
+                    int len = 0;
+                    if (lane < nseg) len = sm.seg_begin[lane + 1] - sm.seg_begin[lane];
+                    nch = (len + 31) >> 5;
+                    const int cbi = warp_incl_scan(nch, lane);
+                    const int nchunks = __shfl_sync(0xffffffffu, cbi, 31);
+                    ok = nchunks <= 32;
+                    if (ok) {
+                        if (lane < nseg) {
+                            const int cb = cbi - nch;
+                            sm.seg_cb[lane] = cb;
+                            const int b = sm.seg_begin[lane];
+                            for (int q = 0; q < nch; ++q) {
+                                sm.chunk_cand[cb + q] = b + 32 * q;
+                                sm.chunk_seg[cb + q] = lane;
+                            }
+                        }
+                        if (lane == 0) {
+                            sm.seg_cb[nseg] = nchunks;
+                            sm.nchunks = nchunks;
+                        }
+                    }
+                }
+                if (!ok) {
+                    // too many images / candidates for one tile: leave the cell to the general kernel
+                    if (lane == 0) deferred[atomicAdd(&ctrl->n_deferred, 1)] = g;
+                    continue;
+                }
+                const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
+                const int home_lane = __ffs(tagm) - 1;
+                const int home_off = __shfl_sync(0xffffffffu, off, home_lane);
+                if (lane == 0) {
+                    sm.item = g; sm.ntarget = ntarget; sm.home_start = home_start; sm.home_off = home_off;
+                    sm.nseg = nseg; sm.total = total;
+                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.mbar), (uint32_t)total * RS);
+                }
+                __syncwarp();
+                if (cn > 0)
+                    tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.mbar));
+                break;
+            }
+        }
+        __syncthreads();
+        if (sm.item < 0) break;
+        const int ntarget = sm.ntarget, home_off = sm.home_off, home_start = sm.home_start;
+        const int nchunks = sm.nchunks;
+        mbar_wait(reinterpret_cast<uint64_t*>(&sm.mbar), phase);
+        phase ^= 1u;
+
+        for (int t = warp; t < ntarget; t += kFastWarps) {
+            const int self = home_off + t;
+            T xi, yi, zi;
+            int i;
+            lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
+            unsigned mymask;
+            if (MODE == FAST_FILL_COO) {
+                mymask = masks[(size_t)(home_start + t) * 32 + lane];
+            } else {
+                fast_masks<T, HALF, FMA>(sm, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
+                __syncwarp();
+                mymask = lane < nchunks ? mb[lane] : 0u;
+                if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
+                __syncwarp();
+            }
+            if (MODE == FAST_COUNT) {
+                masks[(size_t)(home_start + t) * 32 + lane] = mymask;
+                const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
+                if (lane == 0) a.num_neighbors[i] = cnt;
+            } else if (MODE == FAST_FILL_COO) {
+                const size_t p0 = (size_t)a.neighbor_ptr[i];
+                fast_expand<T, true>(a, sm, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts);
+            } else {
+                const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
+                const int cnt = fast_expand<T, false>(a, sm, cand_addr, mymask, lane, i, p0, a.max_neighbors,
+                                                      a.neighbor_matrix, a.out_shifts);
+                finish_matrix_row<T>(a, lane, i, cnt);
+            }
+        }
+        __syncthreads();
+    }
+    // the last CTA to drain the queue re-arms it for the next launch on this workspace
+    if (tid == 0) {
+        __threadfence();
+        const int d = atomicAdd(&ctrl->done[a.queue], 1);
+        if (d == (int)gridDim.x - 1) {
+            ctrl->work_counter[a.queue] = 0;
+            ctrl->done[a.queue] = 0;
+        }
+    }
+}
+
+}  // namespace nvnl

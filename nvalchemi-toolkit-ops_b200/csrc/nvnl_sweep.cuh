@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
     int* cursor = reinterpret_cast<int*>(a.ws + a.L.cursor);
 
     const bool unwrapped = ctrl->unwrapped != 0;
-    const int total_cells = ctrl->total_cells;
+    // work source: every cell when atoms lie outside the primary image, else the cells the fast kernel
+    // (nvnl_fast.cuh) deferred (too many images or candidates for its single shared-memory tile)
+    const int* deferred = reinterpret_cast<const int*>(a.ws + a.L.deferred);
+    const int total_items = unwrapped ? ctrl->total_cells : ctrl->n_deferred;
     // unwrapped inputs also stage each candidate's periodic image (int4): half the record capacity
     const int cap = unwrapped ? (kCandBytes / 2) / (int)sizeof(Rec<T>) : kCandBytes / (int)sizeof(Rec<T>);
     int4* cand_ash = reinterpret_cast<int4*>(smem_raw + kCandBytes / 2);
@@ -270,8 +273,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
     for (;;) {
         if (tid == 0) sm.item = atomicAdd(&ctrl->work_counter[a.queue], 1);
         __syncthreads();
-        const int g = sm.item;
-        if (g >= total_cells) break;
+        const int item = sm.item;
+        if (item >= total_items) break;
+        const int g = unwrapped ? item : deferred[item];
         const int ntarget = cell_count[g];
         const int home_start = cell_start[g];
         if (ntarget == 0) {
@@ -508,6 +512,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
         if (d == (int)gridDim.x - 1) {
             ctrl->work_counter[a.queue] = 0;
             ctrl->done[a.queue] = 0;
+            ctrl->n_deferred = 0;  // consumed: the next fast launch rebuilds the list
         }
     }
 }

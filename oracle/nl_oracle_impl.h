@@ -257,7 +257,7 @@ typedef struct {
     const REAL *pos; int n; const REAL *cell; const unsigned char *pbc; const int *batch_idx;
     REAL cutoff_sq; const int *cpd; const int *radius; const int *atom_shifts; const int *atom_cell;
     const int *count; const int *start; const int *list; int *nm; int *nm_shifts; int *num;
-    int max_neighbors; int half_fill; int fma_mode; const int *cell_off; int *next_chunk;
+    int max_neighbors; int half_fill; int fma_mode; const int *cell_off; int *next_chunk; int n_limit;
 } FN(nlo_query_args);
 
 static void *FN(nlo_query_worker)(void *vp) {
@@ -265,8 +265,8 @@ static void *FN(nlo_query_worker)(void *vp) {
     const int CH = 256;
     for (;;) {
         int lo = __atomic_fetch_add(a->next_chunk, CH, __ATOMIC_RELAXED);
-        if (lo >= a->n) break;
-        int hi = nlo_imin(lo + CH, a->n);
+        if (lo >= a->n_limit) break;
+        int hi = nlo_imin(lo + CH, a->n_limit);
         for (int i = lo; i < hi; ++i) {
             const int s = a->batch_idx ? a->batch_idx[i] : 0;
             const REAL *cm = a->cell + 9 * s;
@@ -315,21 +315,23 @@ static void *FN(nlo_query_worker)(void *vp) {
  * nm must be pre-filled with fill_value, nm_shifts and num zeroed by the caller
  * (cell_list.py:1358-1373).  The reference runs one Warp thread per atom (serial on the Warp CPU
  * device); nthreads > 1 splits the atom range over pthreads (slot order then varies, like on GPU).
+ * n_limit > 0 runs only the first n_limit per-atom threads (bounded benchmark sample; output then partial).
  */
 void FN(nlo_query_cell_list)(const REAL *pos, int n, const REAL *cell, const unsigned char *pbc,
                              const int *batch_idx, int num_systems, REAL cutoff, const int *cpd,
                              const int *radius, const int *atom_shifts, const int *atom_cell,
                              const int *count, const int *start, const int *list, int *nm, int *nm_shifts,
-                             int *num, int max_neighbors, int half_fill, int fma_mode, int nthreads) {
+                             int *num, int max_neighbors, int half_fill, int fma_mode, int nthreads, int n_limit) {
     int *cell_off = (int *)malloc(sizeof(int) * ((size_t)num_systems + 1));
     cell_off[0] = 0;
     for (int s = 0; s < num_systems; ++s)
         cell_off[s + 1] = cell_off[s] + cpd[3 * s] * cpd[3 * s + 1] * cpd[3 * s + 2];
     int next = 0;
+    if (n_limit <= 0 || n_limit > n) n_limit = n; /* benchmark sampling: only atoms [0, n_limit) act as "thread i" */
     FN(nlo_query_args) a = {pos, n, cell, pbc, batch_idx,
                             cutoff * cutoff /* squared in kernel precision, cell_list.py:444 */,
                             cpd, radius, atom_shifts, atom_cell, count, start, list, nm, nm_shifts, num,
-                            max_neighbors, half_fill, fma_mode, cell_off, &next};
+                            max_neighbors, half_fill, fma_mode, cell_off, &next, n_limit};
     if (nthreads <= 1) {
         FN(nlo_query_worker)(&a);
     } else {

@@ -222,7 +222,7 @@ def build_cell_list(positions, cutoff, cell, pbc, cpd, radius, atom_shifts, atom
 
 def query_cell_list(positions, cutoff, cell, pbc, cpd, radius, atom_shifts, atom_cell, count, start, clist,
                     neighbor_matrix, neighbor_matrix_shifts, num_neighbors, half_fill=False, batch_idx=None,
-                    fma_mode=None, nthreads=1):
+                    fma_mode=None, nthreads=1, n_limit=0):
     """cell_list.py:892-1034 / batch_cell_list.py:915-1067 (mutates the three outputs in place)."""
     pos = _np(positions)
     n = pos.shape[0]
@@ -239,7 +239,7 @@ def query_cell_list(positions, cutoff, cell, pbc, cpd, radius, atom_shifts, atom
        _ptr(np.ascontiguousarray(cpd)), _ptr(np.ascontiguousarray(radius)), _ptr(atom_shifts), _ptr(atom_cell),
        _ptr(count), _ptr(start), _ptr(clist), _ptr(neighbor_matrix), _ptr(neighbor_matrix_shifts),
        _ptr(num_neighbors), ctypes.c_int(neighbor_matrix.shape[1]), ctypes.c_int(bool(half_fill)),
-       ctypes.c_int(fma), ctypes.c_int(nthreads))
+       ctypes.c_int(fma), ctypes.c_int(nthreads), ctypes.c_int(int(n_limit)))
 
 
 def _cell_list_impl(positions, cutoff, cell, pbc, batch_idx, max_neighbors, half_fill, fill_value,
