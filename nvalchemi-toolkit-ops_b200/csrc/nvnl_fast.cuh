@@ -18,6 +18,7 @@ namespace nvnl {
 
 constexpr int kFastThreads = 128;
 constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastRowIdx = 1056;       // >= max candidates per tile (1024) + one chunk
 constexpr int kFastSlackBytes = 1024;  // the tail chunk of the last segment may read past the staged data
 
 enum FastMode { FAST_COUNT = 0, FAST_FILL_COO = 1, FAST_MATRIX = 2 };
@@ -28,7 +29,8 @@ struct FastSmem {
     int seg_begin[33], seg_key[32], seg_cb[33];
     int chunk_cand[32], chunk_seg[32];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];
-    unsigned maskbuf[kFastWarps][32];
+    alignas(16) unsigned maskbuf[kFastWarps][32];
+    unsigned short rowidx[kFastWarps][kFastRowIdx];  // per-warp compacted (chunk<<11 | candidate) list of one row
     int item, ntarget, home_off, home_start, nseg, total, nchunks;
     unsigned long long mbar;
 };
@@ -55,6 +57,10 @@ __device__ __forceinline__ int lds_rec_j(uint32_t addr) {
     else
         asm volatile("ld.shared.b32 %0, [%1+24];" : "=r"(j) : "r"(addr));
     return j;
+}
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, unsigned a, unsigned b, unsigned c, unsigned d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // one 32-candidate chunk: returns the hit ballot
@@ -99,7 +105,10 @@ __device__ __forceinline__ void fast_masks(const FastSmem<T>& sm, uint32_t cand_
                 const unsigned m1 = chunk_mask<T, HALF, FMA, false, false>(addr + 32 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
                 const unsigned m2 = chunk_mask<T, HALF, FMA, false, false>(addr + 64 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
                 const unsigned m3 = chunk_mask<T, HALF, FMA, false, false>(addr + 96 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                if (l0) { mb[ck] = m0; mb[ck + 1] = m1; mb[ck + 2] = m2; mb[ck + 3] = m3; }
+                if (l0) {
+                    if ((ck & 3) == 0) sts_v4(smem_u32(mb + ck), m0, m1, m2, m3);
+                    else { mb[ck] = m0; mb[ck + 1] = m1; mb[ck + 2] = m2; mb[ck + 3] = m3; }
+                }
                 ck += 4;
                 addr += 128 * RS;
             }
@@ -135,55 +144,57 @@ __device__ __forceinline__ void fast_masks(const FastSmem<T>& sm, uint32_t cand_
 }
 
 // Phase 2: expand the hit masks of one atom into an output row.
-//   COO:    out_i[p0+k] = i, out_j[p0+pos] = j, shifts[3(p0+pos)..] = s
-//   MATRIX: neighbor_matrix[p0+pos] = j (pos < limit), shifts likewise
+//   step 1: lane ck walks the set bits of chunk ck's mask and writes (ck << 11 | candidate index) into the
+//           warp's index row at its popc-prefix offset (divergent, ~max popc iterations);
+//   step 2: coalesced passes over the row: out_j (gather of candidate.j), out_i (COO), shifts.
+//   COO:    out_i[p0+k] = i, out_j[p0+k] = j_k, shifts[3(p0+k)..] = s_k
+//   MATRIX: neighbor_matrix[p0+k] = j_k for k < limit, shifts likewise
 template <typename T, bool COO>
 __device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastSmem<T>& sm, uint32_t cand_addr,
                                            unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
-                                           int* __restrict__ out_sh) {
+                                           int* __restrict__ out_sh, unsigned short* __restrict__ rowidx) {
     constexpr uint32_t RS = sizeof(Rec<T>);
-    const unsigned ltmask = (1u << lane) - 1u;
     const int pc = __popc(mymask);
     const int incl = warp_incl_scan(pc, lane);
-    const int excl = incl - pc;
     const int cnt = __shfl_sync(0xffffffffu, incl, 31);
     const int nstore = cnt < limit ? cnt : limit;
-    const int off_idx = COO ? a.index_offset : 0;
-    if (COO) {
-        const int iv = i + off_idx;
-        for (int k = lane; k < nstore; k += 32) a.out_i[p0 + k] = iv;
-    }
     // hits of a leading zero-shift segment occupy the first nzero row slots: their shifts are zero
     int nzero = 0;
     if (sm.seg_key[0] == 0) {
         const int c1 = sm.seg_cb[1];
         nzero = c1 > 0 ? __shfl_sync(0xffffffffu, incl, c1 - 1) : 0;
-        nzero = nzero < limit ? nzero : limit;
-    }
-    int* sh = out_sh + 3 * p0;
-    for (int e = lane; e < 3 * nzero; e += 32) sh[e] = 0;
-    const int nchunks = sm.nchunks;
-    for (int ck = 0; ck < nchunks; ++ck) {
-        const unsigned m = __shfl_sync(0xffffffffu, mymask, ck);
-        if (m == 0u) continue;
-        const int off = __shfl_sync(0xffffffffu, excl, ck);
-        if ((m >> lane) & 1u) {
-            const int pos = off + __popc(m & ltmask);
-            if (pos < limit) {
-                const int c = sm.chunk_cand[ck] + lane;
-                const int j = lds_rec_j<T>(cand_addr + (uint32_t)c * RS);
-                out_j[p0 + pos] = j + off_idx;
-                const int key = sm.seg_key[sm.chunk_seg[ck]];
-                if (key != 0) {
-                    int csx, csy, csz;
-                    unpack_key(key, csx, csy, csz);
-                    sh[3 * pos] = csx;
-                    sh[3 * pos + 1] = csy;
-                    sh[3 * pos + 2] = csz;
-                }
-            }
+    } 
+    {
+        unsigned m = mymask;
+        int off = incl - pc;
+        const unsigned base = ((unsigned)lane << 11) | (unsigned)sm.chunk_cand[lane];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            rowidx[off++] = (unsigned short)(base + b);
         }
     }
+    __syncwarp();
+    const int off_idx = COO ? a.index_offset : 0;
+    const int iv = i + off_idx;
+    for (int k = lane; k < nstore; k += 32) {
+        const unsigned c = rowidx[k] & 2047u;
+        const int j = lds_rec_j<T>(cand_addr + c * RS);
+        out_j[p0 + k] = j + off_idx;
+        if (COO) a.out_i[p0 + k] = iv;
+    }
+    int* sh = out_sh + 3 * p0;
+    const int nz = nzero < nstore ? nzero : nstore;
+    for (int e = lane; e < 3 * nz; e += 32) sh[e] = 0;
+    for (int k = nz + lane; k < nstore; k += 32) {
+        const int ck = rowidx[k] >> 11;
+        int csx, csy, csz;
+        unpack_key(sm.seg_key[sm.chunk_seg[ck]], csx, csy, csz);
+        sh[3 * k] = csx;
+        sh[3 * k + 1] = csy;
+        sh[3 * k + 2] = csz;
+    }
+    __syncwarp();
     return cnt;
 }
 
@@ -383,11 +394,12 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                 if (lane == 0) a.num_neighbors[i] = cnt;
             } else if (MODE == FAST_FILL_COO) {
                 const size_t p0 = (size_t)a.neighbor_ptr[i];
-                fast_expand<T, true>(a, sm, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts);
+                fast_expand<T, true>(a, sm, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts,
+                                     sm.rowidx[warp]);
             } else {
                 const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
                 const int cnt = fast_expand<T, false>(a, sm, cand_addr, mymask, lane, i, p0, a.max_neighbors,
-                                                      a.neighbor_matrix, a.out_shifts);
+                                                      a.neighbor_matrix, a.out_shifts, sm.rowidx[warp]);
                 finish_matrix_row<T>(a, lane, i, cnt);
             }
         }
