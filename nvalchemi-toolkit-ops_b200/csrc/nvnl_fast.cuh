@@ -16,28 +16,40 @@
 
 namespace nvnl {
 
-constexpr int kFastThreads = 128;
-constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastRowIdx = 1056;       // >= max candidates per tile (1024) + one chunk
-constexpr int kFastSlackBytes = 1024;  // the tail chunk of the last segment may read past the staged data
+constexpr int kFastCons = 6;                          // consumer warps per CTA
+constexpr int kFastThreads = (kFastCons + 1) * 32;    // + one producer warp (warp 0)
+constexpr int kFastStages = 2;                        // TMA ring depth
+constexpr int kFastRowIdx = 1056;                     // >= max candidates per tile (1024) + one chunk
+constexpr int kFastSlackBytes = 1024;                 // the tail chunk of the last segment may read past the staged data
+constexpr int kFastStageBytes = kCandBytes + kFastSlackBytes;
 
 enum FastMode { FAST_COUNT = 0, FAST_FILL_COO = 1, FAST_MATRIX = 2 };
 
+// Per-stage tables written by the producer warp, read by the consumer warps.
 template <typename T>
-struct FastSmem {
+struct FastStage {
     T segS[32 * 3];
     int seg_begin[33], seg_key[32], seg_cb[33];
     int chunk_cand[32], chunk_seg[32];
-    int e_st[32], e_cn[32], e_key[32], e_tag[32];
-    alignas(16) unsigned maskbuf[kFastWarps][32];
-    unsigned short rowidx[kFastWarps][kFastRowIdx];  // per-warp compacted (chunk<<11 | candidate) list of one row
-    int item, ntarget, home_off, home_start, nseg, total, nchunks;
-    unsigned long long mbar;
+    int item, ntarget, home_off, home_start, nseg, total, nchunks, next_target;
+};
+
+template <typename T>
+struct FastSmem {
+    FastStage<T> stage[kFastStages];
+    int e_st[32], e_cn[32], e_key[32], e_tag[32];                // producer scratch (shift sort)
+    alignas(16) unsigned maskbuf[kFastCons][32];                 // per consumer warp: hit masks of the current row
+    unsigned short rowidx[kFastCons][kFastRowIdx];               // per consumer warp: (chunk<<11 | candidate) list
+    unsigned long long full[kFastStages], empty[kFastStages];    // mbarriers of the ring
 };
 
 template <typename T>
 constexpr size_t fast_smem_bytes() {
-    return (size_t)kCandBytes + kFastSlackBytes + sizeof(FastSmem<T>);
+    return (size_t)kFastStages * kFastStageBytes + sizeof(FastSmem<T>);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ---- shared-memory accessors on 32-bit shared-space addresses -----------------------------------
@@ -86,7 +98,7 @@ __device__ __forceinline__ unsigned chunk_mask(uint32_t addr, T xi, T yi, T zi, 
 
 // Phase 1: hit masks of one target atom against the staged stencil; chunk ck's ballot -> mb[ck].
 template <typename T, bool HALF, bool FMA>
-__device__ __forceinline__ void fast_masks(const FastSmem<T>& sm, uint32_t cand_addr, T xi, T yi, T zi, int i, T rc2,
+__device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand_addr, T xi, T yi, T zi, int i, T rc2,
                                            int lane, unsigned* __restrict__ mb) {
     constexpr uint32_t RS = sizeof(Rec<T>);
     const int nseg = sm.nseg;
@@ -150,7 +162,7 @@ __device__ __forceinline__ void fast_masks(const FastSmem<T>& sm, uint32_t cand_
 //   COO:    out_i[p0+k] = i, out_j[p0+k] = j_k, shifts[3(p0+k)..] = s_k
 //   MATRIX: neighbor_matrix[p0+k] = j_k for k < limit, shifts likewise
 template <typename T, bool COO>
-__device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastSmem<T>& sm, uint32_t cand_addr,
+__device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastStage<T>& sm, uint32_t cand_addr,
                                            unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
                                            int* __restrict__ out_sh, unsigned short* __restrict__ rowidx) {
     constexpr uint32_t RS = sizeof(Rec<T>);
@@ -199,23 +211,24 @@ __device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastSmem
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_fast: warp-specialised persistent kernel.
+//   warp 0 (producer): pulls target cells from the device queue, enumerates the stencil images, sorts them by
+//     shift, builds the segment/chunk tables of a ring stage and issues the TMA bulk copies that concatenate
+//     the stencil's runs in that stage's shared-memory buffer (full[stage] mbarrier, expect_tx).
+//   warps 1..kFastCons (consumers): wait on full[stage], claim target atoms of the cell one at a time
+//     (shared-memory counter), sweep / expand, and release the stage through empty[stage].
+// No CTA-wide barrier in the steady state: the setup latency of cell k+1 hides behind the sweep of cell k.
+// ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HALF, bool FMA>
-__global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FastSmem<T>& sm = *reinterpret_cast<FastSmem<T>*>(smem_raw + kCandBytes + kFastSlackBytes);
-    Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw);
-    const uint32_t cand_addr = smem_u32(smem_raw);
+    FastSmem<T>& sm = *reinterpret_cast<FastSmem<T>*>(smem_raw + (size_t)kFastStages * kFastStageBytes);
+    const uint32_t smem_base = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
     constexpr int cap = kCandBytes / (int)RS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(a.ws + a.L.ctrl);
-    const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
-    const int* cell_count = reinterpret_cast<const int*>(a.ws + a.L.cell_count);
-    const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
-    const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
-    unsigned* masks = reinterpret_cast<unsigned*>(a.ws + a.L.masks);
-    int* deferred = reinterpret_cast<int*>(a.ws + a.L.deferred);
 
     if (MODE == FAST_COUNT) {
         // re-arm the look-back scan that turns the counts into neighbor_ptr (runs after the count kernels)
@@ -230,24 +243,36 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
         }
     }
     const bool unwrapped = ctrl->unwrapped != 0;  // then every cell belongs to the general kernel
-    const int total_cells = ctrl->total_cells;
     if (tid == 0) {
-        mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar), 1);
+        for (int st = 0; st < kFastStages; ++st) {
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kFastCons);
+        }
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t phase = 0;
-    unsigned* mb = sm.maskbuf[warp];
 
-    while (!unwrapped) {
-        // ---------------- warp 0: find the next cell this kernel can take, stage its stencil ----------------
-        if (warp == 0) {
+    if (warp == 0) {
+        // =========================== producer ===========================
+        const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
+        const int* cell_count = reinterpret_cast<const int*>(a.ws + a.L.cell_count);
+        const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
+        const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
+        int* deferred = reinterpret_cast<int*>(a.ws + a.L.deferred);
+        const int total_cells = unwrapped ? 0 : ctrl->total_cells;
+        int stage = 0;
+        uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
+        for (;;) {
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
+            FastStage<T>& sg = sm.stage[stage];
+            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kFastStageBytes);
+            bool done = false;
             for (;;) {
                 int g = 0;
                 if (lane == 0) g = atomicAdd(&ctrl->work_counter[a.queue], 1);
                 g = __shfl_sync(0xffffffffu, g, 0);
                 if (g >= total_cells) {
-                    if (lane == 0) sm.item = -1;
+                    done = true;
                     break;
                 }
                 const int ntarget = cell_count[g];
@@ -298,7 +323,6 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                 const int off = incl - cn;
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 ok = ok && total <= cap;
-                // segments
                 int nseg = 1;
                 int nch = 0;
                 if (ok) {
@@ -309,8 +333,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                         nseg = __popc(hm);
                         if (head) {
                             const int si = __popc(hm & ((1u << lane) - 1u));
-                            sm.seg_begin[si] = off;
-                            sm.seg_key[si] = key;
+                            sg.seg_begin[si] = off;
+                            sg.seg_key[si] = key;
                             int csx, csy, csz;
                             unpack_key(key, csx, csy, csz);
                             T cm[9];
@@ -318,15 +342,15 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                             for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
                             T Sx, Sy, Sz;
                             shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
-                            sm.segS[3 * si] = Sx; sm.segS[3 * si + 1] = Sy; sm.segS[3 * si + 2] = Sz;
+                            sg.segS[3 * si] = Sx; sg.segS[3 * si + 1] = Sy; sg.segS[3 * si + 2] = Sz;
                         }
-                        if (lane == 0) sm.seg_begin[nseg] = total;
+                        if (lane == 0) sg.seg_begin[nseg] = total;
                     } else if (lane == 0) {
-                        sm.seg_begin[0] = 0; sm.seg_begin[1] = total; sm.seg_key[0] = 0;
+                        sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0;
                     }
                     __syncwarp();
                     int len = 0;
-                    if (lane < nseg) len = sm.seg_begin[lane + 1] - sm.seg_begin[lane];
+                    if (lane < nseg) len = sg.seg_begin[lane + 1] - sg.seg_begin[lane];
                     nch = (len + 31) >> 5;
                     const int cbi = warp_incl_scan(nch, lane);
                     const int nchunks = __shfl_sync(0xffffffffu, cbi, 31);
@@ -334,16 +358,16 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                     if (ok) {
                         if (lane < nseg) {
                             const int cb = cbi - nch;
-                            sm.seg_cb[lane] = cb;
-                            const int b = sm.seg_begin[lane];
+                            sg.seg_cb[lane] = cb;
+                            const int b = sg.seg_begin[lane];
                             for (int q = 0; q < nch; ++q) {
-                                sm.chunk_cand[cb + q] = b + 32 * q;
-                                sm.chunk_seg[cb + q] = lane;
+                                sg.chunk_cand[cb + q] = b + 32 * q;
+                                sg.chunk_seg[cb + q] = lane;
                             }
                         }
                         if (lane == 0) {
-                            sm.seg_cb[nseg] = nchunks;
-                            sm.nchunks = nchunks;
+                            sg.seg_cb[nseg] = nchunks;
+                            sg.nchunks = nchunks;
                         }
                     }
                 }
@@ -356,62 +380,86 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const SweepArgs<T> a) 
                 const int home_lane = __ffs(tagm) - 1;
                 const int home_off = __shfl_sync(0xffffffffu, off, home_lane);
                 if (lane == 0) {
-                    sm.item = g; sm.ntarget = ntarget; sm.home_start = home_start; sm.home_off = home_off;
-                    sm.nseg = nseg; sm.total = total;
-                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.mbar), (uint32_t)total * RS);
+                    sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
+                    sg.nseg = nseg; sg.total = total; sg.next_target = 0;
                 }
+                __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
+                if (lane == 0)
+                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), (uint32_t)total * RS);
                 __syncwarp();
                 if (cn > 0)
-                    tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.mbar));
+                    tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
                 break;
             }
-        }
-        __syncthreads();
-        if (sm.item < 0) break;
-        const int ntarget = sm.ntarget, home_off = sm.home_off, home_start = sm.home_start;
-        const int nchunks = sm.nchunks;
-        mbar_wait(reinterpret_cast<uint64_t*>(&sm.mbar), phase);
-        phase ^= 1u;
-
-        for (int t = warp; t < ntarget; t += kFastWarps) {
-            const int self = home_off + t;
-            T xi, yi, zi;
-            int i;
-            lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
-            unsigned mymask;
-            if (MODE == FAST_FILL_COO) {
-                mymask = masks[(size_t)(home_start + t) * 32 + lane];
-            } else {
-                fast_masks<T, HALF, FMA>(sm, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
-                __syncwarp();
-                mymask = lane < nchunks ? mb[lane] : 0u;
-                if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
-                __syncwarp();
+            if (done) {
+                if (lane == 0) {
+                    sg.item = -1;
+                    mbar_arrive(reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                }
+                break;
             }
-            if (MODE == FAST_COUNT) {
-                masks[(size_t)(home_start + t) * 32 + lane] = mymask;
-                const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
-                if (lane == 0) a.num_neighbors[i] = cnt;
-            } else if (MODE == FAST_FILL_COO) {
-                const size_t p0 = (size_t)a.neighbor_ptr[i];
-                fast_expand<T, true>(a, sm, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts,
-                                     sm.rowidx[warp]);
-            } else {
-                const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
-                const int cnt = fast_expand<T, false>(a, sm, cand_addr, mymask, lane, i, p0, a.max_neighbors,
-                                                      a.neighbor_matrix, a.out_shifts, sm.rowidx[warp]);
-                finish_matrix_row<T>(a, lane, i, cnt);
+            if (++stage == kFastStages) { stage = 0; ephase ^= 1u; }
+        }
+        // the last CTA to drain the queue re-arms it for the next launch on this workspace
+        if (lane == 0) {
+            __threadfence();
+            const int d = atomicAdd(&ctrl->done[a.queue], 1);
+            if (d == (int)gridDim.x - 1) {
+                ctrl->work_counter[a.queue] = 0;
+                ctrl->done[a.queue] = 0;
             }
         }
-        __syncthreads();
-    }
-    // the last CTA to drain the queue re-arms it for the next launch on this workspace
-    if (tid == 0) {
-        __threadfence();
-        const int d = atomicAdd(&ctrl->done[a.queue], 1);
-        if (d == (int)gridDim.x - 1) {
-            ctrl->work_counter[a.queue] = 0;
-            ctrl->done[a.queue] = 0;
+    } else {
+        // =========================== consumers ===========================
+        const int cw = warp - 1;
+        unsigned* masks = reinterpret_cast<unsigned*>(a.ws + a.L.masks);
+        unsigned* mb = sm.maskbuf[cw];
+        unsigned short* rowidx = sm.rowidx[cw];
+        int stage = 0;
+        uint32_t fphase = 0;
+        for (;;) {
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
+            FastStage<T>& sg = sm.stage[stage];
+            if (sg.item < 0) break;
+            const uint32_t cand_addr = smem_base + (uint32_t)stage * kFastStageBytes;
+            const int ntarget = sg.ntarget, home_off = sg.home_off, home_start = sg.home_start;
+            const int nchunks = sg.nchunks;
+            for (;;) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&sg.next_target, 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= ntarget) break;
+                const int self = home_off + t;
+                T xi, yi, zi;
+                int i;
+                lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
+                unsigned mymask;
+                if (MODE == FAST_FILL_COO) {
+                    mymask = masks[(size_t)(home_start + t) * 32 + lane];
+                } else {
+                    fast_masks<T, HALF, FMA>(sg, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
+                    __syncwarp();
+                    mymask = lane < nchunks ? mb[lane] : 0u;
+                    if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
+                    __syncwarp();
+                }
+                if (MODE == FAST_COUNT) {
+                    masks[(size_t)(home_start + t) * 32 + lane] = mymask;
+                    const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
+                    if (lane == 0) a.num_neighbors[i] = cnt;
+                } else if (MODE == FAST_FILL_COO) {
+                    const size_t p0 = (size_t)a.neighbor_ptr[i];
+                    fast_expand<T, true>(a, sg, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts, rowidx);
+                } else {
+                    const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
+                    const int cnt = fast_expand<T, false>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
+                                                          a.neighbor_matrix, a.out_shifts, rowidx);
+                    finish_matrix_row<T>(a, lane, i, cnt);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
+            if (++stage == kFastStages) { stage = 0; fphase ^= 1u; }
         }
     }
 }
