@@ -1,0 +1,88 @@
+"""world_size-2 gloo tests (CPU) of the batch-sharding logic: partitioning, global index offsets, the size
+exchange, the padded payload all-gather and the re-assembly.  The per-rank neighbor lists come from the oracle
+through the module's test hook — the collective plumbing is what is under test here; the CUDA local path is
+covered by the -m gpu tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_local(positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset, _bb):
+    import reference_oracle as ro
+
+    e, p, s = ro.batch_cell_list(positions, cutoff, cell, pbc, batch_idx, max_neighbors=2048, half_fill=half_fill,
+                                 return_neighbor_list=True)
+    num = torch.from_numpy(np.diff(p).astype(np.int32))
+    total = int(e.shape[1])
+
+    def fill(block, pmax):
+        block[:total] = torch.from_numpy(e[0]) + index_offset
+        block[pmax:pmax + total] = torch.from_numpy(e[1]) + index_offset
+        block[2 * pmax:2 * pmax + 3 * total] = torch.from_numpy(np.ascontiguousarray(s)).reshape(-1)
+
+    return num, total, int(num.max()) if num.numel() else 0, fill
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "nvalchemi-toolkit-ops_b200"), os.path.join(ROOT, "oracle"),
+              os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nvalchemiops_b200.neighborlist.distributed import sharded_batch_neighbor_list
+    from systems import bench_batch
+
+    pos, cell, pbc, bidx, bptr = bench_batch(9, 60, 140, seed=5, mixed_pbc=True)
+    e, ptr, s = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_coo=_oracle_local)
+    torch.save({"e": e, "ptr": ptr, "s": s}, os.path.join(out_dir, f"r{rank}.pt"))
+    shard = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, gather=False, _local_coo=_oracle_local)
+    torch.save({"e": shard[0], "range": shard[3]}, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_batch_matches_single_process(tmp_path, world):
+    import reference_oracle as ro
+    from systems import bench_batch
+
+    port = 29600 + world + (os.getpid() % 200)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    pos, cell, pbc, bidx, bptr = bench_batch(9, 60, 140, seed=5, mixed_pbc=True)
+    e, p, s = ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=2048, return_neighbor_list=True)
+    want = ro.records_from_coo(e, s)
+    covered = []
+    for r in range(world):
+        got = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert np.array_equal(ro.records_from_coo(got["e"], got["s"]), want), f"rank {r}"
+        assert np.array_equal(got["ptr"].numpy(), p)
+        assert (np.diff(got["e"][0].numpy()) >= 0).all(), "global COO stays sorted by source atom"
+        sh = torch.load(os.path.join(tmp_path, f"s{r}.pt"))
+        lo, hi = sh["range"]
+        src = sh["e"][0].numpy()
+        assert ((src >= lo) & (src < hi)).all()
+        covered.append((lo, hi))
+    covered.sort()
+    assert covered[0][0] == 0 and covered[-1][1] == pos.shape[0]
+    assert all(covered[k][1] == covered[k + 1][0] for k in range(world - 1))
+
+
+def test_partition_balances_atoms():
+    from nvalchemiops_b200.neighborlist.distributed import partition_systems
+
+    ptr = [0, 10, 20, 30, 40, 50, 60, 70, 80]
+    assert partition_systems(ptr, 2) == [(0, 4), (4, 8)]
+    assert partition_systems(ptr, 8) == [(k, k + 1) for k in range(8)]
+    parts = partition_systems([0, 1000, 1010, 1020, 1030], 2)
+    assert parts[0][0] == 0 and parts[-1][1] == 4 and all(a <= b for a, b in parts)
+    parts = partition_systems([0, 5, 10], 4)  # more ranks than systems: some ranks get nothing
+    assert parts[0][0] == 0 and parts[-1][1] == 2 and sum(b - a for a, b in parts) == 2
