@@ -210,6 +210,67 @@ __device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastStag
     return cnt;
 }
 
+// position of the r-th (0-based) set bit of m (r < popc(m)): popc halving, ~33 SASS instructions
+__device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
+    int bit = 0, t;
+    t = __popc(m & 0xFFFFu); if (r >= t) { r -= t; bit = 16; m >>= 16; }
+    t = __popc(m & 0xFFu);   if (r >= t) { r -= t; bit += 8; m >>= 8; }
+    t = __popc(m & 0xFu);    if (r >= t) { r -= t; bit += 4; m >>= 4; }
+    t = __popc(m & 0x3u);    if (r >= t) { r -= t; bit += 2; m >>= 2; }
+    t = (int)(m & 1u);       if (r >= t) { bit += 1; }
+    return bit;
+}
+
+// Phase 2 (balanced): every lane produces its own output entries k = lane, lane+32, ...:
+//   chunk of entry k  = first chunk whose inclusive popc prefix exceeds k (5-step search in shared memory),
+//   bit inside it     = nth_set_bit(mask[chunk], k - prefix[chunk-1]).
+// ~90 hits / 32 lanes = 3 iterations per atom instead of a serial walk bounded by the densest chunk (~22 bits).
+template <typename T, bool COO>
+__device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastStage<T>& sm, uint32_t cand_addr,
+                                            unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
+                                            int* __restrict__ out_sh, unsigned* __restrict__ mb, int* __restrict__ pre) {
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    const int pc = __popc(mymask);
+    const int incl = warp_incl_scan(pc, lane);
+    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
+    const int nstore = cnt < limit ? cnt : limit;
+    mb[lane] = mymask;
+    pre[lane] = incl;
+    int nzero = 0;  // hits of a leading zero-shift segment occupy the first nzero row slots
+    if (sm.seg_key[0] == 0) {
+        const int c1 = sm.seg_cb[1];
+        nzero = c1 > 0 ? __shfl_sync(0xffffffffu, incl, c1 - 1) : 0;
+    }
+    __syncwarp();
+    const int off_idx = COO ? a.index_offset : 0;
+    const int iv = i + off_idx;
+    int* sh = out_sh + 3 * p0;
+    for (int k = lane; k < nstore; k += 32) {
+        int ck = (pre[15] <= k) ? 16 : 0;
+        ck += (pre[ck + 7] <= k) ? 8 : 0;
+        ck += (pre[ck + 3] <= k) ? 4 : 0;
+        ck += (pre[ck + 1] <= k) ? 2 : 0;
+        ck += (pre[ck] <= k) ? 1 : 0;
+        const int r = k - (ck ? pre[ck - 1] : 0);
+        const int bit = nth_set_bit(mb[ck], r);
+        const int c = sm.chunk_cand[ck] + bit;
+        const int j = lds_rec_j<T>(cand_addr + (uint32_t)c * RS);
+        out_j[p0 + k] = j + off_idx;
+        if (COO) a.out_i[p0 + k] = iv;
+        if (k >= nzero) {
+            int csx, csy, csz;
+            unpack_key(sm.seg_key[sm.chunk_seg[ck]], csx, csy, csz);
+            sh[3 * k] = csx;
+            sh[3 * k + 1] = csy;
+            sh[3 * k + 2] = csz;
+        }
+    }
+    const int nz = nzero < nstore ? nzero : nstore;
+    for (int e = lane; e < 3 * nz; e += 32) sh[e] = 0;
+    __syncwarp();
+    return cnt;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_fast: warp-specialised persistent kernel.
 //   warp 0 (producer): pulls target cells from the device queue, enumerates the stencil images, sorts them by
@@ -424,37 +485,59 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
             const uint32_t cand_addr = smem_base + (uint32_t)stage * kFastStageBytes;
             const int ntarget = sg.ntarget, home_off = sg.home_off, home_start = sg.home_start;
             const int nchunks = sg.nchunks;
-            for (;;) {
-                int t = 0;
-                if (lane == 0) t = atomicAdd(&sg.next_target, 1);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (t >= ntarget) break;
-                const int self = home_off + t;
-                T xi, yi, zi;
-                int i;
-                lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
-                unsigned mymask;
-                if (MODE == FAST_FILL_COO) {
-                    mymask = masks[(size_t)(home_start + t) * 32 + lane];
-                } else {
+            int* pre = reinterpret_cast<int*>(rowidx);  // per-warp scratch: inclusive popc prefix per chunk
+            if (MODE == FAST_FILL_COO) {
+                // software pipeline: the mask / row pointer of the NEXT target are in flight while this one is expanded
+                const int* __restrict__ nptr = a.neighbor_ptr;
+                int t0 = 0;
+                if (lane == 0) t0 = atomicAdd(&sg.next_target, 1);
+                t0 = __shfl_sync(0xffffffffu, t0, 0);
+                unsigned m0 = 0u;
+                int i0 = 0, q0 = 0;
+                if (t0 < ntarget) {
+                    m0 = masks[(size_t)(home_start + t0) * 32 + lane];
+                    i0 = lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t0) * RS);
+                    q0 = nptr[i0];
+                }
+                while (t0 < ntarget) {
+                    int t1 = 0;
+                    if (lane == 0) t1 = atomicAdd(&sg.next_target, 1);
+                    t1 = __shfl_sync(0xffffffffu, t1, 0);
+                    unsigned m1 = 0u;
+                    int i1 = 0, q1 = 0;
+                    if (t1 < ntarget) {
+                        m1 = masks[(size_t)(home_start + t1) * 32 + lane];
+                        i1 = lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t1) * RS);
+                        q1 = nptr[i1];
+                    }
+                    fast_expand2<T, true>(a, sg, cand_addr, m0, lane, i0, (size_t)q0, 0x7fffffff, a.out_j, a.out_shifts, mb, pre);
+                    t0 = t1; m0 = m1; i0 = i1; q0 = q1;
+                }
+            } else {
+                for (;;) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&sg.next_target, 1);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    if (t >= ntarget) break;
+                    const int self = home_off + t;
+                    T xi, yi, zi;
+                    int i;
+                    lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
                     fast_masks<T, HALF, FMA>(sg, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
                     __syncwarp();
-                    mymask = lane < nchunks ? mb[lane] : 0u;
+                    unsigned mymask = lane < nchunks ? mb[lane] : 0u;
                     if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
                     __syncwarp();
-                }
-                if (MODE == FAST_COUNT) {
-                    masks[(size_t)(home_start + t) * 32 + lane] = mymask;
-                    const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
-                    if (lane == 0) a.num_neighbors[i] = cnt;
-                } else if (MODE == FAST_FILL_COO) {
-                    const size_t p0 = (size_t)a.neighbor_ptr[i];
-                    fast_expand<T, true>(a, sg, cand_addr, mymask, lane, i, p0, 0x7fffffff, a.out_j, a.out_shifts, rowidx);
-                } else {
-                    const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
-                    const int cnt = fast_expand<T, false>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
-                                                          a.neighbor_matrix, a.out_shifts, rowidx);
-                    finish_matrix_row<T>(a, lane, i, cnt);
+                    if (MODE == FAST_COUNT) {
+                        masks[(size_t)(home_start + t) * 32 + lane] = mymask;
+                        const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
+                        if (lane == 0) a.num_neighbors[i] = cnt;
+                    } else {
+                        const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
+                        const int cnt = fast_expand2<T, false>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
+                                                               a.neighbor_matrix, a.out_shifts, mb, pre);
+                        finish_matrix_row<T>(a, lane, i, cnt);
+                    }
                 }
             }
             __syncwarp();
