@@ -19,7 +19,7 @@ namespace nvnl {
 constexpr int kFastCons = 6;                          // consumer warps per CTA
 constexpr int kFastThreads = (kFastCons + 1) * 32;    // + one producer warp (warp 0)
 constexpr int kFastStages = 2;                        // TMA ring depth
-constexpr int kFastRowIdx = 1056;                     // >= max candidates per tile (1024) + one chunk
+constexpr int kFastMaxTargets = 64;                   // target atoms per cell the fast kernel takes (else: general kernel)
 constexpr int kFastSlackBytes = 1024;                 // the tail chunk of the last segment may read past the staged data
 constexpr int kFastStageBytes = kCandBytes + kFastSlackBytes;
 
@@ -32,6 +32,7 @@ struct FastStage {
     int seg_begin[33], seg_key[32], seg_cb[33];
     int chunk_cand[32], chunk_seg[32];
     int item, ntarget, home_off, home_start, nseg, total, nchunks, next_target;
+    int irow[kFastMaxTargets], qrow[kFastMaxTargets];  // FILL: original index and neighbor_ptr of every target
 };
 
 template <typename T>
@@ -39,7 +40,8 @@ struct FastSmem {
     FastStage<T> stage[kFastStages];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                // producer scratch (shift sort)
     alignas(16) unsigned maskbuf[kFastCons][32];                 // per consumer warp: hit masks of the current row
-    unsigned short rowidx[kFastCons][kFastRowIdx];               // per consumer warp: (chunk<<11 | candidate) list
+    int pre[kFastCons][32];                                      // per consumer warp: inclusive popc prefix per chunk
+    alignas(16) unsigned smasks[kFastStages][kFastMaxTargets * 32];  // FILL: the cell's hit masks (TMA from global)
     unsigned long long full[kFastStages], empty[kFastStages];    // mbarriers of the ring
 };
 
@@ -153,61 +155,6 @@ __device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand
             }
         }
     }
-}
-
-// Phase 2: expand the hit masks of one atom into an output row.
-//   step 1: lane ck walks the set bits of chunk ck's mask and writes (ck << 11 | candidate index) into the
-//           warp's index row at its popc-prefix offset (divergent, ~max popc iterations);
-//   step 2: coalesced passes over the row: out_j (gather of candidate.j), out_i (COO), shifts.
-//   COO:    out_i[p0+k] = i, out_j[p0+k] = j_k, shifts[3(p0+k)..] = s_k
-//   MATRIX: neighbor_matrix[p0+k] = j_k for k < limit, shifts likewise
-template <typename T, bool COO>
-__device__ __forceinline__ int fast_expand(const SweepArgs<T>& a, const FastStage<T>& sm, uint32_t cand_addr,
-                                           unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
-                                           int* __restrict__ out_sh, unsigned short* __restrict__ rowidx) {
-    constexpr uint32_t RS = sizeof(Rec<T>);
-    const int pc = __popc(mymask);
-    const int incl = warp_incl_scan(pc, lane);
-    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
-    const int nstore = cnt < limit ? cnt : limit;
-    // hits of a leading zero-shift segment occupy the first nzero row slots: their shifts are zero
-    int nzero = 0;
-    if (sm.seg_key[0] == 0) {
-        const int c1 = sm.seg_cb[1];
-        nzero = c1 > 0 ? __shfl_sync(0xffffffffu, incl, c1 - 1) : 0;
-    } 
-    {
-        unsigned m = mymask;
-        int off = incl - pc;
-        const unsigned base = ((unsigned)lane << 11) | (unsigned)sm.chunk_cand[lane];
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            rowidx[off++] = (unsigned short)(base + b);
-        }
-    }
-    __syncwarp();
-    const int off_idx = COO ? a.index_offset : 0;
-    const int iv = i + off_idx;
-    for (int k = lane; k < nstore; k += 32) {
-        const unsigned c = rowidx[k] & 2047u;
-        const int j = lds_rec_j<T>(cand_addr + c * RS);
-        out_j[p0 + k] = j + off_idx;
-        if (COO) a.out_i[p0 + k] = iv;
-    }
-    int* sh = out_sh + 3 * p0;
-    const int nz = nzero < nstore ? nzero : nstore;
-    for (int e = lane; e < 3 * nz; e += 32) sh[e] = 0;
-    for (int k = nz + lane; k < nstore; k += 32) {
-        const int ck = rowidx[k] >> 11;
-        int csx, csy, csz;
-        unpack_key(sm.seg_key[sm.chunk_seg[ck]], csx, csy, csz);
-        sh[3 * k] = csx;
-        sh[3 * k + 1] = csy;
-        sh[3 * k + 2] = csz;
-    }
-    __syncwarp();
-    return cnt;
 }
 
 // position of the r-th (0-based) set bit of m (r < popc(m)): popc halving, ~33 SASS instructions
@@ -346,7 +293,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                 const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];
                 const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
                 const int nimg = nx * ny * nzz;
-                bool ok = nimg <= 32;
+                bool ok = nimg <= 32 && ntarget <= kFastMaxTargets;
                 int st = 0, cn = 0, key = kKeyEmpty, tag = 0;
                 const int coff = sp.cell_offset;
                 if (ok && lane < nimg) {
@@ -444,9 +391,24 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                     sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
                     sg.nseg = nseg; sg.total = total; sg.next_target = 0;
                 }
+                uint32_t tx = (uint32_t)total * RS;
+                if (MODE == FAST_FILL_COO) {
+                    // the consumers of a FILL stage touch no global memory but their stores: the producer gathers
+                    // each target's original index and row pointer, and TMA-copies the cell's contiguous mask block
+                    for (int l = lane; l < ntarget; l += 32) {
+                        const int ii = sorted[home_start + l].j;
+                        sg.irow[l] = ii;
+                        sg.qrow[l] = a.neighbor_ptr[ii];
+                    }
+                    tx += (uint32_t)ntarget * 128u;
+                }
                 __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
-                if (lane == 0)
-                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), (uint32_t)total * RS);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), tx);
+                    if (MODE == FAST_FILL_COO)
+                        tma_load_1d(sm.smasks[stage], reinterpret_cast<const unsigned*>(a.ws + a.L.masks) + (size_t)home_start * 32,
+                                    (uint32_t)ntarget * 128u, reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                }
                 __syncwarp();
                 if (cn > 0)
                     tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
@@ -475,7 +437,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
         const int cw = warp - 1;
         unsigned* masks = reinterpret_cast<unsigned*>(a.ws + a.L.masks);
         unsigned* mb = sm.maskbuf[cw];
-        unsigned short* rowidx = sm.rowidx[cw];
+        int* pre = sm.pre[cw];
         int stage = 0;
         uint32_t fphase = 0;
         for (;;) {
@@ -485,33 +447,15 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
             const uint32_t cand_addr = smem_base + (uint32_t)stage * kFastStageBytes;
             const int ntarget = sg.ntarget, home_off = sg.home_off, home_start = sg.home_start;
             const int nchunks = sg.nchunks;
-            int* pre = reinterpret_cast<int*>(rowidx);  // per-warp scratch: inclusive popc prefix per chunk
             if (MODE == FAST_FILL_COO) {
-                // software pipeline: the mask / row pointer of the NEXT target are in flight while this one is expanded
-                const int* __restrict__ nptr = a.neighbor_ptr;
-                int t0 = 0;
-                if (lane == 0) t0 = atomicAdd(&sg.next_target, 1);
-                t0 = __shfl_sync(0xffffffffu, t0, 0);
-                unsigned m0 = 0u;
-                int i0 = 0, q0 = 0;
-                if (t0 < ntarget) {
-                    m0 = masks[(size_t)(home_start + t0) * 32 + lane];
-                    i0 = lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t0) * RS);
-                    q0 = nptr[i0];
-                }
-                while (t0 < ntarget) {
-                    int t1 = 0;
-                    if (lane == 0) t1 = atomicAdd(&sg.next_target, 1);
-                    t1 = __shfl_sync(0xffffffffu, t1, 0);
-                    unsigned m1 = 0u;
-                    int i1 = 0, q1 = 0;
-                    if (t1 < ntarget) {
-                        m1 = masks[(size_t)(home_start + t1) * 32 + lane];
-                        i1 = lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t1) * RS);
-                        q1 = nptr[i1];
-                    }
-                    fast_expand2<T, true>(a, sg, cand_addr, m0, lane, i0, (size_t)q0, 0x7fffffff, a.out_j, a.out_shifts, mb, pre);
-                    t0 = t1; m0 = m1; i0 = i1; q0 = q1;
+                const unsigned* __restrict__ smk = sm.smasks[stage];
+                for (;;) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&sg.next_target, 1);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    if (t >= ntarget) break;
+                    fast_expand2<T, true>(a, sg, cand_addr, smk[t * 32 + lane], lane, sg.irow[t], (size_t)sg.qrow[t], 0x7fffffff,
+                                          a.out_j, a.out_shifts, mb, pre);
                 }
             } else {
                 for (;;) {
