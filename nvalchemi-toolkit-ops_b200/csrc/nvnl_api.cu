@@ -301,12 +301,18 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
         SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
+        k_gather_ptr<float><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
+                                                                              reinterpret_cast<int*>(ws + a.L.ptr_sorted));
+        NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_sweep<float, MODE_FILL_COO>(a, half_fill, fma, st);
     }
     if (dtype == NVNL_F64) {
         SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
+        k_gather_ptr<double><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
+                                                                               reinterpret_cast<int*>(ws + a.L.ptr_sorted));
+        NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_sweep<double, MODE_FILL_COO>(a, half_fill, fma, st);
     }
     return fail(-1, "nvnl_fill_coo: unsupported dtype");

@@ -19,7 +19,7 @@ namespace nvnl {
 // ------------------------------------------------------------------------------------------------
 struct WsLayout {
     size_t ctrl, sys, bbox, cell_count, cell_start, atom_cell, atom_rank, atom_ashift, sorted, sorted_ashift,
-        cursor, scan_status0, scan_status1, masks, deferred, total;
+        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, total;
     long long max_cells;  // N + S (upper bound on the number of cells, see k_grid)
 };
 
@@ -49,6 +49,7 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     L.scan_status1 = take(sizeof(unsigned long long) * (size_t)((n + 1) / kScanTile + 2));
     L.masks = take(sizeof(unsigned) * 32 * (size_t)n);   // one hit mask per (atom, 32-candidate chunk)
     L.deferred = take(sizeof(int) * (size_t)(L.max_cells + 2));
+    L.ptr_sorted = take(sizeof(int) * (size_t)(n + 4));     // neighbor_ptr gathered into cell-sorted atom order
     L.total = o;
     return L;
 }

@@ -32,7 +32,7 @@ struct FastStage {
     int seg_begin[33], seg_key[32], seg_cb[33];
     int chunk_cand[32], chunk_seg[32];
     int item, ntarget, home_off, home_start, nseg, total, nchunks, next_target;
-    int irow[kFastMaxTargets], qrow[kFastMaxTargets];  // FILL: original index and neighbor_ptr of every target
+    int qrow[kFastMaxTargets];  // FILL: neighbor_ptr (row start) of every target
 };
 
 template <typename T>
@@ -192,30 +192,54 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
     const int off_idx = COO ? a.index_offset : 0;
     const int iv = i + off_idx;
     int* sh = out_sh + 3 * p0;
-    for (int k = lane; k < nstore; k += 32) {
-        int ck = (pre[15] <= k) ? 16 : 0;
-        ck += (pre[ck + 7] <= k) ? 8 : 0;
-        ck += (pre[ck + 3] <= k) ? 4 : 0;
-        ck += (pre[ck + 1] <= k) ? 2 : 0;
-        ck += (pre[ck] <= k) ? 1 : 0;
-        const int r = k - (ck ? pre[ck - 1] : 0);
-        const int bit = nth_set_bit(mb[ck], r);
-        const int c = sm.chunk_cand[ck] + bit;
-        const int j = lds_rec_j<T>(cand_addr + (uint32_t)c * RS);
-        out_j[p0 + k] = j + off_idx;
-        if (COO) a.out_i[p0 + k] = iv;
-        if (k >= nzero) {
-            int csx, csy, csz;
-            unpack_key(sm.seg_key[sm.chunk_seg[ck]], csx, csy, csz);
-            sh[3 * k] = csx;
-            sh[3 * k + 1] = csy;
-            sh[3 * k + 2] = csz;
+    // four independent entries per lane per trip: the search / nth-bit chains interleave (ILP at low occupancy)
+    for (int k0 = lane; k0 < nstore; k0 += 128) {
+        int ckv[4], cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u;
+            const int kk = k < nstore ? k : 0;
+            int ck = (pre[15] <= kk) ? 16 : 0;
+            ck += (pre[ck + 7] <= kk) ? 8 : 0;
+            ck += (pre[ck + 3] <= kk) ? 4 : 0;
+            ck += (pre[ck + 1] <= kk) ? 2 : 0;
+            ck += (pre[ck] <= kk) ? 1 : 0;
+            const int r = kk - (ck ? pre[ck - 1] : 0);
+            const int bit = nth_set_bit(mb[ck], r);
+            ckv[u] = ck;
+            cv[u] = sm.chunk_cand[ck] + bit;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u;
+            if (k < nstore) {
+                const int j = lds_rec_j<T>(cand_addr + (uint32_t)cv[u] * RS);
+                out_j[p0 + k] = j + off_idx;
+                if (COO) a.out_i[p0 + k] = iv;
+                if (k >= nzero) {
+                    int csx, csy, csz;
+                    unpack_key(sm.seg_key[sm.chunk_seg[ckv[u]]], csx, csy, csz);
+                    sh[3 * k] = csx;
+                    sh[3 * k + 1] = csy;
+                    sh[3 * k + 2] = csz;
+                }
+            }
         }
     }
     const int nz = nzero < nstore ? nzero : nstore;
     for (int e = lane; e < 3 * nz; e += 32) sh[e] = 0;
     __syncwarp();
     return cnt;
+}
+
+// neighbor_ptr in cell-sorted atom order: ptr_sorted[k] = neighbor_ptr[sorted[k].j].  Lets the FILL producer read the
+// row pointers of a cell's targets as one coalesced load instead of a dependent gather on its critical path.
+template <typename T>
+__global__ void k_gather_ptr(const unsigned char* __restrict__ ws, WsLayout L, long long n,
+                             const int* __restrict__ neighbor_ptr, int* __restrict__ ptr_sorted) {
+    const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(ws + L.sorted);
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) ptr_sorted[k] = neighbor_ptr[sorted[k].j];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,31 +287,34 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
     if (warp == 0) {
         // =========================== producer ===========================
         const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
-        const int* cell_count = reinterpret_cast<const int*>(a.ws + a.L.cell_count);
         const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
         const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
         int* deferred = reinterpret_cast<int*>(a.ws + a.L.deferred);
         const int total_cells = unwrapped ? 0 : ctrl->total_cells;
+        const int* ptr_sorted = reinterpret_cast<const int*>(a.ws + a.L.ptr_sorted);
         int stage = 0;
         uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
+        // the queue index of the NEXT cell is always in flight (one hop off the critical path)
+        int g_next = 0;
+        if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[a.queue], 1);
         for (;;) {
             mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
             FastStage<T>& sg = sm.stage[stage];
             Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kFastStageBytes);
             bool done = false;
             for (;;) {
-                int g = 0;
-                if (lane == 0) g = atomicAdd(&ctrl->work_counter[a.queue], 1);
-                g = __shfl_sync(0xffffffffu, g, 0);
+                const int g = __shfl_sync(0xffffffffu, g_next, 0);
                 if (g >= total_cells) {
                     done = true;
                     break;
                 }
-                const int ntarget = cell_count[g];
-                if (ntarget == 0) continue;
+                if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[a.queue], 1);
+                // hop 1: the cell's run (count = start[g+1] - start[g]; cell_start has one entry past the last cell)
                 const int home_start = cell_start[g];
-                const int j0 = sorted[home_start].j;
-                const int s = a.batch_idx ? a.batch_idx[j0] : 0;
+                const int ntarget = cell_start[g + 1] - home_start;
+                if (ntarget == 0) continue;
+                int s = 0;
+                if (a.num_systems > 1) s = a.batch_idx[sorted[home_start].j];
                 const SysParams& sp = sys[s];
                 const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
                 const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];
@@ -296,6 +323,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                 bool ok = nimg <= 32 && ntarget <= kFastMaxTargets;
                 int st = 0, cn = 0, key = kKeyEmpty, tag = 0;
                 const int coff = sp.cell_offset;
+                // hop 2 (all independent): the stencil images' runs and, for FILL, the targets' row pointers
+                int q0 = 0, q1 = 0;
+                if (MODE == FAST_FILL_COO && ok) {
+                    if (lane < ntarget) q0 = ptr_sorted[home_start + lane];
+                    if (lane + 32 < ntarget) q1 = ptr_sorted[home_start + lane + 32];
+                }
                 if (ok && lane < nimg) {
                     const int local = g - coff;
                     const int cx = local % cpd0, cy = (local / cpd0) % cpd1, cz = local / (cpd0 * cpd1);
@@ -308,8 +341,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                     if (sp.pbc[2]) divmod_floor(tz, cpd2, csz, tz); else in = in && tz >= 0 && tz < cpd2;
                     if (in) {
                         const int gc = coff + tx + cpd0 * (ty + cpd1 * tz);
-                        cn = cell_count[gc];
                         st = cell_start[gc];
+                        cn = cell_start[gc + 1] - st;
                         if (cn > 0) key = pack_key(csx, csy, csz);
                     }
                     tag = (dx == 0 && dy == 0 && dz == 0) ? 1 : 0;
@@ -393,13 +426,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                 }
                 uint32_t tx = (uint32_t)total * RS;
                 if (MODE == FAST_FILL_COO) {
-                    // the consumers of a FILL stage touch no global memory but their stores: the producer gathers
-                    // each target's original index and row pointer, and TMA-copies the cell's contiguous mask block
-                    for (int l = lane; l < ntarget; l += 32) {
-                        const int ii = sorted[home_start + l].j;
-                        sg.irow[l] = ii;
-                        sg.qrow[l] = a.neighbor_ptr[ii];
-                    }
+                    // the consumers of a FILL stage touch no global memory but their stores: the producer brings in the
+                    // targets' row pointers (pre-gathered into sorted order) and TMA-copies the cell's mask block
+                    if (lane < ntarget) sg.qrow[lane] = q0;
+                    if (lane + 32 < ntarget) sg.qrow[lane + 32] = q1;
                     tx += (uint32_t)ntarget * 128u;
                 }
                 __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
@@ -454,7 +484,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                     if (lane == 0) t = atomicAdd(&sg.next_target, 1);
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntarget) break;
-                    fast_expand2<T, true>(a, sg, cand_addr, smk[t * 32 + lane], lane, sg.irow[t], (size_t)sg.qrow[t], 0x7fffffff,
+                    fast_expand2<T, true>(a, sg, cand_addr, smk[t * 32 + lane], lane,
+                                          lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t) * RS), (size_t)sg.qrow[t], 0x7fffffff,
                                           a.out_j, a.out_shifts, mb, pre);
                 }
             } else {
