@@ -29,8 +29,8 @@ enum FastMode { FAST_COUNT = 0, FAST_FILL_COO = 1, FAST_MATRIX = 2 };
 template <typename T>
 struct FastStage {
     T segS[32 * 3];
-    int seg_begin[33], seg_key[32], seg_cb[33];
-    int chunk_cand[32], chunk_seg[32];
+    int seg_begin[33], seg_key[32];
+    int chunk_seg[32];  // segment of the first candidate of each dense 32-candidate chunk
     int item, ntarget, home_off, home_start, nseg, total, nchunks, next_target;
     int qrow[kFastMaxTargets];  // FILL: neighbor_ptr (row start) of every target
 };
@@ -99,61 +99,59 @@ __device__ __forceinline__ unsigned chunk_mask(uint32_t addr, T xi, T yi, T zi, 
 }
 
 // Phase 1: hit masks of one target atom against the staged stencil; chunk ck's ballot -> mb[ck].
+// Chunks are DENSE over the concatenated tile (candidate c lives in chunk c >> 5, bit c & 31), so a tile of
+// <= 1024 candidates never needs more than 32 mask words.  Chunks that lie entirely inside the leading zero-shift
+// segment take the lean path; every other chunk picks its shift vector per lane (a chunk may straddle segments).
 template <typename T, bool HALF, bool FMA>
 __device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand_addr, T xi, T yi, T zi, int i, T rc2,
                                            int lane, unsigned* __restrict__ mb) {
     constexpr uint32_t RS = sizeof(Rec<T>);
-    const int nseg = sm.nseg;
+    using A = Arith<T>;
     const bool l0 = lane == 0;
-    for (int sg = 0; sg < nseg; ++sg) {
-        const int b = sm.seg_begin[sg], e = sm.seg_begin[sg + 1];
-        const int key = sm.seg_key[sg];
-        int ck = sm.seg_cb[sg];
-        uint32_t addr = cand_addr + (uint32_t)(b + lane) * RS;
-        const int nfull = (e - b) >> 5, rem = (e - b) & 31;
-        if (key == 0) {
-            int k = 0;
+    const int total = sm.total;
+    const int nchunks = sm.nchunks;
+    const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;  // candidates [0, zend) have zero shift
+    const int nzfull = zend >> 5;                                // chunks entirely inside the zero-shift segment
+    uint32_t addr = cand_addr + (uint32_t)lane * RS;
+    int ck = 0;
 #pragma unroll 1
-            for (; k + 4 <= nfull; k += 4) {
-                const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                const unsigned m1 = chunk_mask<T, HALF, FMA, false, false>(addr + 32 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                const unsigned m2 = chunk_mask<T, HALF, FMA, false, false>(addr + 64 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                const unsigned m3 = chunk_mask<T, HALF, FMA, false, false>(addr + 96 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                if (l0) {
-                    if ((ck & 3) == 0) sts_v4(smem_u32(mb + ck), m0, m1, m2, m3);
-                    else { mb[ck] = m0; mb[ck + 1] = m1; mb[ck + 2] = m2; mb[ck + 3] = m3; }
-                }
-                ck += 4;
-                addr += 128 * RS;
-            }
+    for (; ck + 4 <= nzfull; ck += 4) {
+        const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+        const unsigned m1 = chunk_mask<T, HALF, FMA, false, false>(addr + 32 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+        const unsigned m2 = chunk_mask<T, HALF, FMA, false, false>(addr + 64 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+        const unsigned m3 = chunk_mask<T, HALF, FMA, false, false>(addr + 96 * RS, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+        if (l0) sts_v4(smem_u32(mb + ck), m0, m1, m2, m3);
+        addr += 128 * RS;
+    }
 #pragma unroll 1
-            for (; k < nfull; ++k) {
-                const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
-                if (l0) mb[ck] = m0;
-                ++ck;
-                addr += 32 * RS;
-            }
-            if (rem) {
-                const unsigned m0 = chunk_mask<T, HALF, FMA, false, true>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, lane < rem);
-                if (l0) mb[ck] = m0;
-            }
-        } else {
-            const T Sx = sm.segS[3 * sg], Sy = sm.segS[3 * sg + 1], Sz = sm.segS[3 * sg + 2];
+    for (; ck < nzfull; ++ck) {
+        const unsigned m0 = chunk_mask<T, HALF, FMA, false, false>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false, true);
+        if (l0) mb[ck] = m0;
+        addr += 32 * RS;
+    }
+    // remaining chunks: shifted segments, segment boundaries, the tail
+#pragma unroll 1
+    for (; ck < nchunks; ++ck) {
+        const int c = (ck << 5) + lane;
+        int sg = sm.chunk_seg[ck];
+        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;  // per lane; usually 0 or 1 step
+        const T Sx = sm.segS[3 * sg], Sy = sm.segS[3 * sg + 1], Sz = sm.segS[3 * sg + 2];
+        T x, y, z;
+        int j;
+        lds_rec(addr, x, y, z, j);
+        // (r_j - r_i) + 0 == r_j - r_i bit for bit, so zero-shift lanes can share the shifted arithmetic
+        const T dx = A::add(A::sub(x, xi), Sx), dy = A::add(A::sub(y, yi), Sy), dz = A::add(A::sub(z, zi), Sz);
+        const T d2 = dist2<T, FMA>(dx, dy, dz);
+        bool hit = (d2 < rc2) && (c < total);
+        if (HALF) {
             int csx, csy, csz;
-            unpack_key(key, csx, csy, csz);
+            unpack_key(sm.seg_key[sg], csx, csy, csz);
             const bool lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
-#pragma unroll 2
-            for (int k = 0; k < nfull; ++k) {
-                const unsigned m0 = chunk_mask<T, HALF, FMA, true, false>(addr, xi, yi, zi, i, Sx, Sy, Sz, rc2, lexpos, true);
-                if (l0) mb[ck] = m0;
-                ++ck;
-                addr += 32 * RS;
-            }
-            if (rem) {
-                const unsigned m0 = chunk_mask<T, HALF, FMA, true, true>(addr, xi, yi, zi, i, Sx, Sy, Sz, rc2, lexpos, lane < rem);
-                if (l0) mb[ck] = m0;
-            }
+            hit = hit && (i < j || (i == j && lexpos));
         }
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit);
+        if (l0) mb[ck] = m0;
+        addr += 32 * RS;
     }
 }
 
@@ -183,10 +181,14 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
     const int nstore = cnt < limit ? cnt : limit;
     mb[lane] = mymask;
     pre[lane] = incl;
-    int nzero = 0;  // hits of a leading zero-shift segment occupy the first nzero row slots
-    if (sm.seg_key[0] == 0) {
-        const int c1 = sm.seg_cb[1];
-        nzero = c1 > 0 ? __shfl_sync(0xffffffffu, incl, c1 - 1) : 0;
+    // hits of the leading zero-shift segment (candidates [0, zend)) occupy the first nzero row slots
+    int nzero = 0;
+    {
+        const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;
+        const int zc = zend >> 5, zb = zend & 31;
+        const int before = zc > 0 ? __shfl_sync(0xffffffffu, incl, (zc - 1) & 31) : 0;
+        const unsigned mz = __shfl_sync(0xffffffffu, mymask, zc & 31);
+        nzero = before + (zb ? __popc(mz & ((1u << zb) - 1u)) : 0);
     }
     __syncwarp();
     const int off_idx = COO ? a.index_offset : 0;
@@ -207,7 +209,7 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
             const int r = kk - (ck ? pre[ck - 1] : 0);
             const int bit = nth_set_bit(mb[ck], r);
             ckv[u] = ck;
-            cv[u] = sm.chunk_cand[ck] + bit;
+            cv[u] = (ck << 5) + bit;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -217,8 +219,10 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
                 out_j[p0 + k] = j + off_idx;
                 if (COO) a.out_i[p0 + k] = iv;
                 if (k >= nzero) {
+                    int sg = sm.chunk_seg[ckv[u]];
+                    while (sg + 1 < sm.nseg && cv[u] >= sm.seg_begin[sg + 1]) ++sg;
                     int csx, csy, csz;
-                    unpack_key(sm.seg_key[sm.chunk_seg[ckv[u]]], csx, csy, csz);
+                    unpack_key(sm.seg_key[sg], csx, csy, csz);
                     sh[3 * k] = csx;
                     sh[3 * k + 1] = csy;
                     sh[3 * k + 2] = csz;
@@ -365,7 +369,6 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 ok = ok && total <= cap;
                 int nseg = 1;
-                int nch = 0;
                 if (ok) {
                     if (shiftmask) {
                         const int pk = __shfl_up_sync(0xffffffffu, key, 1);
@@ -390,27 +393,15 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) 
                         sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0;
                     }
                     __syncwarp();
-                    int len = 0;
-                    if (lane < nseg) len = sg.seg_begin[lane + 1] - sg.seg_begin[lane];
-                    nch = (len + 31) >> 5;
-                    const int cbi = warp_incl_scan(nch, lane);
-                    const int nchunks = __shfl_sync(0xffffffffu, cbi, 31);
-                    ok = nchunks <= 32;
-                    if (ok) {
-                        if (lane < nseg) {
-                            const int cb = cbi - nch;
-                            sg.seg_cb[lane] = cb;
-                            const int b = sg.seg_begin[lane];
-                            for (int q = 0; q < nch; ++q) {
-                                sg.chunk_cand[cb + q] = b + 32 * q;
-                                sg.chunk_seg[cb + q] = lane;
-                            }
-                        }
-                        if (lane == 0) {
-                            sg.seg_cb[nseg] = nchunks;
-                            sg.nchunks = nchunks;
-                        }
+                    // dense chunk table: segment of the first candidate of chunk `lane`
+                    const int nchunks = (total + 31) >> 5;
+                    if (lane < nchunks) {
+                        int sgi = 0;
+                        while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
+                        sg.chunk_seg[lane] = sgi;
                     }
+                    if (!shiftmask && lane < 3) sg.segS[lane] = (T)0;  // single zero-shift segment
+                    if (lane == 0) sg.nchunks = nchunks;
                 }
                 if (!ok) {
                     // too many images / candidates for one tile: leave the cell to the general kernel

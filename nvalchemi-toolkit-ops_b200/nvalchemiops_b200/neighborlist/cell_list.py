@@ -44,7 +44,7 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
         cutoff_sq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
 
     h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
-    if cache is not None:
+    if cache is not None and any(v is not None for v in cache.values()):
         cpd, rad = _engine.get_grid(h)
         if cache.get("cells_per_dimension") is not None:
             cache["cells_per_dimension"].copy_(cpd.reshape(cache["cells_per_dimension"].shape))
