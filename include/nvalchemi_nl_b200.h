@@ -96,10 +96,12 @@ int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
 /* Multi-GPU re-assembly (north_star: batch_ptr-sharded ranks + ONE NCCL all-gather; the reference has
  * no distributed code).  Each rank fills a block [ src(stride) | dst(stride) | shifts(3*stride) ] with
  * nvnl_fill_coo (edge_index = block, shifts = block + 2*stride, num_pairs = stride); after the
- * all-gather `recv` holds n_ranks such blocks and this kernel writes the global edge_index
- * [2,total_pairs] and shifts [total_pairs,3].  counts_host: pairs per rank (HOST pointer). */
-int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, const int64_t* counts_host,
-                         int32_t* edge_index, int64_t total_pairs, int32_t* shifts, void* stream);
+ * all-gather `recv` holds n_ranks such blocks, block_stride_ints int32 apart (>= 5*stride_pairs; ranks may
+ * append metadata after the payload), and this kernel writes the global edge_index [2,total_pairs] and
+ * shifts [total_pairs,3].  counts_host: pairs per rank (HOST pointer). */
+int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, int64_t block_stride_ints,
+                         const int64_t* counts_host, int32_t* edge_index, int64_t total_pairs, int32_t* shifts,
+                         void* stream);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t nvnl_launch_count(void);

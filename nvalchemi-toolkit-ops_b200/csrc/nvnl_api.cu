@@ -207,14 +207,15 @@ struct RankOffsets {
 
 // Re-assemble the global COO arrays from the all-gathered per-rank blocks
 //   recv[g] = [ src (stride) | dst (stride) | shifts (3*stride) ]  (int32, stride = padded pair count)
-__global__ void k_unpack_gathered(const int* __restrict__ recv, int n_ranks, long long stride, RankOffsets ro,
-                                  int* __restrict__ edge_index, long long total, int* __restrict__ shifts) {
+__global__ void k_unpack_gathered(const int* __restrict__ recv, int n_ranks, long long stride, long long block_stride,
+                                  RankOffsets ro, int* __restrict__ edge_index, long long total,
+                                  int* __restrict__ shifts) {
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += nthreads) {
         int g = 0;
         while (g + 1 < n_ranks && p >= ro.off[g + 1]) ++g;
         const long long q = p - ro.off[g];
-        const int* blk = recv + (long long)g * 5 * stride;
+        const int* blk = recv + (long long)g * block_stride;
         edge_index[p] = blk[q];
         edge_index[total + p] = blk[stride + q];
         shifts[3 * p] = blk[2 * stride + 3 * q];
@@ -353,8 +354,10 @@ int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
     return 0;
 }
 
-int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, const int64_t* counts_host,
-                         int32_t* edge_index, int64_t total_pairs, int32_t* shifts, void* stream) {
+int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, int64_t block_stride_ints,
+                         const int64_t* counts_host, int32_t* edge_index, int64_t total_pairs, int32_t* shifts,
+                         void* stream) {
+    if (block_stride_ints < 5 * stride_pairs) return fail(-1, "nvnl_unpack_gathered: block stride smaller than the payload");
     if (n_ranks <= 0 || n_ranks > 64) return fail(-1, "nvnl_unpack_gathered: n_ranks must be in [1, 64]");
     if (!counts_host) return fail(-1, "nvnl_unpack_gathered: null counts");
     RankOffsets ro;
@@ -370,7 +373,8 @@ int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pa
     long long blocks = (total_pairs + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_unpack_gathered<<<(unsigned)blocks, 256, 0, st>>>(recv, n_ranks, stride_pairs, ro, edge_index, total_pairs, shifts);
+    k_unpack_gathered<<<(unsigned)blocks, 256, 0, st>>>(recv, n_ranks, stride_pairs, block_stride_ints, ro, edge_index,
+                                                        total_pairs, shifts);
     NVNL_CHECK_LAUNCH("k_unpack_gathered");
     return 0;
 }

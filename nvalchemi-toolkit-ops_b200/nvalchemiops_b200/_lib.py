@@ -33,7 +33,7 @@ _SIGNATURES = {
     "nvnl_fill_matrix": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_get_grid": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
-    "nvnl_unpack_gathered": (c_int, [c_void_p, c_int32, c_int64, ctypes.POINTER(c_int64), c_void_p, c_int64,
+    "nvnl_unpack_gathered": (c_int, [c_void_p, c_int32, c_int64, c_int64, ctypes.POINTER(c_int64), c_void_p, c_int64,
                                      c_void_p, c_void_p]),
 }
 

@@ -148,17 +148,13 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
 
         edge = torch.empty((2, P), dtype=torch.int32, device=dev)
         shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
-        # the unpack kernel reads [src|dst|shifts] blocks of stride 5*pmax: strip the num_neighbors tail first
-        recv2 = recv.reshape(world, blk)
-        payload = recv2[:, :5 * pmax].contiguous() if nmax else recv2
         cnt_arr = (ctypes.c_int64 * world)(*counts)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().nvnl_unpack_gathered(ctypes.c_void_p(payload.data_ptr()), world, pmax, cnt_arr,
+            _lib.check(_lib.lib().nvnl_unpack_gathered(ctypes.c_void_p(recv.data_ptr()), world, pmax, blk, cnt_arr,
                                                        ctypes.c_void_p(edge.data_ptr()), P,
                                                        ctypes.c_void_p(shifts.data_ptr()),
                                                        ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                        "nvnl_unpack_gathered")
-            payload.record_stream(torch.cuda.current_stream(dev))
     else:
         edge, shifts = _torch_unpack(recv, world, pmax, nmax, counts, natoms, P, dev)
     num_all = torch.cat([recv[g * blk + 5 * pmax: g * blk + 5 * pmax + natoms[g]] for g in range(world)])

@@ -327,3 +327,48 @@ def test_large_cells_multi_tile_path():
         nm, num, sh = _nl().cell_list(pos.to(DEV), 5.5, cell.to(DEV), pbc.to(DEV), max_neighbors=2048)
         assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), mode
         _check_matrix_padding(nm, num, sh, 3000)
+
+
+def test_sharded_blocks_fill_and_unpack_on_one_gpu():
+    """The multi-GPU data path without the collective: two 'ranks' are emulated on one device — each fills its
+    [src | dst | shifts | num] block with global indices (index_offset), the blocks are concatenated the way
+    all_gather_into_tensor would, and nvnl_unpack_gathered re-assembles the global COO arrays."""
+    import ctypes
+
+    from nvalchemiops_b200 import _lib
+    from nvalchemiops_b200.neighborlist import _engine
+    from nvalchemiops_b200.neighborlist.distributed import partition_systems
+
+    pos, cell, pbc, bidx, bptr = bench_batch(10, 300, 700, seed=8, mixed_pbc=True)
+    want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1024))
+    pos, cell, pbc, bptr_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV), bptr.to(DEV)
+    world = 2
+    parts = partition_systems(bptr.tolist(), world)
+    locals_ = []
+    for (s0, s1) in parts:
+        a0, a1 = int(bptr[s0]), int(bptr[s1])
+        lptr = (bptr_d[s0:s1 + 1] - a0).to(torch.int32)
+        lidx = torch.repeat_interleave(torch.arange(s1 - s0, dtype=torch.int32, device=DEV), (lptr[1:] - lptr[:-1]).long())
+        h = _engine.build(pos[a0:a1], 6.0, cell[s0:s1], pbc[s0:s1], batch_idx=lidx, batch_ptr=lptr)
+        num, ptr = _engine.count(h, 36.0)
+        total = _engine.status(h)[0]
+        locals_.append((h, num, ptr, total, a0, a1))
+    pmax = max(t[3] for t in locals_)
+    nmax = max(t[5] - t[4] for t in locals_)
+    blk = 5 * pmax + nmax
+    recv = torch.full((world * blk,), -7, dtype=torch.int32, device=DEV)
+    for g, (h, num, ptr, total, a0, a1) in enumerate(locals_):
+        block = recv[g * blk:(g + 1) * blk]
+        _engine.fill_coo(h, 36.0, ptr, block[:2 * pmax], block[2 * pmax:5 * pmax], pmax, False, a0)
+        block[5 * pmax:5 * pmax + (a1 - a0)] = num
+    counts = [t[3] for t in locals_]
+    P = sum(counts)
+    edge = torch.empty((2, P), dtype=torch.int32, device=DEV)
+    shifts = torch.empty((P, 3), dtype=torch.int32, device=DEV)
+    cnt_arr = (ctypes.c_int64 * world)(*counts)
+    _lib.check(_lib.lib().nvnl_unpack_gathered(ctypes.c_void_p(recv.data_ptr()), world, pmax, blk, cnt_arr,
+                                               ctypes.c_void_p(edge.data_ptr()), P, ctypes.c_void_p(shifts.data_ptr()),
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "unpack")
+    torch.cuda.synchronize()
+    assert np.array_equal(ro.records_from_coo(edge.cpu(), shifts.cpu()), want)
+    assert (edge[0, 1:] >= edge[0, :-1]).all()
