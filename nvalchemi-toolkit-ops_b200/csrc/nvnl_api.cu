@@ -121,10 +121,10 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         long long blocks = (n + 2047) / 2048;
         if (blocks > (long long)sms * 4) blocks = (long long)sms * 4;
         if (blocks < 1) blocks = 1;
-        k_bbox<T><<<(unsigned)blocks, kScanThreads, 0, st>>>(ws, L, n, ns, pos, batch_idx, need_counts);
+        k_bbox<T><<<(unsigned)blocks, kSmallBlock, 0, st>>>(ws, L, n, ns, pos, batch_idx, need_counts);
         NVNL_CHECK_LAUNCH("k_bbox");
     }
-    k_grid<<<1, kScanThreads, 0, st>>>(ws, L, ns, cutoff);
+    k_grid<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff);
     NVNL_CHECK_LAUNCH("k_grid");
     const bool vec = (reinterpret_cast<uintptr_t>(pos) % 16) == 0;
     {

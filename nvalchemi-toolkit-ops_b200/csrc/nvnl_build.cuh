@@ -138,7 +138,7 @@ __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, 
     SysParams* sys = reinterpret_cast<SysParams*>(ws + L.sys);
     long long* bbox = reinterpret_cast<long long*>(ws + L.bbox);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
-    __shared__ long long s_red[6][kScanThreads / 32];
+    __shared__ long long s_red[6][kSmallBlock / 32];
     __shared__ int s_cnt;
     const long long chunk = 2048;
     for (long long base = (long long)blockIdx.x * chunk; base < n; base += (long long)gridDim.x * chunk) {
@@ -246,7 +246,7 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
     SysParams* sys = reinterpret_cast<SysParams*>(ws + L.sys);
     const long long* bbox = reinterpret_cast<const long long*>(ws + L.bbox);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
-    __shared__ int s_warp[kScanThreads / 32];
+    __shared__ int s_warp[kSmallBlock / 32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();

@@ -16,8 +16,9 @@ constexpr int kCandBytes = 16384;                  // staged candidate records p
 constexpr int kRowCap = 160;                       // per-warp staged hits before a flush
 constexpr int kMaxImg = 128;                       // cell images handled per batch (5^3 = 125 fits)
 constexpr int kScanItems = 8;                      // items per thread in the look-back scan
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;                 // 8192-element tiles: the serial look-back chain is 4x shorter
 constexpr int kScanTile = kScanItems * kScanThreads;
+constexpr int kSmallBlock = 256;                   // block size of the per-system / bounding-box kernels
 
 enum SweepMode { MODE_COUNT = 0, MODE_FILL_COO = 1, MODE_FILL_MATRIX = 2 };
 
