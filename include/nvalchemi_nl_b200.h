@@ -82,16 +82,43 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
  * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of
  * neighbor_matrix [n_atoms,max_neighbors], neighbor_matrix_shifts [n_atoms,max_neighbors,3] and
  * num_neighbors [n_atoms] is written exactly once.  num_neighbors keeps counting past
- * max_neighbors (neighbor_utils.py:139-147). */
+ * max_neighbors (neighbor_utils.py:139-147).  pad_rows = 0 leaves the unused slots untouched — the bare
+ * query_cell_list op, which does not reset its outputs either (cell_list.py:892-1034). */
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                      double cutoff_sq, int half_fill, int fma, int32_t* neighbor_matrix,
                      int32_t* neighbor_matrix_shifts, int32_t* num_neighbors, int32_t max_neighbors,
-                     int32_t fill_value, void* stream);
+                     int32_t fill_value, int32_t pad_rows, void* stream);
 
 /* Introspection for tests / rebuild detection: copies the per-system grid (cells per dimension and
  * stencil radius, int32 [n_systems,3] each, device pointers, either may be NULL). */
 int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int32_t* cells_per_dimension,
                   int32_t* neighbor_search_radius, void* stream);
+
+/* ---- split build/query workflow and rebuild detection ------------------------------------------ */
+
+/* Fills reference-shaped cache tensors (neighbor_utils.py:494-539) from the workspace for callers that inspect them;
+ * any pointer may be NULL.  Values describe THIS implementation's grid.  cache_cells = length of the two per-cell
+ * arrays (entries past the number of cells are zeroed). */
+int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                      int32_t* cells_per_dimension, int32_t* neighbor_search_radius, int32_t* atom_periodic_shifts,
+                      int32_t* atom_to_cell_mapping, int32_t* atoms_per_cell_count, int32_t* cell_atom_start_indices,
+                      int64_t cache_cells, int32_t* cell_atom_list, void* stream);
+
+/* query_cell_list with moved atoms (cell_list.py:1108-1192): re-gathers `positions` into the cell-sorted records
+ * without re-binning, so the next nvnl_count / nvnl_fill_* evaluates distances with the current coordinates against
+ * the cell assignment of the last nvnl_build (valid while no atom moved more than (cell width - cutoff)/2). */
+int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
+                           void* stream);
+
+/* cell_list_needs_rebuild (rebuild_detection.py:36-121, 258-383): *flag (device int32) = 1 if any atom's cell under
+ * the grid of the last nvnl_build differs from its stored cell, else 0. */
+int nvnl_cells_changed(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
+                       const int32_t* batch_idx, int32_t* flag, void* stream);
+
+/* neighbor_list_needs_rebuild (rebuild_detection.py:168-217, 386-503): *flag = 1 if any atom moved farther than
+ * `threshold` from its reference position.  No workspace involved. */
+int nvnl_moved_beyond(const void* reference_positions, const void* current_positions, int dtype, int64_t n_atoms,
+                      double threshold, int32_t* flag, void* stream);
 
 /* Multi-GPU re-assembly (north_star: batch_ptr-sharded ranks + ONE NCCL all-gather; the reference has
  * no distributed code).  Each rank fills a block [ src(stride) | dst(stride) | shifts(3*stride) ] with

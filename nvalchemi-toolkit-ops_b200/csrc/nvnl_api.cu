@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "../../include/nvalchemi_nl_b200.h"
+#include "nvnl_cache.cuh"
 #include "nvnl_fast.cuh"
 
 using namespace nvnl;
@@ -30,15 +31,23 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 int rec_bytes(int dtype) { return dtype == NVNL_F64 ? (int)sizeof(Rec<double>) : (int)sizeof(Rec<float>); }
 
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 
 constexpr size_t kSweepSmemBytes = (size_t)kCandBytes + (size_t)kSweepWarps * kRowCap * 4 * sizeof(int) + sizeof(SweepSmem);
@@ -46,7 +55,8 @@ constexpr size_t kSweepSmemBytes = (size_t)kCandBytes + (size_t)kSweepWarps * kR
 template <typename T, int MODE, bool HALF, bool FMA>
 int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
     auto kern = k_sweep<T, MODE, HALF, FMA>;
-    static int blocks_per_sm = 0;  // one static per instantiation
+    static int bps[kMaxDevices] = {0};  // per instantiation and device (function attributes are per device)
+    int& blocks_per_sm = bps[current_device()];
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemBytes);
         if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_sweep)", e);
@@ -67,7 +77,8 @@ template <typename T, int MODE, bool HALF, bool FMA>
 int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     auto kern = k_fast<T, MODE, HALF, FMA>;
     constexpr size_t smem = fast_smem_bytes<T>();
-    static int blocks_per_sm = 0;
+    static int bps[kMaxDevices] = {0};
+    int& blocks_per_sm = bps[current_device()];
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_fast)", e);
@@ -321,7 +332,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
 
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                      double cutoff_sq, int half_fill, int fma, int32_t* neighbor_matrix, int32_t* neighbor_matrix_shifts,
-                     int32_t* num_neighbors, int32_t max_neighbors, int32_t fill_value, void* stream) {
+                     int32_t* num_neighbors, int32_t max_neighbors, int32_t fill_value, int32_t pad_rows, void* stream) {
     if (!workspace || !num_neighbors || n_atoms <= 0 || max_neighbors < 0)
         return fail(-1, "nvnl_fill_matrix: bad arguments");
     if (max_neighbors > 0 && (!neighbor_matrix || !neighbor_matrix_shifts))
@@ -331,13 +342,13 @@ int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_syst
     if (dtype == NVNL_F32) {
         SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_matrix = neighbor_matrix; a.out_shifts = neighbor_matrix_shifts; a.num_neighbors = num_neighbors;
-        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2;
+        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2; a.pad = pad_rows ? 1 : 0;
         return launch_sweep<float, MODE_FILL_MATRIX>(a, half_fill, fma, st);
     }
     if (dtype == NVNL_F64) {
         SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_matrix = neighbor_matrix; a.out_shifts = neighbor_matrix_shifts; a.num_neighbors = num_neighbors;
-        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2;
+        a.max_neighbors = max_neighbors; a.fill_value = fill_value; a.queue = 2; a.pad = pad_rows ? 1 : 0;
         return launch_sweep<double, MODE_FILL_MATRIX>(a, half_fill, fma, st);
     }
     return fail(-1, "nvnl_fill_matrix: unsupported dtype");
@@ -351,6 +362,86 @@ int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
     k_get_grid<<<(n_systems + 127) / 128, 128, 0, st>>>(static_cast<const unsigned char*>(workspace), L, n_systems,
                                                        cells_per_dimension, neighbor_search_radius);
     NVNL_CHECK_LAUNCH("k_get_grid");
+    return 0;
+}
+
+int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                      int32_t* cells_per_dimension, int32_t* neighbor_search_radius, int32_t* atom_periodic_shifts,
+                      int32_t* atom_to_cell_mapping, int32_t* atoms_per_cell_count, int32_t* cell_atom_start_indices,
+                      int64_t cache_cells, int32_t* cell_atom_list, void* stream) {
+    if (!workspace || n_atoms <= 0 || n_systems <= 0 || cache_cells < 0) return fail(-1, "nvnl_export_cache: bad arguments");
+    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+    long long work = n_atoms > cache_cells ? n_atoms : cache_cells;
+    unsigned blocks = (unsigned)((work + 255) / 256);
+    if (blocks > (unsigned)sm_count() * 16) blocks = (unsigned)sm_count() * 16;
+    if (dtype == NVNL_F32)
+        k_export_cache<float><<<blocks, 256, 0, st>>>(ws, L, n_atoms, n_systems, batch_idx, cells_per_dimension,
+                                                     neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                                                     atoms_per_cell_count, cell_atom_start_indices, cache_cells, cell_atom_list);
+    else if (dtype == NVNL_F64)
+        k_export_cache<double><<<blocks, 256, 0, st>>>(ws, L, n_atoms, n_systems, batch_idx, cells_per_dimension,
+                                                      neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                                                      atoms_per_cell_count, cell_atom_start_indices, cache_cells, cell_atom_list);
+    else
+        return fail(-1, "nvnl_export_cache: unsupported dtype");
+    NVNL_CHECK_LAUNCH("k_export_cache");
+    return 0;
+}
+
+int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
+                           void* stream) {
+    if (!workspace || !positions || n_atoms <= 0) return fail(-1, "nvnl_refresh_positions: bad arguments");
+    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    const unsigned blocks = (unsigned)((n_atoms + 255) / 256);
+    if (dtype == NVNL_F32)
+        k_refresh_positions<float><<<blocks, 256, 0, st>>>(ws, L, n_atoms, static_cast<const float*>(positions));
+    else if (dtype == NVNL_F64)
+        k_refresh_positions<double><<<blocks, 256, 0, st>>>(ws, L, n_atoms, static_cast<const double*>(positions));
+    else
+        return fail(-1, "nvnl_refresh_positions: unsupported dtype");
+    NVNL_CHECK_LAUNCH("k_refresh_positions");
+    return 0;
+}
+
+int nvnl_cells_changed(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
+                       const int32_t* batch_idx, int32_t* flag, void* stream) {
+    if (!workspace || !positions || !flag || n_atoms <= 0) return fail(-1, "nvnl_cells_changed: bad arguments");
+    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_cells_changed: memset", e);
+    const unsigned blocks = (unsigned)((n_atoms + 255) / 256);
+    if (dtype == NVNL_F32)
+        k_cells_changed<float><<<blocks, 256, 0, st>>>(ws, L, n_atoms, n_systems, static_cast<const float*>(positions), batch_idx, flag);
+    else if (dtype == NVNL_F64)
+        k_cells_changed<double><<<blocks, 256, 0, st>>>(ws, L, n_atoms, n_systems, static_cast<const double*>(positions), batch_idx, flag);
+    else
+        return fail(-1, "nvnl_cells_changed: unsupported dtype");
+    NVNL_CHECK_LAUNCH("k_cells_changed");
+    return 0;
+}
+
+int nvnl_moved_beyond(const void* reference_positions, const void* current_positions, int dtype, int64_t n_atoms,
+                      double threshold, int32_t* flag, void* stream) {
+    if (!reference_positions || !current_positions || !flag || n_atoms <= 0) return fail(-1, "nvnl_moved_beyond: bad arguments");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_moved_beyond: memset", e);
+    const unsigned blocks = (unsigned)((n_atoms + 255) / 256);
+    if (dtype == NVNL_F32)
+        k_moved_beyond<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(reference_positions),
+                                                     static_cast<const float*>(current_positions), n_atoms, (float)threshold, flag);
+    else if (dtype == NVNL_F64)
+        k_moved_beyond<double><<<blocks, 256, 0, st>>>(static_cast<const double*>(reference_positions),
+                                                      static_cast<const double*>(current_positions), n_atoms, threshold, flag);
+    else
+        return fail(-1, "nvnl_moved_beyond: unsupported dtype");
+    NVNL_CHECK_LAUNCH("k_moved_beyond");
     return 0;
 }
 

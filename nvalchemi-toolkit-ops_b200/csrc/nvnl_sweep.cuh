@@ -40,6 +40,7 @@ struct SweepArgs {
     int fill_value;
     int index_offset;         // added to every atom index written to COO outputs (rank sharding)
     int queue;                // which Ctrl::work_counter this launch uses
+    int pad;                  // FILL_MATRIX: write fill_value / zero shifts into the unused slots of every row
 };
 
 constexpr int kKeyEmpty = 0x7fffffff;
@@ -108,9 +109,11 @@ __device__ __forceinline__ void finish_matrix_row(const SweepArgs<T>& a, int lan
     const int M = a.max_neighbors;
     const int used = total < M ? total : M;
     const size_t p0 = (size_t)i * (size_t)M;
-    for (int k = used + lane; k < M; k += 32) a.neighbor_matrix[p0 + k] = a.fill_value;
-    int* sh = a.out_shifts + 3 * p0;
-    for (int e = 3 * used + lane; e < 3 * M; e += 32) sh[e] = 0;
+    if (a.pad) {
+        for (int k = used + lane; k < M; k += 32) a.neighbor_matrix[p0 + k] = a.fill_value;
+        int* sh = a.out_shifts + 3 * p0;
+        for (int e = 3 * used + lane; e < 3 * M; e += 32) sh[e] = 0;
+    }
     if (lane == 0) a.num_neighbors[i] = total;
 }
 

@@ -125,8 +125,9 @@ def status(h: CellListHandle):
 
 
 def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, fill_value,
-                 half_fill=False):
-    """Fill the three padded outputs in place (nvnl_fill_matrix): no host sync, graph-capturable."""
+                 half_fill=False, pad_rows=True):
+    """Fill the three padded outputs in place (nvnl_fill_matrix): no host sync, graph-capturable.
+    ``pad_rows=False`` leaves the unused slots of every row untouched (the bare query op)."""
     for t, nm in ((neighbor_matrix, "neighbor_matrix"), (neighbor_matrix_shifts, "neighbor_matrix_shifts"),
                   (num_neighbors, "num_neighbors")):
         _require_cuda(t, nm)
@@ -141,7 +142,7 @@ def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_
             L.nvnl_fill_matrix(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
                                int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_matrix),
                                _ptr(neighbor_matrix_shifts), _ptr(num_neighbors), M, int(fill_value),
-                               _stream(h.device)),
+                               int(bool(pad_rows)), _stream(h.device)),
             "nvnl_fill_matrix",
         )
 
@@ -200,3 +201,66 @@ def get_grid(h: CellListHandle):
         _lib.check(L.nvnl_get_grid(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(cpd), _ptr(rad), _stream(h.device)),
                    "nvnl_get_grid")
     return cpd, rad
+
+
+def export_cache(h: CellListHandle, cells_per_dimension=None, neighbor_search_radius=None, atom_periodic_shifts=None,
+                 atom_to_cell_mapping=None, atoms_per_cell_count=None, cell_atom_start_indices=None, cell_atom_list=None):
+    """Write the reference-shaped cache tensors (int32, contiguous, on the handle's device) that are not None."""
+    tensors = (cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+               atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)
+    for t in tensors:
+        if t is not None and (t.dtype != torch.int32 or not t.is_contiguous() or t.device != h.device):
+            raise ValueError("cell-list cache tensors must be contiguous int32 tensors on the positions' device")
+    ncache = 0
+    for t in (atoms_per_cell_count, cell_atom_start_indices):
+        if t is not None:
+            ncache = t.numel() if ncache == 0 else min(ncache, t.numel())
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_export_cache(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), _ptr(cells_per_dimension),
+                                _ptr(neighbor_search_radius), _ptr(atom_periodic_shifts), _ptr(atom_to_cell_mapping),
+                                _ptr(atoms_per_cell_count), _ptr(cell_atom_start_indices), ncache, _ptr(cell_atom_list),
+                                _stream(h.device)),
+            "nvnl_export_cache",
+        )
+
+
+def refresh_positions(h: CellListHandle, positions):
+    """Re-gather ``positions`` into the sorted records without re-binning (stale-cache query)."""
+    _require_cuda(positions, "positions")
+    if positions.shape[0] != h.n or positions.dtype != h.dtype:
+        raise ValueError("positions do not match the cell list they are queried against")
+    positions = positions.contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(L.nvnl_refresh_positions(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(positions), _stream(h.device)),
+                   "nvnl_refresh_positions")
+    h.ws._nvnl_keepalive_pos = positions
+
+
+def cells_changed(h: CellListHandle, positions) -> torch.Tensor:
+    """int32 device flag [1]: 1 if any atom left the cell it was binned into by the last build."""
+    _require_cuda(positions, "current_positions")
+    positions = positions.contiguous()
+    flag = torch.empty(1, dtype=torch.int32, device=h.device)
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(L.nvnl_cells_changed(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(positions), _ptr(h.batch_idx), _ptr(flag),
+                                        _stream(h.device)), "nvnl_cells_changed")
+    return flag
+
+
+def moved_beyond(reference_positions, current_positions, threshold) -> torch.Tensor:
+    _require_cuda(current_positions, "current_positions")
+    _require_cuda(reference_positions, "reference_positions")
+    code = _dtype_code(current_positions.dtype)
+    if reference_positions.shape != current_positions.shape or reference_positions.dtype != current_positions.dtype:
+        raise ValueError("reference_positions and current_positions must have the same shape and dtype")
+    ref, cur = reference_positions.contiguous(), current_positions.contiguous()
+    flag = torch.empty(1, dtype=torch.int32, device=cur.device)
+    L = _lib.lib()
+    with torch.cuda.device(cur.device):
+        _lib.check(L.nvnl_moved_beyond(_ptr(ref), _ptr(cur), code, cur.shape[0], float(threshold), _ptr(flag),
+                                       _stream(cur.device)), "nvnl_moved_beyond")
+    return flag

@@ -6,7 +6,8 @@ from __future__ import annotations
 
 import torch
 
-from .cell_list import _run
+from . import _engine
+from .cell_list import _attach, _find_handle, _run
 
 
 def estimate_batch_cell_list_sizes(cell: torch.Tensor, pbc: torch.Tensor, cutoff: float, max_nbins: int = 1000):
@@ -60,3 +61,32 @@ def batch_cell_list(
     return _run(positions, cutoff, cell.reshape(-1, 3, 3), pbc.reshape(-1, 3), batch_idx, batch_ptr, max_neighbors,
                 half_fill, fill_value, return_neighbor_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors,
                 cache, empty_fill=empty_fill)
+
+
+def batch_build_cell_list(positions, cutoff, cell, pbc, batch_idx, cells_per_dimension, neighbor_search_radius,
+                          atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                          cell_atom_list) -> None:
+    """Batched ``build_cell_list`` (reference batch_cell_list.py:1070-1135); see ``cell_list.build_cell_list``."""
+    if positions.shape[0] == 0 or cutoff <= 0:
+        return
+    h = _engine.build(positions, cutoff, cell.reshape(-1, 3, 3), pbc.reshape(-1, 3), batch_idx=batch_idx)
+    _engine.export_cache(h, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                         atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)
+    _attach(h, cells_per_dimension, atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count,
+            cell_atom_start_indices, cell_atom_list)
+
+
+def batch_query_cell_list(positions, cell, pbc, cutoff, batch_idx, cells_per_dimension, neighbor_search_radius,
+                          atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                          cell_atom_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, half_fill=False) -> None:
+    """Batched ``query_cell_list`` — note the reference's argument order ``(positions, cell, pbc, cutoff, batch_idx, ...)``
+    (batch_cell_list.py:1139-1144)."""
+    if positions.shape[0] == 0 or cutoff <= 0:
+        return
+    h = _find_handle(cell_atom_list, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                     atom_periodic_shifts, cells_per_dimension)
+    if cutoff > h.cutoff * (1.0 + 1e-12):
+        raise ValueError(f"query cutoff {cutoff} exceeds the cutoff {h.cutoff} the cell list was built for")
+    _engine.refresh_positions(h, positions)
+    _engine.query_matrix(h, _engine.cutoff_sq_in_dtype(cutoff, positions.dtype), neighbor_matrix, neighbor_matrix_shifts,
+                         num_neighbors, 0, half_fill, pad_rows=False)

@@ -127,3 +127,84 @@ def cell_list(
     return _run(positions, cutoff, cell[:1], pbc.reshape(1, 3), None, None, max_neighbors, half_fill, fill_value,
                 return_neighbor_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, cache,
                 empty_fill=fill_value)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# split build / query (the MD workflow: build with cutoff + skin, re-query while atoms move) — reference
+# cell_list.py:1037-1192 and docs/userguide/components/neighborlist.md:421-500
+# ----------------------------------------------------------------------------------------------------------------
+_HANDLE_ATTR = "_nvnl_handle"
+
+
+def _attach(handle, *tensors):
+    for t in tensors:
+        if t is not None:
+            setattr(t, _HANDLE_ATTR, handle)
+
+
+def _find_handle(*tensors):
+    for t in tensors:
+        h = getattr(t, _HANDLE_ATTR, None) if t is not None else None
+        if h is not None:
+            return h
+    raise RuntimeError(
+        "nvalchemiops_b200: these cache tensors were not produced by build_cell_list / batch_build_cell_list of this "
+        "package (the cell list itself lives in an opaque device workspace attached to them)."
+    )
+
+
+def build_cell_list(
+    positions: torch.Tensor,
+    cutoff: float,
+    cell: torch.Tensor,
+    pbc: torch.Tensor,
+    cells_per_dimension: torch.Tensor,
+    neighbor_search_radius: torch.Tensor,
+    atom_periodic_shifts: torch.Tensor,
+    atom_to_cell_mapping: torch.Tensor,
+    atoms_per_cell_count: torch.Tensor,
+    cell_atom_start_indices: torch.Tensor,
+    cell_atom_list: torch.Tensor,
+) -> None:
+    """Build the cell list (reference cell_list.py:1037-1105).  The seven cache tensors are filled with this
+    implementation's grid / binning (for inspection and for ``cell_list_needs_rebuild``); the structure the queries
+    actually use is an opaque device workspace attached to them — pass the SAME tensor objects to ``query_cell_list``."""
+    if positions.shape[0] == 0 or cutoff <= 0:
+        return
+    cell = cell if cell.ndim == 3 else cell.unsqueeze(0)
+    h = _engine.build(positions, cutoff, cell[:1], pbc.reshape(1, 3))
+    _engine.export_cache(h, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                         atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)
+    _attach(h, cells_per_dimension, atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count,
+            cell_atom_start_indices, cell_atom_list)
+
+
+def query_cell_list(
+    positions: torch.Tensor,
+    cutoff: float,
+    cell: torch.Tensor,
+    pbc: torch.Tensor,
+    cells_per_dimension: torch.Tensor,
+    neighbor_search_radius: torch.Tensor,
+    atom_periodic_shifts: torch.Tensor,
+    atom_to_cell_mapping: torch.Tensor,
+    atoms_per_cell_count: torch.Tensor,
+    cell_atom_start_indices: torch.Tensor,
+    cell_atom_list: torch.Tensor,
+    neighbor_matrix: torch.Tensor,
+    neighbor_matrix_shifts: torch.Tensor,
+    num_neighbors: torch.Tensor,
+    half_fill: bool = False,
+) -> None:
+    """Query a (possibly stale) cell list with the current ``positions`` and a cutoff <= the build cutoff
+    (reference cell_list.py:1108-1192).  Writes hits and ``num_neighbors`` in place; like the reference op it does
+    not reset the unused slots of ``neighbor_matrix`` / ``neighbor_matrix_shifts`` (the caller pre-fills them)."""
+    if positions.shape[0] == 0 or cutoff <= 0:
+        return
+    h = _find_handle(cell_atom_list, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                     atom_periodic_shifts, cells_per_dimension)
+    if cutoff > h.cutoff * (1.0 + 1e-12):
+        raise ValueError(f"query cutoff {cutoff} exceeds the cutoff {h.cutoff} the cell list was built for")
+    _engine.refresh_positions(h, positions)
+    _engine.query_matrix(h, _engine.cutoff_sq_in_dtype(cutoff, positions.dtype), neighbor_matrix, neighbor_matrix_shifts,
+                         num_neighbors, 0, half_fill, pad_rows=False)

@@ -372,3 +372,96 @@ def test_sharded_blocks_fill_and_unpack_on_one_gpu():
     torch.cuda.synchronize()
     assert np.array_equal(ro.records_from_coo(edge.cpu(), shifts.cpu()), want)
     assert (edge[0, 1:] >= edge[0, :-1]).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# split build / query workflow and rebuild detection (reference cell_list.py:1037-1192,
+# rebuild_detection.py, docs/userguide/components/neighborlist.md:421-500)
+# ----------------------------------------------------------------------------------------------
+def _alloc_cache(n, ncell_cap, ns=None):
+    shape3 = (3,) if ns is None else (ns, 3)
+    z = lambda *s: torch.zeros(s, dtype=torch.int32, device=DEV)  # noqa: E731
+    return [z(*shape3), z(*shape3), z(n, 3), z(n, 3), z(ncell_cap), z(ncell_cap), z(n)]
+
+
+def test_build_query_split_with_moving_atoms():
+    """Build once with cutoff + skin, then re-query with displaced atoms and the bare cutoff: every query must equal
+    a from-scratch oracle run on the displaced positions (the stale cell assignment stays valid below skin/2)."""
+    nl = _nl()
+    rc, skin = 4.0, 1.0
+    for pbc_flag in ([True, True, True], [True, False, True]):
+        pos, cell, pbc = random_system(800, 22.0, torch.float32, seed=21, pbc_flag=pbc_flag)
+        cache = _alloc_cache(800, 4096)
+        nl.build_cell_list(pos.to(DEV), rc + skin, cell.to(DEV), pbc.to(DEV), *cache)
+        assert cache[0].tolist() == [4, 4, 4] or not all(pbc_flag)      # 22 / (5 * 1.001) -> 4 cells per periodic dim
+        assert int(cache[4].sum()) == 800 and sorted(cache[6].cpu().tolist()) == list(range(800))
+        g = torch.Generator().manual_seed(3)
+        cur = pos.clone()
+        for step in range(4):
+            if step:
+                cur = cur + (torch.rand(800, 3, generator=g) - 0.5) * 0.2   # |d| <= 0.17 per step, 0.52 total < skin/2... 
+            nm = torch.full((800, 64), 800, dtype=torch.int32, device=DEV)
+            sh = torch.zeros((800, 64, 3), dtype=torch.int32, device=DEV)
+            num = torch.zeros((800,), dtype=torch.int32, device=DEV)
+            nl.query_cell_list(cur.to(DEV), rc, cell.to(DEV), pbc.to(DEV), *cache, nm, sh, num)
+            want = ro.records_from_matrix(*ro.cell_list(cur, rc, cell, pbc, max_neighbors=64))
+            assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), f"step {step} pbc {pbc_flag}"
+            _check_matrix_padding(nm, num, sh, 800)   # untouched slots keep the caller's pre-fill
+        with pytest.raises(ValueError):
+            nl.query_cell_list(cur.to(DEV), rc + 2 * skin, cell.to(DEV), pbc.to(DEV), *cache, nm, sh, num)
+    with pytest.raises(RuntimeError):
+        nl.query_cell_list(cur.to(DEV), rc, cell.to(DEV), pbc.to(DEV), *_alloc_cache(800, 4096), nm, sh, num)
+
+
+def test_batch_build_query_split():
+    nl = _nl()
+    pos, cell, pbc, bidx, bptr = bench_batch(6, 200, 400, seed=12, mixed_pbc=True)
+    n = pos.shape[0]
+    cache = _alloc_cache(n, 4096, ns=6)
+    nl.batch_build_cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), bidx.to(DEV), *cache)
+    nm = torch.full((n, 256), -1, dtype=torch.int32, device=DEV)
+    sh = torch.zeros((n, 256, 3), dtype=torch.int32, device=DEV)
+    num = torch.zeros((n,), dtype=torch.int32, device=DEV)
+    nl.batch_query_cell_list(pos.to(DEV), cell.to(DEV), pbc.to(DEV), 5.0, bidx.to(DEV), *cache, nm, sh, num)
+    want = ro.records_from_matrix(*ro.batch_cell_list(pos, 5.0, cell, pbc, bidx, max_neighbors=256))
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+
+
+def test_rebuild_detection():
+    nl = _nl()
+    pos, cell, pbc = random_system(2000, 30.0, torch.float32, seed=31)
+    pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    # neighbor_list_needs_rebuild: displacement vs skin (rebuild_detection.py:168-217)
+    assert nl.neighbor_list_needs_rebuild(pos_d, pos_d.clone(), 0.5).tolist() == [False]
+    moved = pos_d.clone(); moved[1234, 1] += 0.6
+    r = nl.neighbor_list_needs_rebuild(pos_d, moved, 0.5)
+    assert r.dtype == torch.bool and r.shape == (1,) and r.tolist() == [True]
+    assert nl.neighbor_list_needs_rebuild(pos_d, moved, 0.7).tolist() == [False]
+    assert nl.check_neighbor_list_rebuild_needed(pos_d, moved, 0.5) is True
+    assert nl.neighbor_list_needs_rebuild(pos_d[:10], moved, 0.5).tolist() == [True]          # shape mismatch
+    assert nl.neighbor_list_needs_rebuild(pos_d[:0], pos_d[:0], 0.5).tolist() == [False]     # empty
+    # oracle restatement of the same predicate on random displacements
+    g = torch.Generator().manual_seed(1)
+    for thr in (0.05, 0.2, 1.0):
+        cur = pos + (torch.rand(2000, 3, generator=g) - 0.5) * 0.4
+        want = bool((np.sqrt(((cur - pos).numpy().astype(np.float64) ** 2).sum(1)) > thr).any())
+        assert nl.check_neighbor_list_rebuild_needed(pos_d, cur.to(DEV), thr) is want
+    # cell_list_needs_rebuild: cell crossing under the grid of the last build (rebuild_detection.py:36-121)
+    cache = _alloc_cache(2000, 4096)
+    nl.build_cell_list(pos_d, 5.0, cell_d, pbc_d, *cache)
+    cpd = cache[0].cpu().numpy()
+    assert cpd.tolist() == [5, 5, 5]
+    assert nl.cell_list_needs_rebuild(pos_d, cache[3], cache[0], cell_d, pbc_d).tolist() == [False]
+    w = 30.0 / 5
+    inside = pos.clone(); inside[7] = torch.tensor([2.5 * w, 2.5 * w, 2.5 * w])       # cell centre
+    cache2 = _alloc_cache(2000, 4096)
+    nl.build_cell_list(inside.to(DEV), 5.0, cell_d, pbc_d, *cache2)
+    small = inside.clone(); small[7, 0] += 0.3 * w                                      # stays in its cell
+    assert nl.check_cell_list_rebuild_needed(small.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is False
+    big = inside.clone(); big[7, 0] += 0.6 * w                                          # crosses into the next cell
+    assert nl.check_cell_list_rebuild_needed(big.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is True
+    wrap = inside.clone(); wrap[7, 0] += 30.0                                           # a full period: same cell
+    assert nl.check_cell_list_rebuild_needed(wrap.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is False
+    # the exported mapping agrees with the geometry
+    cells = torch.floor(pos / w).long().clamp(0, 4)
+    assert torch.equal(cache[3].cpu().long(), cells)
