@@ -37,12 +37,8 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
             torch.zeros((total_atoms, 0, 3), dtype=torch.int32, device=device),
         )
 
-    user_buffers = neighbor_matrix is not None and neighbor_matrix_shifts is not None and num_neighbors is not None
-    if max_neighbors is None and not user_buffers:
-        max_neighbors = estimate_max_neighbors(cutoff)
     if cutoff_sq is None:
         cutoff_sq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
-
     h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
     if cache is not None and any(v is not None for v in cache.values()):
         cpd, rad = _engine.get_grid(h)
@@ -50,7 +46,17 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
             cache["cells_per_dimension"].copy_(cpd.reshape(cache["cells_per_dimension"].shape))
         if cache.get("neighbor_search_radius") is not None:
             cache["neighbor_search_radius"].copy_(rad.reshape(cache["neighbor_search_radius"].shape))
+    return _query(h, cutoff, cutoff_sq, max_neighbors, half_fill, fill_value, return_neighbor_list, neighbor_matrix,
+                  neighbor_matrix_shifts, num_neighbors)
 
+
+def _query(h, cutoff, cutoff_sq, max_neighbors, half_fill, fill_value, return_neighbor_list, neighbor_matrix,
+           neighbor_matrix_shifts, num_neighbors):
+    """One query of a built cell list: padded matrix (in place when buffers are given) or direct COO."""
+    total_atoms, device = h.n, h.device
+    user_buffers = neighbor_matrix is not None and neighbor_matrix_shifts is not None and num_neighbors is not None
+    if max_neighbors is None and not user_buffers:
+        max_neighbors = estimate_max_neighbors(cutoff)
     if return_neighbor_list and neighbor_matrix is None:
         # direct COO path: the padded matrix is never materialised
         neighbor_list, neighbor_ptr, shifts, _num = _engine.query_coo(h, cutoff_sq, half_fill, max_neighbors)

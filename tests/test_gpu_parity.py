@@ -465,3 +465,27 @@ def test_rebuild_detection():
     # the exported mapping agrees with the geometry
     cells = torch.floor(pos / w).long().clamp(0, 4)
     assert torch.equal(cache[3].cpu().long(), cells)
+
+
+def test_dual_cutoff_routes():
+    """cutoff2 -> naive_dual_cutoff: one build, two queries; reference return arity (neighborlist.py:150-176)."""
+    nl = _nl()
+    pos, cell, pbc = random_system(400, 12.0, torch.float32, seed=17)
+    out = nl.neighbor_list(pos.to(DEV), 2.5, cell=cell.to(DEV), pbc=pbc.to(DEV), cutoff2=5.0, max_neighbors1=64,
+                           max_neighbors2=256)
+    assert len(out) == 6
+    for k, rc, M in ((0, 2.5, 64), (3, 5.0, 256)):
+        want = ro.records_from_matrix(*ro.cell_list(pos, rc, cell, pbc, max_neighbors=M))
+        assert out[k].shape == (400, M)
+        assert np.array_equal(_records_gpu_matrix(out[k], out[k + 1], out[k + 2]), want)
+    out = nl.neighbor_list(pos.to(DEV), 2.5, cutoff2=4.0, max_neighbors1=64, max_neighbors2=128)   # no PBC: 4-tuple
+    assert len(out) == 4
+    free = torch.tensor([False] * 3)
+    for k, rc, M in ((0, 2.5, 64), (2, 4.0, 128)):
+        want = ro.records_from_matrix(*ro.cell_list(pos, rc, torch.eye(3).reshape(1, 3, 3), free, max_neighbors=M))
+        assert np.array_equal(ro.records_from_matrix(out[k].cpu(), out[k + 1].cpu()), want)
+    out = nl.neighbor_list(pos.to(DEV), 2.5, cell=cell.to(DEV), pbc=pbc.to(DEV), cutoff2=5.0, return_neighbor_list=True,
+                           max_neighbors1=64, max_neighbors2=256)
+    assert len(out) == 6 and out[0].shape[0] == 2 and out[3].shape[0] == 2
+    assert np.array_equal(ro.records_from_coo(out[3].cpu(), out[5].cpu()),
+                          ro.records_from_matrix(*ro.cell_list(pos, 5.0, cell, pbc, max_neighbors=256)))
