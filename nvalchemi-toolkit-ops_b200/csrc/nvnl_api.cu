@@ -76,7 +76,7 @@ int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
 template <typename T, int MODE, bool HALF, bool FMA>
 int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     auto kern = k_fast<T, MODE, HALF, FMA>;
-    constexpr size_t smem = fast_smem_bytes<T>();
+    constexpr size_t smem = fast_smem_bytes<T, MODE>();
     static int bps[kMaxDevices] = {0};
     int& blocks_per_sm = bps[current_device()];
     if (blocks_per_sm == 0) {

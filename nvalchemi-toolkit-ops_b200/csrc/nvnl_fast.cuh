@@ -35,19 +35,20 @@ struct FastStage {
     int qrow[kFastMaxTargets];  // FILL: neighbor_ptr (row start) of every target
 };
 
-template <typename T>
+template <typename T, int MODE>
 struct FastSmem {
     FastStage<T> stage[kFastStages];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                // producer scratch (shift sort)
     alignas(16) unsigned maskbuf[kFastCons][32];                 // per consumer warp: hit masks of the current row
     int pre[kFastCons][32];                                      // per consumer warp: inclusive popc prefix per chunk
-    alignas(16) unsigned smasks[kFastStages][kFastMaxTargets * 32];  // FILL: the cell's hit masks (TMA from global)
+    // FILL only: the cell's hit masks (TMA from global); other modes keep a token array so 5 CTAs fit per SM
+    alignas(16) unsigned smasks[kFastStages][MODE == 1 ? kFastMaxTargets * 32 : 4];
     unsigned long long full[kFastStages], empty[kFastStages];    // mbarriers of the ring
 };
 
-template <typename T>
+template <typename T, int MODE>
 constexpr size_t fast_smem_bytes() {
-    return (size_t)kFastStages * kFastStageBytes + sizeof(FastSmem<T>);
+    return (size_t)kFastStages * kFastStageBytes + sizeof(FastSmem<T, MODE>);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -256,9 +257,9 @@ __global__ void k_gather_ptr(const unsigned char* __restrict__ ws, WsLayout L, l
 // No CTA-wide barrier in the steady state: the setup latency of cell k+1 hides behind the sweep of cell k.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HALF, bool FMA>
-__global__ void __launch_bounds__(kFastThreads, 4) k_fast(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const SweepArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FastSmem<T>& sm = *reinterpret_cast<FastSmem<T>*>(smem_raw + (size_t)kFastStages * kFastStageBytes);
+    FastSmem<T, MODE>& sm = *reinterpret_cast<FastSmem<T, MODE>*>(smem_raw + (size_t)kFastStages * kFastStageBytes);
     const uint32_t smem_base = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
     constexpr int cap = kCandBytes / (int)RS;
