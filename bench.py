@@ -219,6 +219,9 @@ def main():
     import torch.distributed as dist
 
     if world > 1:
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (set on some boxes) prints a banner to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from nvalchemiops_b200 import launch_count
