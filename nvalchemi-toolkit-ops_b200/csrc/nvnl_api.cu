@@ -50,7 +50,7 @@ int sm_count() {
     return n[dev];
 }
 
-constexpr size_t kSweepSmemBytes = (size_t)kCandBytes + (size_t)kSweepWarps * kRowCap * 4 * sizeof(int) + sizeof(SweepSmem);
+constexpr size_t kSweepSmemBytes = (size_t)kSweepCandBytes + (size_t)kSweepWarps * kRowCap * 4 * sizeof(int) + sizeof(SweepSmem);
 
 template <typename T, int MODE, bool HALF, bool FMA>
 int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {

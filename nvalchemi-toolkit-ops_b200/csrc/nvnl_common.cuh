@@ -12,7 +12,8 @@ namespace nvnl {
 
 constexpr int kSweepThreads = 256;                 // 8 warps per CTA
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kCandBytes = 16384;                  // staged candidate records per tile (bytes)
+constexpr int kCandBytes = 16384;                  // fast kernel: staged candidate records per ring stage (bytes)
+constexpr int kSweepCandBytes = 32768;             // general kernel: one tile (records, or records + periodic images)
 constexpr int kRowCap = 160;                       // per-warp staged hits before a flush
 constexpr int kMaxImg = 128;                       // cell images handled per batch (5^3 = 125 fits)
 constexpr int kScanItems = 8;                      // items per thread in the look-back scan

@@ -62,8 +62,9 @@ struct SweepSmem {
     // image / piece tables (indices: position in the shift-sorted order)
     int ustart[kMaxImg], ucnt[kMaxImg], ukey[kMaxImg];
     int sstart[kMaxImg], scnt[kMaxImg], skey[kMaxImg];
-    int seg_begin[kMaxImg + 1], seg_key[kMaxImg];
-    int nseg, total, item, more, pc_img, pc_off;
+    int seg_begin[kMaxImg + 1], seg_end[kMaxImg], seg_key[kMaxImg];
+    int sfirst[kMaxImg], sdst[kMaxImg];  // aliasing plan: first image of the same cell, its tile offset
+    int nseg, total, item, more, pc_img, pc_off, aliased;
     unsigned long long mbar;
 };
 
@@ -135,7 +136,7 @@ __device__ __forceinline__ int sweep_target(const SweepArgs<T>& a, const SweepSm
     int written = written_in;
     const int nseg = sm.nseg;
     for (int sg = 0; sg < nseg; ++sg) {
-        const int b = sm.seg_begin[sg], e = sm.seg_begin[sg + 1];
+        const int b = sm.seg_begin[sg], e = sm.seg_end[sg];
         const int key = sm.seg_key[sg];
         int csx, csy, csz;
         unpack_key(key, csx, csy, csz);
@@ -227,11 +228,11 @@ __device__ __forceinline__ int sweep_target(const SweepArgs<T>& a, const SweepSm
 // k_sweep
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HALF, bool FMA>
-__global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw);
-    int* rows = reinterpret_cast<int*>(smem_raw + kCandBytes);
-    SweepSmem& sm = *reinterpret_cast<SweepSmem*>(smem_raw + kCandBytes + kSweepWarps * kRowCap * 4 * sizeof(int));
+    int* rows = reinterpret_cast<int*>(smem_raw + kSweepCandBytes);
+    SweepSmem& sm = *reinterpret_cast<SweepSmem*>(smem_raw + kSweepCandBytes + kSweepWarps * kRowCap * 4 * sizeof(int));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int* row_j = rows + warp * (4 * kRowCap);
@@ -251,8 +252,8 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
     const int* deferred = reinterpret_cast<const int*>(a.ws + a.L.deferred);
     const int total_items = unwrapped ? ctrl->total_cells : ctrl->n_deferred;
     // unwrapped inputs also stage each candidate's periodic image (int4): half the record capacity
-    const int cap = unwrapped ? (kCandBytes / 2) / (int)sizeof(Rec<T>) : kCandBytes / (int)sizeof(Rec<T>);
-    int4* cand_ash = reinterpret_cast<int4*>(smem_raw + kCandBytes / 2);
+    const int cap = unwrapped ? (kSweepCandBytes / 2) / (int)sizeof(Rec<T>) : kSweepCandBytes / (int)sizeof(Rec<T>);
+    int4* cand_ash = reinterpret_cast<int4*>(smem_raw + kSweepCandBytes / 2);
 
     if (tid == 0) {
         mbar_init(reinterpret_cast<uint64_t*>(&sm.mbar), 1);
@@ -347,13 +348,92 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
                 sm.scnt[rank] = sm.ucnt[tid];
                 sm.skey[rank] = sm.ukey[tid];
             }
-            if (tid == 0) { sm.pc_img = 0; sm.pc_off = 0; }
+            if (tid == 0) { sm.pc_img = 0; sm.pc_off = 0; sm.aliased = 0; }
             __syncthreads();
+            // Small periodic boxes repeat the same cell under several shifts (box < 2 rc: 27+ images of one cell).
+            // Find, for every image, the first image of the same cell: such a batch can be staged once per DISTINCT
+            // cell, with one segment per image aliasing the shared records.
+            if (!multi_batch && tid < kMaxImg) {
+                const int st = sm.sstart[tid], cn = sm.scnt[tid];
+                int f = tid;
+                if (cn > 0)
+                    for (int q = 0; q < tid; ++q)
+                        if (sm.scnt[q] > 0 && sm.sstart[q] == st) { f = q; break; }
+                sm.sfirst[tid] = f;
+            }
+            __syncthreads();
+            if (!multi_batch && warp == 0) {
+                int uc[4], cn4[4];
+                int lsum = 0, lall = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int p = lane * 4 + q;
+                    cn4[q] = sm.scnt[p];
+                    uc[q] = (cn4[q] > 0 && sm.sfirst[p] == p) ? cn4[q] : 0;
+                    lsum += uc[q];
+                    lall += cn4[q];
+                }
+                const int incl = warp_incl_scan(lsum, lane);
+                const int total_unique = __shfl_sync(0xffffffffu, incl, 31);
+                const int total_all = __reduce_add_sync(0xffffffffu, lall);
+                // only worth it when the plain concatenation would not fit one tile but the distinct cells do
+                if (total_all > cap && total_unique <= cap && total_unique > 0) {
+                    int run = incl - lsum;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sm.sdst[lane * 4 + q] = run;
+                        run += uc[q];
+                    }
+                    __syncwarp();
+                    // one segment per non-empty image
+                    int lseg = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) lseg += cn4[q] > 0 ? 1 : 0;
+                    const int sincl = warp_incl_scan(lseg, lane);
+                    int si = sincl - lseg;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int p = lane * 4 + q;
+                        if (cn4[q] > 0) {
+                            const int b = sm.sdst[sm.sfirst[p]];
+                            sm.seg_begin[si] = b;
+                            sm.seg_end[si] = b + cn4[q];
+                            sm.seg_key[si] = sm.skey[p];
+                            ++si;
+                        }
+                    }
+                    if (lane == 31) {
+                        sm.nseg = sincl;
+                        sm.total = total_unique;
+                        sm.more = 0;
+                        sm.aliased = 1;
+                    }
+                    if (lane == 0) {
+                        const uint32_t bytes =
+                            (uint32_t)total_unique * (uint32_t)(sizeof(Rec<T>) + (unwrapped ? sizeof(int4) : 0));
+                        mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.mbar), bytes);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int p = lane * 4 + q;
+                        if (uc[q] > 0) {
+                            tma_load_1d(cand + sm.sdst[p], sorted + sm.sstart[p], (uint32_t)uc[q] * (uint32_t)sizeof(Rec<T>),
+                                        reinterpret_cast<uint64_t*>(&sm.mbar));
+                            if (unwrapped)
+                                tma_load_1d(cand_ash + sm.sdst[p], sorted_ashift + sm.sstart[p],
+                                            (uint32_t)uc[q] * (uint32_t)sizeof(int4), reinterpret_cast<uint64_t*>(&sm.mbar));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const bool aliased = sm.aliased != 0;
 
             // ---- tiles of this batch ----
             for (;;) {
                 // plan (warp 0): which pieces of which images go into this tile, and where
-                if (warp == 0) {
+                if (warp == 0 && !aliased) {
                     const int pc_img = sm.pc_img, pc_off = sm.pc_off;
                     int avail[4], take[4], dst[4], src[4], keyv[4];
                     int lsum = 0;
@@ -431,6 +511,9 @@ __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(const SweepArgs<T> a
                             sm.total = total;
                             sm.more = (min_img < kMaxImg) ? 1 : 0;
                         }
+                        __syncwarp();
+                        const int ns_ = any_shift ? nseg : (total > 0 ? 1 : 0);
+                        for (int sgi = lane; sgi < ns_; sgi += 32) sm.seg_end[sgi] = sm.seg_begin[sgi + 1];
                     }
                     // TMA: concatenate the pieces in shared memory
                     if (total > 0) {
