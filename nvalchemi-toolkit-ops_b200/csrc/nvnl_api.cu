@@ -154,7 +154,7 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         k_scan<<<blocks, kScanThreads, 0, st>>>(reinterpret_cast<const int*>(ws + L.cell_count),
                                                reinterpret_cast<int*>(ws + L.cell_start), cnt,
                                                reinterpret_cast<unsigned long long*>(ws + L.scan_status0),
-                                               &ctrl->scan_tile[0], nullptr, nullptr);
+                                               &ctrl->scan_tile[0], nullptr, nullptr, &ctrl->total_cells);
         NVNL_CHECK_LAUNCH("k_scan(cells)");
     }
     {
@@ -195,7 +195,7 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
         const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
         k_scan<<<blocks, kScanThreads, 0, st>>>(num_neighbors, neighbor_ptr, n,
                                                reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
-                                               &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count);
+                                               &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count, nullptr);
         NVNL_CHECK_LAUNCH("k_scan(neighbors)");
     }
     return 0;

@@ -420,13 +420,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const int* __restrict__ i
                                                        unsigned long long* __restrict__ status,
                                                        int* __restrict__ tile_counter,
                                                        unsigned long long* __restrict__ total64,
-                                                       int* __restrict__ max_out) {
+                                                       int* __restrict__ max_out, const int* __restrict__ live_ptr) {
     __shared__ int s_tile;
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
     __syncthreads();
     const int tile = s_tile;
+    // inputs past *live_ptr are known to be zero and their prefixes are never read (cell histogram: only the first
+    // total_cells entries are live, the array is sized for the N + S upper bound): those tiles retire at once
+    if (live_ptr && (long long)tile * kScanTile > (long long)(*live_ptr) + 1) return;
     const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
     int v[kScanItems];
     int tsum = 0, tmax = 0;
