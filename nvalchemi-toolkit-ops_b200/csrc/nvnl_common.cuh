@@ -138,15 +138,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: a waiting warp sleeps in hardware instead of spinning through issue slots
+    // (ncu showed ~8 % of the count kernel's issued instructions in the bare try_wait/branch/yield loop)
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "NVNL_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra NVNL_DONE_%=;\n\t"
         "bra NVNL_WAIT_%=;\n\t"
         "NVNL_DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a positive multiple of 16.

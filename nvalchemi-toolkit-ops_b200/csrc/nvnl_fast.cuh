@@ -130,6 +130,13 @@ __device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand
         if (l0) mb[ck] = m0;
         addr += 32 * RS;
     }
+    if (sm.nseg == 1 && ck < nchunks) {
+        // interior cell: the only other chunk is the partial tail of the zero-shift segment
+        const unsigned m0 = chunk_mask<T, HALF, FMA, false, true>(addr, xi, yi, zi, i, 0, 0, 0, rc2, false,
+                                                                  (ck << 5) + lane < total);
+        if (l0) mb[ck] = m0;
+        ++ck;
+    }
     // remaining chunks: shifted segments, segment boundaries, the tail
 #pragma unroll 1
     for (; ck < nchunks; ++ck) {
