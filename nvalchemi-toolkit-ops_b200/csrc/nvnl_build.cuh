@@ -48,7 +48,8 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     L.scan_status0 = take(sizeof(unsigned long long) * (size_t)((L.max_cells + 2) / kScanTile + 2));
     L.scan_status1 = take(sizeof(unsigned long long) * (size_t)((n + 1) / kScanTile + 2));
     L.masks = take(sizeof(unsigned) * 32 * (size_t)n);   // one hit mask per (atom, 32-candidate chunk)
-    L.deferred = take(sizeof(int) * (size_t)(L.max_cells + 2));
+    // (cell, first target) work items the fast kernel leaves to the general kernel: <= #cells + N/32 entries
+    L.deferred = take(sizeof(int2) * (size_t)(L.max_cells + 2 + n / 32 + 1));
     L.ptr_sorted = take(sizeof(int) * (size_t)(n + 4));     // neighbor_ptr gathered into cell-sorted atom order
     L.total = o;
     return L;

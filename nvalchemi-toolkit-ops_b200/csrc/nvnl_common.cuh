@@ -15,6 +15,7 @@ constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kCandBytes = 16384;                  // fast kernel: staged candidate records per ring stage (bytes)
 constexpr int kSweepCandBytes = 32768;             // general kernel: one tile (records, or records + periodic images)
 constexpr int kRowCap = 160;                       // per-warp staged hits before a flush
+constexpr int kDeferTargets = 32;                  // target atoms per deferred work item of the general kernel
 constexpr int kMaxImg = 128;                       // cell images handled per batch (5^3 = 125 fits)
 constexpr int kScanItems = 8;                      // items per thread in the look-back scan
 constexpr int kScanThreads = 1024;                 // 8192-element tiles: the serial look-back chain is 4x shorter

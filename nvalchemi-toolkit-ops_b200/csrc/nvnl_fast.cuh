@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
         const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
         const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
         const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
-        int* deferred = reinterpret_cast<int*>(a.ws + a.L.deferred);
+        int2* deferred = reinterpret_cast<int2*>(a.ws + a.L.deferred);
         const int total_cells = unwrapped ? 0 : ctrl->total_cells;
         const int* ptr_sorted = reinterpret_cast<const int*>(a.ws + a.L.ptr_sorted);
         int stage = 0;
@@ -412,8 +412,13 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                     if (lane == 0) sg.nchunks = nchunks;
                 }
                 if (!ok) {
-                    // too many images / candidates for one tile: leave the cell to the general kernel
-                    if (lane == 0) deferred[atomicAdd(&ctrl->n_deferred, 1)] = g;
+                    // too many images / candidates / targets for one tile: leave the cell to the general kernel, as
+                    // work items of kDeferTargets target atoms each (a whole small periodic system can be one "cell")
+                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&ctrl->n_deferred, nitems);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
                     continue;
                 }
                 const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);

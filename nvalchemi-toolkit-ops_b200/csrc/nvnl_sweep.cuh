@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
     const bool unwrapped = ctrl->unwrapped != 0;
     // work source: every cell when atoms lie outside the primary image, else the cells the fast kernel
     // (nvnl_fast.cuh) deferred (too many images or candidates for its single shared-memory tile)
-    const int* deferred = reinterpret_cast<const int*>(a.ws + a.L.deferred);
+    const int2* deferred = reinterpret_cast<const int2*>(a.ws + a.L.deferred);
     const int total_items = unwrapped ? ctrl->total_cells : ctrl->n_deferred;
     // unwrapped inputs also stage each candidate's periodic image (int4): half the record capacity
     const int cap = unwrapped ? (kSweepCandBytes / 2) / (int)sizeof(Rec<T>) : kSweepCandBytes / (int)sizeof(Rec<T>);
@@ -279,8 +279,12 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
         __syncthreads();
         const int item = sm.item;
         if (item >= total_items) break;
-        const int g = unwrapped ? item : deferred[item];
-        const int ntarget = cell_count[g];
+        const int2 it = unwrapped ? make_int2(item, 0) : deferred[item];
+        const int g = it.x;
+        const int ncell_atoms = cell_count[g];
+        // targets of this work item: the whole cell (unwrapped sweep) or a kDeferTargets slice of it
+        const int t_begin = it.y;
+        const int ntarget = unwrapped ? ncell_atoms : (t_begin + kDeferTargets < ncell_atoms ? t_begin + kDeferTargets : ncell_atoms);
         const int home_start = cell_start[g];
         if (ntarget == 0) {
             __syncthreads();
@@ -547,7 +551,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
                     mbar_wait(reinterpret_cast<uint64_t*>(&sm.mbar), phase);
                     phase ^= 1u;
                     // ---- sweep: one warp per target atom ----
-                    for (int t = warp; t < ntarget; t += kSweepWarps) {
+                    for (int t = t_begin + warp; t < ntarget; t += kSweepWarps) {
                         const Rec<T> ti = sorted[home_start + t];
                         int4 ai = make_int4(0, 0, 0, 0);
                         if (unwrapped) ai = sorted_ashift[home_start + t];
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
         }
         // multi-tile rows: finalize once every tile has been swept, and re-arm the running totals
         if (multi) {
-            for (int t = warp; t < ntarget; t += kSweepWarps) {
+            for (int t = t_begin + warp; t < ntarget; t += kSweepWarps) {
                 const int i = sorted[home_start + t].j;
                 const int tot = cursor[i];
                 __syncwarp();
