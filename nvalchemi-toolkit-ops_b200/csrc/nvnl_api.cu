@@ -73,10 +73,10 @@ int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
-template <typename T, int MODE, bool HALF, bool FMA>
+template <typename T, int MODE, bool HALF, bool FMA, bool UNW>
 int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
-    auto kern = k_fast<T, MODE, HALF, FMA>;
-    constexpr size_t smem = fast_smem_bytes<T, MODE>();
+    auto kern = k_fast<T, MODE, HALF, FMA, UNW>;
+    constexpr size_t smem = fast_smem_bytes<T, MODE, UNW>();
     static int bps[kMaxDevices] = {0};
     int& blocks_per_sm = bps[current_device()];
     if (blocks_per_sm == 0) {
@@ -95,12 +95,14 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
-// Every query is two launches: the lean kernel takes the cells it can (and lists the rest), the general
-// kernel takes the listed cells — or all of them when atoms lie outside the primary periodic image.
+// Every query is three launches: the lean kernel in its wrapped and unwrapped variant (the one that does not match the
+// input retires at once) takes the cells it can and lists the rest; the general kernel takes the listed work items.
 template <typename T, int MODE, bool HALF, bool FMA>
 int launch_pair(SweepArgs<T> a, cudaStream_t st) {
-    a.queue = MODE;  // fast: queues 0..2
-    int rc = launch_fast_t<T, MODE, HALF, FMA>(a, st);
+    a.queue = MODE;  // fast: queues 0..2 (the wrapped and the unwrapped variant run back to back; one of them retires at once)
+    int rc = launch_fast_t<T, MODE, HALF, FMA, false>(a, st);
+    if (rc) return rc;
+    rc = launch_fast_t<T, MODE, HALF, FMA, true>(a, st);
     if (rc) return rc;
     a.queue = 3;     // general
     return launch_sweep_t<T, MODE, HALF, FMA>(a, st);

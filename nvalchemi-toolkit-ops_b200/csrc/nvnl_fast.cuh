@@ -22,6 +22,8 @@ constexpr int kFastStages = 2;                        // TMA ring depth
 constexpr int kFastMaxTargets = 64;                   // target atoms per cell the fast kernel takes (else: general kernel)
 constexpr int kFastSlackBytes = 1024;                 // the tail chunk of the last segment may read past the staged data
 constexpr int kFastStageBytes = kCandBytes + kFastSlackBytes;
+// unwrapped variant: every candidate's periodic image (int4) is staged behind the records of the stage
+constexpr int kFastStageBytesU = 2 * (kCandBytes + kFastSlackBytes);
 
 enum FastMode { FAST_COUNT = 0, FAST_FILL_COO = 1, FAST_MATRIX = 2 };
 
@@ -33,6 +35,8 @@ struct FastStage {
     int chunk_seg[32];  // segment of the first candidate of each dense 32-candidate chunk
     int item, ntarget, home_off, home_start, nseg, total, nchunks, next_target;
     int qrow[kFastMaxTargets];  // FILL: neighbor_ptr (row start) of every target
+    T cm[9];                    // unwrapped variant: cell matrix and periodicity of the cell's system
+    int pbc[3];
 };
 
 template <typename T, int MODE>
@@ -46,9 +50,9 @@ struct FastSmem {
     unsigned long long full[kFastStages], empty[kFastStages];    // mbarriers of the ring
 };
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool UNW>
 constexpr size_t fast_smem_bytes() {
-    return (size_t)kFastStages * kFastStageBytes + sizeof(FastSmem<T, MODE>);
+    return (size_t)kFastStages * (UNW ? kFastStageBytesU : kFastStageBytes) + sizeof(FastSmem<T, MODE>);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -163,6 +167,48 @@ __device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand
     }
 }
 
+__device__ __forceinline__ int4 lds_int4(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// Phase 1 for inputs with atoms outside the primary periodic image: the integer shift of a pair is
+// cs(segment) + a_i - a_j (cell_list.py:506-523), so it — and its lattice vector — is evaluated per lane.
+template <typename T, bool HALF, bool FMA>
+__device__ __forceinline__ void fast_masks_unw(const FastStage<T>& sm, uint32_t cand_addr, uint32_t ash_addr, T xi, T yi,
+                                               T zi, int i, int4 ai, const T* __restrict__ cm, T rc2, int lane,
+                                               unsigned* __restrict__ mb) {
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    using A = Arith<T>;
+    const int total = sm.total, nchunks = sm.nchunks, nseg = sm.nseg;
+    const int p0 = sm.pbc[0], p1 = sm.pbc[1], p2 = sm.pbc[2];
+#pragma unroll 1
+    for (int ck = 0; ck < nchunks; ++ck) {
+        const int c = (ck << 5) + lane;
+        int sg = sm.chunk_seg[ck];
+        while (sg + 1 < nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+        int csx, csy, csz;
+        unpack_key(sm.seg_key[sg], csx, csy, csz);
+        T x, y, z;
+        int j;
+        lds_rec(cand_addr + (uint32_t)c * RS, x, y, z, j);
+        const int4 aj = lds_int4(ash_addr + (uint32_t)c * 16u);
+        const int sx = p0 ? csx + ai.x - aj.x : 0, sy = p1 ? csy + ai.y - aj.y : 0, sz = p2 ? csz + ai.z - aj.z : 0;
+        T Sx, Sy, Sz;
+        shift_vector<T, FMA>(cm, sx, sy, sz, Sx, Sy, Sz);
+        const T dx = A::add(A::sub(x, xi), Sx), dy = A::add(A::sub(y, yi), Sy), dz = A::add(A::sub(z, zi), Sz);
+        const T d2 = dist2<T, FMA>(dx, dy, dz);
+        bool hit = (d2 < rc2) && (c < total);
+        if (HALF) {
+            const bool lexpos = sx > 0 || (sx == 0 && (sy > 0 || (sy == 0 && sz > 0)));
+            hit = hit && (i < j || (i == j && lexpos));
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) mb[ck] = m0;
+    }
+}
+
 // position of the r-th (0-based) set bit of m (r < popc(m)): popc halving, ~33 SASS instructions
 __device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
     int bit = 0, t;
@@ -178,10 +224,11 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
 //   chunk of entry k  = first chunk whose inclusive popc prefix exceeds k (5-step search in shared memory),
 //   bit inside it     = nth_set_bit(mask[chunk], k - prefix[chunk-1]).
 // ~90 hits / 32 lanes = 3 iterations per atom instead of a serial walk bounded by the densest chunk (~22 bits).
-template <typename T, bool COO>
+template <typename T, bool COO, bool UNW>
 __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastStage<T>& sm, uint32_t cand_addr,
                                             unsigned mymask, int lane, int i, size_t p0, int limit, int* __restrict__ out_j,
-                                            int* __restrict__ out_sh, unsigned* __restrict__ mb, int* __restrict__ pre) {
+                                            int* __restrict__ out_sh, unsigned* __restrict__ mb, int* __restrict__ pre,
+                                            uint32_t ash_addr, int4 ai) {
     constexpr uint32_t RS = sizeof(Rec<T>);
     const int pc = __popc(mymask);
     const int incl = warp_incl_scan(pc, lane);
@@ -191,7 +238,7 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
     pre[lane] = incl;
     // hits of the leading zero-shift segment (candidates [0, zend)) occupy the first nzero row slots
     int nzero = 0;
-    {
+    if (!UNW) {
         const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;
         const int zc = zend >> 5, zb = zend & 31;
         const int before = zc > 0 ? __shfl_sync(0xffffffffu, incl, (zc - 1) & 31) : 0;
@@ -231,6 +278,12 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
                     while (sg + 1 < sm.nseg && cv[u] >= sm.seg_begin[sg + 1]) ++sg;
                     int csx, csy, csz;
                     unpack_key(sm.seg_key[sg], csx, csy, csz);
+                    if (UNW) {
+                        const int4 aj = lds_int4(ash_addr + (uint32_t)cv[u] * 16u);
+                        csx = sm.pbc[0] ? csx + ai.x - aj.x : 0;
+                        csy = sm.pbc[1] ? csy + ai.y - aj.y : 0;
+                        csz = sm.pbc[2] ? csz + ai.z - aj.z : 0;
+                    }
                     sh[3 * k] = csx;
                     sh[3 * k + 1] = csy;
                     sh[3 * k + 2] = csz;
@@ -263,10 +316,13 @@ __global__ void k_gather_ptr(const unsigned char* __restrict__ ws, WsLayout L, l
 //     (shared-memory counter), sweep / expand, and release the stage through empty[stage].
 // No CTA-wide barrier in the steady state: the setup latency of cell k+1 hides behind the sweep of cell k.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, bool HALF, bool FMA>
-__global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const SweepArgs<T> a) {
+template <typename T, int MODE, bool HALF, bool FMA, bool UNW>
+__global__ void __launch_bounds__(kFastThreads, UNW ? (MODE == 1 ? 2 : 3) : (MODE == 1 ? 4 : 5))
+k_fast(const SweepArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FastSmem<T, MODE>& sm = *reinterpret_cast<FastSmem<T, MODE>*>(smem_raw + (size_t)kFastStages * kFastStageBytes);
+    constexpr int kStageBytes = UNW ? kFastStageBytesU : kFastStageBytes;
+    constexpr int kAshOffset = kCandBytes + kFastSlackBytes;  // unwrapped variant: periodic images behind the records
+    FastSmem<T, MODE>& sm = *reinterpret_cast<FastSmem<T, MODE>*>(smem_raw + (size_t)kFastStages * kStageBytes);
     const uint32_t smem_base = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
     constexpr int cap = kCandBytes / (int)RS;
@@ -286,7 +342,9 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
             ctrl->max_count = 0;
         }
     }
-    const bool unwrapped = ctrl->unwrapped != 0;  // then every cell belongs to the general kernel
+    // two variants of this kernel are launched back to back; the one matching the input (all atoms inside the primary
+    // periodic image, or not) does the work, the other retires at once
+    const bool active = (ctrl->unwrapped != 0) == UNW;
     if (tid == 0) {
         for (int st = 0; st < kFastStages; ++st) {
             mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
@@ -302,7 +360,8 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
         const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
         const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
         int2* deferred = reinterpret_cast<int2*>(a.ws + a.L.deferred);
-        const int total_cells = unwrapped ? 0 : ctrl->total_cells;
+        const int total_cells = active ? ctrl->total_cells : 0;
+        const int4* sorted_ashift = reinterpret_cast<const int4*>(a.ws + a.L.sorted_ashift);
         const int* ptr_sorted = reinterpret_cast<const int*>(a.ws + a.L.ptr_sorted);
         int stage = 0;
         uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
@@ -312,7 +371,8 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
         for (;;) {
             mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
             FastStage<T>& sg = sm.stage[stage];
-            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kFastStageBytes);
+            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kStageBytes);
+            int4* cand_ash = reinterpret_cast<int4*>(smem_raw + (size_t)stage * kStageBytes + kAshOffset);
             bool done = false;
             for (;;) {
                 const int g = __shfl_sync(0xffffffffu, g_next, 0);
@@ -429,6 +489,11 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                     sg.nseg = nseg; sg.total = total; sg.next_target = 0;
                 }
                 uint32_t tx = (uint32_t)total * RS;
+                if (UNW) {
+                    tx += (uint32_t)total * 16u;
+                    if (lane < 9) sg.cm[lane] = (T)sp.cellm[lane];
+                    if (lane < 3) sg.pbc[lane] = sp.pbc[lane];
+                }
                 if (MODE == FAST_FILL_COO) {
                     // the consumers of a FILL stage touch no global memory but their stores: the producer brings in the
                     // targets' row pointers (pre-gathered into sorted order) and TMA-copies the cell's mask block
@@ -444,8 +509,12 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                                     (uint32_t)ntarget * 128u, reinterpret_cast<uint64_t*>(&sm.full[stage]));
                 }
                 __syncwarp();
-                if (cn > 0)
+                if (cn > 0) {
                     tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                    if (UNW)
+                        tma_load_1d(cand_ash + off, sorted_ashift + st, (uint32_t)cn * 16u,
+                                    reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                }
                 break;
             }
             if (done) {
@@ -478,7 +547,13 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
             mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
             FastStage<T>& sg = sm.stage[stage];
             if (sg.item < 0) break;
-            const uint32_t cand_addr = smem_base + (uint32_t)stage * kFastStageBytes;
+            const uint32_t cand_addr = smem_base + (uint32_t)stage * kStageBytes;
+            const uint32_t ash_addr = cand_addr + kAshOffset;
+            T cm[9];
+            if (UNW) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) cm[k] = sg.cm[k];
+            }
             const int ntarget = sg.ntarget, home_off = sg.home_off, home_start = sg.home_start;
             const int nchunks = sg.nchunks;
             if (MODE == FAST_FILL_COO) {
@@ -488,9 +563,11 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                     if (lane == 0) t = atomicAdd(&sg.next_target, 1);
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntarget) break;
-                    fast_expand2<T, true>(a, sg, cand_addr, smk[t * 32 + lane], lane,
-                                          lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t) * RS), (size_t)sg.qrow[t], 0x7fffffff,
-                                          a.out_j, a.out_shifts, mb, pre);
+                    int4 ai = make_int4(0, 0, 0, 0);
+                    if (UNW) ai = lds_int4(ash_addr + (uint32_t)(home_off + t) * 16u);
+                    fast_expand2<T, true, UNW>(a, sg, cand_addr, smk[t * 32 + lane], lane,
+                                               lds_rec_j<T>(cand_addr + (uint32_t)(home_off + t) * RS), (size_t)sg.qrow[t],
+                                               0x7fffffff, a.out_j, a.out_shifts, mb, pre, ash_addr, ai);
                 }
             } else {
                 for (;;) {
@@ -502,7 +579,13 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                     T xi, yi, zi;
                     int i;
                     lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
-                    fast_masks<T, HALF, FMA>(sg, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
+                    int4 ai = make_int4(0, 0, 0, 0);
+                    if (UNW) {
+                        ai = lds_int4(ash_addr + (uint32_t)self * 16u);
+                        fast_masks_unw<T, HALF, FMA>(sg, cand_addr, ash_addr, xi, yi, zi, i, ai, cm, a.cutoff_sq, lane, mb);
+                    } else {
+                        fast_masks<T, HALF, FMA>(sg, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
+                    }
                     __syncwarp();
                     unsigned mymask = lane < nchunks ? mb[lane] : 0u;
                     if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
@@ -513,8 +596,8 @@ __global__ void __launch_bounds__(kFastThreads, MODE == 1 ? 4 : 5) k_fast(const 
                         if (lane == 0) a.num_neighbors[i] = cnt;
                     } else {
                         const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
-                        const int cnt = fast_expand2<T, false>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
-                                                               a.neighbor_matrix, a.out_shifts, mb, pre);
+                        const int cnt = fast_expand2<T, false, UNW>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
+                                                                    a.neighbor_matrix, a.out_shifts, mb, pre, ash_addr, ai);
                         finish_matrix_row<T>(a, lane, i, cnt);
                     }
                 }

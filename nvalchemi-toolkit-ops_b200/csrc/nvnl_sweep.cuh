@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
     int* cursor = reinterpret_cast<int*>(a.ws + a.L.cursor);
 
     const bool unwrapped = ctrl->unwrapped != 0;
-    // work source: every cell when atoms lie outside the primary image, else the cells the fast kernel
-    // (nvnl_fast.cuh) deferred (too many images or candidates for its single shared-memory tile)
+    // work source: the (cell, first target) items the fast kernels (nvnl_fast.cuh) deferred — too many images,
+    // candidates or target atoms for their single shared-memory tile
     const int2* deferred = reinterpret_cast<const int2*>(a.ws + a.L.deferred);
-    const int total_items = unwrapped ? ctrl->total_cells : ctrl->n_deferred;
+    const int total_items = ctrl->n_deferred;
     // unwrapped inputs also stage each candidate's periodic image (int4): half the record capacity
     const int cap = unwrapped ? (kSweepCandBytes / 2) / (int)sizeof(Rec<T>) : kSweepCandBytes / (int)sizeof(Rec<T>);
     int4* cand_ash = reinterpret_cast<int4*>(smem_raw + kSweepCandBytes / 2);
@@ -279,12 +279,12 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
         __syncthreads();
         const int item = sm.item;
         if (item >= total_items) break;
-        const int2 it = unwrapped ? make_int2(item, 0) : deferred[item];
+        const int2 it = deferred[item];
         const int g = it.x;
         const int ncell_atoms = cell_count[g];
-        // targets of this work item: the whole cell (unwrapped sweep) or a kDeferTargets slice of it
+        // targets of this work item: a kDeferTargets slice of the cell
         const int t_begin = it.y;
-        const int ntarget = unwrapped ? ncell_atoms : (t_begin + kDeferTargets < ncell_atoms ? t_begin + kDeferTargets : ncell_atoms);
+        const int ntarget = t_begin + kDeferTargets < ncell_atoms ? t_begin + kDeferTargets : ncell_atoms;
         const int home_start = cell_start[g];
         if (ntarget == 0) {
             __syncthreads();

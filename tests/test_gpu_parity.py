@@ -489,3 +489,28 @@ def test_dual_cutoff_routes():
     assert len(out) == 6 and out[0].shape[0] == 2 and out[3].shape[0] == 2
     assert np.array_equal(ro.records_from_coo(out[3].cpu(), out[5].cpu()),
                           ro.records_from_matrix(*ro.cell_list(pos, 5.0, cell, pbc, max_neighbors=256)))
+
+
+@pytest.mark.parametrize("pbc_flag", [[True, True, True], [True, True, False]])
+def test_unwrapped_coordinates_medium_box(pbc_flag):
+    """MD-style unwrapped coordinates (atoms up to two lattice vectors outside the box) on a box large enough for the
+    unwrapped variant of the fast kernel: full set parity, COO and matrix, plus a half-fill run."""
+    pos, cell, pbc = random_system(6000, 40.0, torch.float32, seed=23, pbc_flag=pbc_flag)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(-2, 3, (6000, 3), generator=g).float()
+    img[:, 2] = img[:, 2] if pbc_flag[2] else 0.0
+    pos = pos + img * 40.0
+    o = ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=256, nthreads=8)
+    assert o[1].max() <= 256
+    want = ro.records_from_matrix(*o)
+    e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256, return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    assert s.abs().max().item() >= 2
+    nm, num, sh = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256)
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 6000)
+    eh, ph, sh2 = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256, half_fill=True,
+                                  return_neighbor_list=True)
+    assert 2 * eh.shape[1] == want.shape[0]
+    assert np.array_equal(ro.canonical_undirected(ro.records_from_coo(eh.cpu(), sh2.cpu())),
+                          np.unique(ro.canonical_undirected(want), axis=0))
