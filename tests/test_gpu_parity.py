@@ -514,3 +514,52 @@ def test_unwrapped_coordinates_medium_box(pbc_flag):
     assert 2 * eh.shape[1] == want.shape[0]
     assert np.array_equal(ro.canonical_undirected(ro.records_from_coo(eh.cpu(), sh2.cpu())),
                           np.unique(ro.canonical_undirected(want), axis=0))
+
+
+def test_batch_with_empty_systems_unaligned_positions_and_f64():
+    """Edge cases of the batch path: systems without atoms, positions that are a non-16-byte-aligned view (scalar load
+    path of the hash / scatter kernels), float64 inputs, half-fill in a batch."""
+    nl = _nl()
+    pos, cell, pbc, bidx, bptr = bench_batch(7, 120, 260, seed=14, mixed_pbc=True)
+    # insert two empty systems (ids 2 and 5 get no atoms)
+    remap = torch.tensor([0, 1, 3, 4, 6, 7, 8])
+    bidx2 = remap[bidx.long()].to(torch.int32)
+    cell2 = torch.eye(3).repeat(9, 1, 1) * 15.0
+    pbc2 = torch.ones(9, 3, dtype=torch.bool)
+    cell2[remap] = cell
+    pbc2[remap] = pbc
+    for dtype in (torch.float32, torch.float64):
+        p = pos.to(dtype)
+        c = cell2.to(dtype)
+        want = ro.records_from_matrix(*ro.batch_cell_list(p, 6.0, c, pbc2, bidx2, max_neighbors=512))
+        big = torch.zeros((p.shape[0] + 1, 3), dtype=dtype, device=DEV)
+        big[1:] = p.to(DEV)
+        view = big[1:]                                  # data_ptr offset by 12 / 24 bytes: not 16-byte aligned
+        assert view.data_ptr() % 16 != 0
+        e, ptr, s = nl.batch_cell_list(view, 6.0, c.to(DEV), pbc2.to(DEV), bidx2.to(DEV), max_neighbors=512,
+                                       return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), dtype
+        eh, ph, sh = nl.batch_cell_list(view, 6.0, c.to(DEV), pbc2.to(DEV), bidx2.to(DEV), max_neighbors=512,
+                                        half_fill=True, return_neighbor_list=True)
+        assert np.array_equal(ro.canonical_undirected(ro.records_from_coo(eh.cpu(), sh.cpu())),
+                              np.unique(ro.canonical_undirected(want), axis=0)), dtype
+
+
+def test_invalid_inputs_are_reported():
+    """Device-side validation surfaces as Python exceptions on the COO path (the one place with a host sync)."""
+    nl = _nl()
+    pos, cell, pbc = random_system(100, 10.0, torch.float32, seed=2)
+    bad = pos.clone(); bad[3, 0] = 3.0e9                      # > 1e6 periodic images away
+    with pytest.raises(ValueError, match="periodic images"):
+        nl.cell_list(bad.to(DEV), 3.0, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+    sing = cell.clone(); sing[0, 2] = sing[0, 1]                # singular cell
+    with pytest.raises(ValueError, match="singular"):
+        nl.cell_list(pos.to(DEV), 3.0, sing.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+    bidx = torch.zeros(100, dtype=torch.int32); bidx[7] = 5     # only 2 systems given
+    cells = cell.repeat(2, 1, 1); pbcs = pbc.repeat(2, 1)
+    with pytest.raises(ValueError, match="batch_idx"):
+        nl.batch_cell_list(pos.to(DEV), 3.0, cells.to(DEV), pbcs.to(DEV), bidx.to(DEV), return_neighbor_list=True)
+    # the workspace is reusable after an error: a valid call right after still matches the oracle
+    e, p, s = nl.cell_list(pos.to(DEV), 3.0, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True, max_neighbors=256)
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()),
+                          ro.records_from_matrix(*ro.cell_list(pos, 3.0, cell, pbc, max_neighbors=256)))
