@@ -43,7 +43,7 @@ template <typename T, int MODE>
 struct FastSmem {
     FastStage<T> stage[kFastStages];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                // producer scratch (shift sort)
-    alignas(16) unsigned maskbuf[kFastCons][32];                 // per consumer warp: hit masks of the current row
+    alignas(16) unsigned maskbuf[kFastCons][2][32];              // per consumer warp: hit masks of the current row(s)
     int pre[kFastCons][32];                                      // per consumer warp: inclusive popc prefix per chunk
     // FILL only: the cell's hit masks (TMA from global); other modes keep a token array so 5 CTAs fit per SM
     alignas(16) unsigned smasks[kFastStages][MODE == 1 ? kFastMaxTargets * 32 : 4];
@@ -165,6 +165,133 @@ __device__ __forceinline__ void fast_masks(const FastStage<T>& sm, uint32_t cand
         if (l0) mb[ck] = m0;
         addr += 32 * RS;
     }
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 take a scalar broadcast operand) -------------------
+// Two target atoms A, B share one candidate load; every step of the distance test is one packed instruction for
+// both.  Each half is an IEEE round-to-nearest fp32 operation, so the results equal the scalar path bit for bit.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// one 32-candidate chunk against two targets: hit ballots mA, mB
+template <bool HALF, bool FMA, bool SHIFTED, bool TAIL>
+__device__ __forceinline__ void chunk_mask2(uint32_t addr, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB, float Sx,
+                                            float Sy, float Sz, float rc2, bool lexpos, bool valid, unsigned& mA,
+                                            unsigned& mB) {
+    float x, y, z;
+    int j;
+    lds_rec(addr, x, y, z, j);
+    f32x2_t dx = sub2(pack2(x, x), XI), dy = sub2(pack2(y, y), YI), dz = sub2(pack2(z, z), ZI);
+    if (SHIFTED) {
+        dx = add2(dx, pack2(Sx, Sx));
+        dy = add2(dy, pack2(Sy, Sy));
+        dz = add2(dz, pack2(Sz, Sz));
+    }
+    f32x2_t d2;
+    if (FMA) {
+        d2 = mul2(dx, dx);
+        d2 = fma2(dy, dy, d2);
+        d2 = fma2(dz, dz, d2);
+    } else {
+        d2 = add2(mul2(dx, dx), mul2(dy, dy));
+        d2 = add2(d2, mul2(dz, dz));
+    }
+    float dA, dB;
+    unpack2(d2, dA, dB);
+    bool hA = dA < rc2, hB = dB < rc2;
+    if (TAIL) { hA = hA && valid; hB = hB && valid; }
+    if (HALF) {
+        hA = hA && (iA < j || (iA == j && lexpos));
+        hB = hB && (iB < j || (iB == j && lexpos));
+    }
+    mA = __ballot_sync(0xffffffffu, hA);
+    mB = __ballot_sync(0xffffffffu, hB);
+}
+
+// Phase 1 for two targets at once (fp32): same chunk structure as fast_masks.
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void fast_masks2(const FastStage<float>& sm, uint32_t cand_addr, float xa, float ya, float za, int iA,
+                                            float xb, float yb, float zb, int iB, float rc2, int lane,
+                                            unsigned* __restrict__ mbA, unsigned* __restrict__ mbB) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    const bool l0 = lane == 0;
+    const int total = sm.total, nchunks = sm.nchunks;
+    const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;
+    const int nzfull = zend >> 5;
+    const f32x2_t XI = pack2(xa, xb), YI = pack2(ya, yb), ZI = pack2(za, zb);
+    uint32_t addr = cand_addr + (uint32_t)lane * RS;
+    int ck = 0;
+#pragma unroll 1
+    for (; ck + 2 <= nzfull; ck += 2) {
+        unsigned a0, b0, a1, b1;
+        chunk_mask2<HALF, FMA, false, false>(addr, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a0, b0);
+        chunk_mask2<HALF, FMA, false, false>(addr + 32 * RS, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a1, b1);
+        if (l0) { mbA[ck] = a0; mbA[ck + 1] = a1; mbB[ck] = b0; mbB[ck + 1] = b1; }
+        addr += 64 * RS;
+    }
+#pragma unroll 1
+    for (; ck < nzfull; ++ck) {
+        unsigned a0, b0;
+        chunk_mask2<HALF, FMA, false, false>(addr, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a0, b0);
+        if (l0) { mbA[ck] = a0; mbB[ck] = b0; }
+        addr += 32 * RS;
+    }
+    if (sm.nseg == 1 && ck < nchunks) {
+        unsigned a0, b0;
+        chunk_mask2<HALF, FMA, false, true>(addr, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, (ck << 5) + lane < total, a0, b0);
+        if (l0) { mbA[ck] = a0; mbB[ck] = b0; }
+        ++ck;
+    }
+#pragma unroll 1
+    for (; ck < nchunks; ++ck) {
+        const int c = (ck << 5) + lane;
+        int sg = sm.chunk_seg[ck];
+        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+        bool lexpos = false;
+        if (HALF) {
+            int csx, csy, csz;
+            unpack_key(sm.seg_key[sg], csx, csy, csz);
+            lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
+        }
+        unsigned a0, b0;
+        chunk_mask2<HALF, FMA, true, true>(addr, XI, YI, ZI, iA, iB, sm.segS[3 * sg], sm.segS[3 * sg + 1], sm.segS[3 * sg + 2],
+                                           rc2, lexpos, c < total, a0, b0);
+        if (l0) { mbA[ck] = a0; mbB[ck] = b0; }
+        addr += 32 * RS;
+    }
+}
+// double precision has no packed form: two scalar sweeps
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void fast_masks2(const FastStage<double>& sm, uint32_t cand_addr, double xa, double ya, double za,
+                                            int iA, double xb, double yb, double zb, int iB, double rc2, int lane,
+                                            unsigned* __restrict__ mbA, unsigned* __restrict__ mbB) {
+    fast_masks<double, HALF, FMA>(sm, cand_addr, xa, ya, za, iA, rc2, lane, mbA);
+    fast_masks<double, HALF, FMA>(sm, cand_addr, xb, yb, zb, iB, rc2, lane, mbB);
 }
 
 __device__ __forceinline__ int4 lds_int4(uint32_t addr) {
@@ -539,7 +666,8 @@ k_fast(const SweepArgs<T> a) {
         // =========================== consumers ===========================
         const int cw = warp - 1;
         unsigned* masks = reinterpret_cast<unsigned*>(a.ws + a.L.masks);
-        unsigned* mb = sm.maskbuf[cw];
+        unsigned* mb = sm.maskbuf[cw][0];
+        unsigned* mb2 = sm.maskbuf[cw][1];
         int* pre = sm.pre[cw];
         int stage = 0;
         uint32_t fphase = 0;
@@ -571,34 +699,54 @@ k_fast(const SweepArgs<T> a) {
                 }
             } else {
                 for (;;) {
+                    // two targets per trip: they share every candidate load and, in fp32, every FP instruction (f32x2)
                     int t = 0;
-                    if (lane == 0) t = atomicAdd(&sg.next_target, 1);
+                    if (lane == 0) t = atomicAdd(&sg.next_target, 2);
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntarget) break;
-                    const int self = home_off + t;
-                    T xi, yi, zi;
-                    int i;
-                    lds_rec(cand_addr + (uint32_t)self * RS, xi, yi, zi, i);
-                    int4 ai = make_int4(0, 0, 0, 0);
-                    if (UNW) {
-                        ai = lds_int4(ash_addr + (uint32_t)self * 16u);
-                        fast_masks_unw<T, HALF, FMA>(sg, cand_addr, ash_addr, xi, yi, zi, i, ai, cm, a.cutoff_sq, lane, mb);
-                    } else {
-                        fast_masks<T, HALF, FMA>(sg, cand_addr, xi, yi, zi, i, a.cutoff_sq, lane, mb);
+                    const bool two = !UNW && (t + 1 < ntarget);
+                    const int ntrip = (t + 1 < ntarget) ? 2 : 1;
+                    T xs[2], ys[2], zs[2];
+                    int is[2];
+                    lds_rec(cand_addr + (uint32_t)(home_off + t) * RS, xs[0], ys[0], zs[0], is[0]);
+                    xs[1] = xs[0]; ys[1] = ys[0]; zs[1] = zs[0]; is[1] = is[0];
+                    if (ntrip == 2) lds_rec(cand_addr + (uint32_t)(home_off + t + 1) * RS, xs[1], ys[1], zs[1], is[1]);
+                    if (two) {
+                        fast_masks2<HALF, FMA>(sg, cand_addr, xs[0], ys[0], zs[0], is[0], xs[1], ys[1], zs[1], is[1], a.cutoff_sq,
+                                               lane, mb, mb2);
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    unsigned mymask = lane < nchunks ? mb[lane] : 0u;
-                    if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
-                    __syncwarp();
-                    if (MODE == FAST_COUNT) {
-                        masks[(size_t)(home_start + t) * 32 + lane] = mymask;
-                        const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
-                        if (lane == 0) a.num_neighbors[i] = cnt;
-                    } else {
-                        const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
-                        const int cnt = fast_expand2<T, false, UNW>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
-                                                                    a.neighbor_matrix, a.out_shifts, mb, pre, ash_addr, ai);
-                        finish_matrix_row<T>(a, lane, i, cnt);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (u >= ntrip) break;
+                        const int tt = t + u;
+                        const int self = home_off + tt;
+                        const int i = is[u];
+                        unsigned* mbu = u ? mb2 : mb;
+                        int4 ai = make_int4(0, 0, 0, 0);
+                        if (!two) {
+                            if (UNW) {
+                                ai = lds_int4(ash_addr + (uint32_t)self * 16u);
+                                fast_masks_unw<T, HALF, FMA>(sg, cand_addr, ash_addr, xs[u], ys[u], zs[u], i, ai, cm, a.cutoff_sq, lane, mbu);
+                            } else {
+                                fast_masks<T, HALF, FMA>(sg, cand_addr, xs[u], ys[u], zs[u], i, a.cutoff_sq, lane, mbu);
+                            }
+                            __syncwarp();
+                        }
+                        unsigned mymask = lane < nchunks ? mbu[lane] : 0u;
+                        if (!HALF && lane == (self >> 5)) mymask &= ~(1u << (self & 31));  // (i, i, 0) is not a pair
+                        __syncwarp();
+                        if (MODE == FAST_COUNT) {
+                            masks[(size_t)(home_start + tt) * 32 + lane] = mymask;
+                            const int cnt = __reduce_add_sync(0xffffffffu, __popc(mymask));
+                            if (lane == 0) a.num_neighbors[i] = cnt;
+                        } else {
+                            const size_t p0 = (size_t)i * (size_t)a.max_neighbors;
+                            // expansion scratch: reuse this target's own mask buffer (its words are already in registers)
+                            const int cnt = fast_expand2<T, false, UNW>(a, sg, cand_addr, mymask, lane, i, p0, a.max_neighbors,
+                                                                        a.neighbor_matrix, a.out_shifts, mbu, pre, ash_addr, ai);
+                            finish_matrix_row<T>(a, lane, i, cnt);
+                        }
                     }
                 }
             }
