@@ -247,12 +247,17 @@ __device__ __forceinline__ void fast_masks2(const FastStage<float>& sm, uint32_t
     uint32_t addr = cand_addr + (uint32_t)lane * RS;
     int ck = 0;
 #pragma unroll 1
-    for (; ck + 2 <= nzfull; ck += 2) {
-        unsigned a0, b0, a1, b1;
+    for (; ck + 4 <= nzfull; ck += 4) {
+        unsigned a0, b0, a1, b1, a2, b2, a3, b3;
         chunk_mask2<HALF, FMA, false, false>(addr, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a0, b0);
         chunk_mask2<HALF, FMA, false, false>(addr + 32 * RS, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a1, b1);
-        if (l0) { mbA[ck] = a0; mbA[ck + 1] = a1; mbB[ck] = b0; mbB[ck + 1] = b1; }
-        addr += 64 * RS;
+        chunk_mask2<HALF, FMA, false, false>(addr + 64 * RS, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a2, b2);
+        chunk_mask2<HALF, FMA, false, false>(addr + 96 * RS, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, a3, b3);
+        if (l0) {
+            sts_v4(smem_u32(mbA + ck), a0, a1, a2, a3);
+            sts_v4(smem_u32(mbB + ck), b0, b1, b2, b3);
+        }
+        addr += 128 * RS;
     }
 #pragma unroll 1
     for (; ck < nzfull; ++ck) {
