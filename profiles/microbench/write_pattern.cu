@@ -9,6 +9,27 @@
 #include <algorithm>
 #include <random>
 #include <cuda_runtime.h>
+template <int ST>
+__device__ __forceinline__ void st(int* p, int v) {
+    if (ST == 0) *p = v;
+    else if (ST == 1) __stcs(p, v);   // streaming (evict-first)
+    else if (ST == 2) __stwt(p, v);   // write-through
+    else __stcg(p, v);                // cache-global (L2 only)
+}
+template <int ST>
+__global__ void k_rows_st(const int* __restrict__ order, const int* __restrict__ ptr, int n, int* __restrict__ src,
+                          int* __restrict__ dst, int* __restrict__ sh) {
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += nw) {
+        const int i = order[w];
+        const size_t p0 = (size_t)ptr[i];
+        const int cnt = ptr[i + 1] - ptr[i];
+        for (int k = lane; k < cnt; k += 32) { st<ST>(src + p0 + k, i); st<ST>(dst + p0 + k, w); }
+        int* s = sh + 3 * p0;
+        for (int e = lane; e < 3 * cnt; e += 32) st<ST>(s + e, 0);
+    }
+}
 __global__ void k_rows(const int* __restrict__ order, const int* __restrict__ ptr, int n, int* __restrict__ src,
                        int* __restrict__ dst, int* __restrict__ sh, int vec) {
     const int lane = threadIdx.x & 31;
@@ -63,6 +84,21 @@ int main() {
                        P * 20.0 / ms / 1e6);
             }
         }
+    {
+        auto run = [&](const char* name, auto kern) {
+            kern<<<148 * 8, 256>>>(drnd, dptr, n, src, dst, sh);
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0);
+            for (int r = 0; r < 5; ++r) kern<<<148 * 8, 256>>>(drnd, dptr, n, src, dst, sh);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+            printf("random order, store variant %-22s %.3f ms  %.0f GB/s\n", name, ms, P * 20.0 / ms / 1e6);
+        };
+        run("default (st.global)", k_rows_st<0>);
+        run("st.global.cs", k_rows_st<1>);
+        run("st.global.wt", k_rows_st<2>);
+        run("st.global.cg", k_rows_st<3>);
+    }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
