@@ -66,17 +66,21 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
 /* Device->host read of the control block (synchronizes `stream`): total number of directed pairs
  * found by the last nvnl_count, the largest per-atom count (what assert_max_neighbors checks,
  * neighbor_utils.py:352-359), number of cells, error bits, and whether any atom was outside the
- * primary periodic image.  The one sync of the COO path (the reference has three). Host pointers. */
+ * primary periodic image, and whether any cell was left to the general kernel (both feed nvnl_fill_coo's
+ * launch_hint).  The one sync of the COO path (the reference has three). Host pointers. */
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
-                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, void* stream);
+                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, int32_t* had_deferred,
+                void* stream);
 
 /* Second half of the COO path: writes edge_index [2,num_pairs] (row 0 = source atoms, sorted),
  * shifts [num_pairs,3].  Output identical in content to cell_list(..., return_neighbor_list=True)
  * (cell_list.py:1432-1441) without materialising the padded matrix.
- *   index_offset is added to every atom index written (rank-sharded batches, 0 otherwise). */
+ *   index_offset is added to every atom index written (rank-sharded batches, 0 otherwise).
+ *   launch_hint: -1 = unknown (all kernel variants are launched, the idle ones retire at once); otherwise
+ *   bit 0 = nvnl_status' `unwrapped`, bit 1 = its `had_deferred`: only the kernels with work are launched. */
 int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, void* stream);
+                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
 
 /* query_cell_list / batch_query_cell_list (cell_list.py:892-1034, batch_cell_list.py:915-1067)
  * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of

@@ -97,23 +97,28 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
 
 // Every query is three launches: the lean kernel in its wrapped and unwrapped variant (the one that does not match the
 // input retires at once) takes the cells it can and lists the rest; the general kernel takes the listed work items.
+// hint < 0: nothing known about the workspace state (launch everything).  hint >= 0 (from nvnl_status after the
+// count pass): bit 0 = atoms outside the primary image, bit 1 = some cell was deferred -> only the kernels that have
+// work are launched.
 template <typename T, int MODE, bool HALF, bool FMA>
-int launch_pair(SweepArgs<T> a, cudaStream_t st) {
+int launch_pair(SweepArgs<T> a, int hint, cudaStream_t st) {
     a.queue = MODE;  // fast: queues 0..2 (the wrapped and the unwrapped variant run back to back; one of them retires at once)
-    int rc = launch_fast_t<T, MODE, HALF, FMA, false>(a, st);
+    int rc = 0;
+    if (hint < 0 || !(hint & 1)) rc = launch_fast_t<T, MODE, HALF, FMA, false>(a, st);
     if (rc) return rc;
-    rc = launch_fast_t<T, MODE, HALF, FMA, true>(a, st);
+    if (hint < 0 || (hint & 1)) rc = launch_fast_t<T, MODE, HALF, FMA, true>(a, st);
     if (rc) return rc;
     a.queue = 3;     // general
-    return launch_sweep_t<T, MODE, HALF, FMA>(a, st);
+    if (hint < 0 || (hint & 2)) rc = launch_sweep_t<T, MODE, HALF, FMA>(a, st);
+    return rc;
 }
 
 template <typename T, int MODE>
-int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st) {
+int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st, int hint = -1) {
     if (half_fill) {
-        return fma ? launch_pair<T, MODE, true, true>(a, st) : launch_pair<T, MODE, true, false>(a, st);
+        return fma ? launch_pair<T, MODE, true, true>(a, hint, st) : launch_pair<T, MODE, true, false>(a, hint, st);
     }
-    return fma ? launch_pair<T, MODE, false, true>(a, st) : launch_pair<T, MODE, false, false>(a, st);
+    return fma ? launch_pair<T, MODE, false, true>(a, hint, st) : launch_pair<T, MODE, false, false>(a, hint, st);
 }
 
 template <typename T>
@@ -284,7 +289,8 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
 }
 
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
-                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, void* stream) {
+                int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, int32_t* had_deferred,
+                void* stream) {
     if (!workspace) return fail(-1, "nvnl_status: null workspace");
     const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
     Ctrl h;
@@ -299,12 +305,13 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
     if (total_cells) *total_cells = h.total_cells;
     if (error_bits) *error_bits = h.error;
     if (unwrapped) *unwrapped = h.unwrapped;
+    if (had_deferred) *had_deferred = h.had_deferred;
     return 0;
 }
 
 int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, void* stream) {
+                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream) {
     if (!workspace || !neighbor_ptr || n_atoms <= 0) return fail(-1, "nvnl_fill_coo: bad arguments");
     if (num_pairs < 0 || num_pairs > 2147483647LL) return fail(-1, "nvnl_fill_coo: num_pairs outside int32 range");
     if (num_pairs == 0) return 0;
@@ -318,7 +325,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
         k_gather_ptr<float><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
                                                                               reinterpret_cast<int*>(ws + a.L.ptr_sorted));
         NVNL_CHECK_LAUNCH("k_gather_ptr");
-        return launch_sweep<float, MODE_FILL_COO>(a, half_fill, fma, st);
+        return launch_sweep<float, MODE_FILL_COO>(a, half_fill, fma, st, launch_hint);
     }
     if (dtype == NVNL_F64) {
         SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
@@ -327,7 +334,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
         k_gather_ptr<double><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
                                                                                reinterpret_cast<int*>(ws + a.L.ptr_sorted));
         NVNL_CHECK_LAUNCH("k_gather_ptr");
-        return launch_sweep<double, MODE_FILL_COO>(a, half_fill, fma, st);
+        return launch_sweep<double, MODE_FILL_COO>(a, half_fill, fma, st, launch_hint);
     }
     return fail(-1, "nvnl_fill_coo: unsupported dtype");
 }

@@ -83,6 +83,7 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
         ctrl->total_pairs = 0ull;
         ctrl->max_count = 0;
         ctrl->n_deferred = 0;
+        ctrl->had_deferred = 0;
     }
     int* cell_count = reinterpret_cast<int*>(ws + L.cell_count);
     for (long long i = gid; i < L.max_cells + 2; i += stride) cell_count[i] = 0;

@@ -54,8 +54,8 @@ struct Ctrl {
     int total_cells;
     int error;                       // ErrorBits
     int scan_tile[2];                // dynamic tile ids for the two look-back scans
-    int n_deferred;                  // cells the fast kernel left to the general kernel
-    int pad1;
+    int n_deferred;                  // work items the fast kernels left to the general kernel (consumed per launch)
+    int had_deferred;                // sticky since the last build: some cell was deferred
     int max_count;                   // max over atoms of num_neighbors (overflow check vs max_neighbors)
     unsigned long long total_pairs;  // 64-bit sum of num_neighbors (overflow check for int32 ptr)
 };

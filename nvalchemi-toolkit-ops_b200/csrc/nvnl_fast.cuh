@@ -608,7 +608,10 @@ k_fast(const SweepArgs<T> a) {
                     // work items of kDeferTargets target atoms each (a whole small periodic system can be one "cell")
                     const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&ctrl->n_deferred, nitems);
+                    if (lane == 0) {
+                        base = atomicAdd(&ctrl->n_deferred, nitems);
+                        ctrl->had_deferred = 1;
+                    }
                     base = __shfl_sync(0xffffffffu, base, 0);
                     for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
                     continue;

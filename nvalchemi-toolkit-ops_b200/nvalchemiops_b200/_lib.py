@@ -27,9 +27,10 @@ _SIGNATURES = {
     "nvnl_count": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
                            c_void_p]),
     "nvnl_status": (c_int, [c_void_p, c_int, c_int64, c_int32, ctypes.POINTER(c_int64), ctypes.POINTER(c_int32),
-                            ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_void_p]),
+                            ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
+                            ctypes.POINTER(c_int32), c_void_p]),
     "nvnl_fill_coo": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
-                              c_int64, c_void_p, c_int32, c_void_p]),
+                              c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_matrix": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "nvnl_export_cache": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

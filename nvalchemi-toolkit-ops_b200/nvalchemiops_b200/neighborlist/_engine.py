@@ -112,16 +112,19 @@ def _raise_on_error_bits(bits: int):
 
 
 def status(h: CellListHandle):
-    """(total_pairs, max_count, total_cells, error_bits, unwrapped) — synchronizes the stream."""
+    """(total_pairs, max_count, total_cells, error_bits, launch_hint) — synchronizes the stream.
+    launch_hint (bit 0: atoms outside the primary image, bit 1: cells left to the general kernel) lets the fill
+    stage launch only the kernels that have work."""
     L = _lib.lib()
-    tp, mc, tc, eb, uw = ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    tp, mc, tc, eb, uw, hd = (ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0),
+                              ctypes.c_int32(0))
     with torch.cuda.device(h.device):
         _lib.check(
             L.nvnl_status(_ptr(h.ws), h.dtype_code, h.n, h.ns, ctypes.byref(tp), ctypes.byref(mc), ctypes.byref(tc),
-                          ctypes.byref(eb), ctypes.byref(uw), _stream(h.device)),
+                          ctypes.byref(eb), ctypes.byref(uw), ctypes.byref(hd), _stream(h.device)),
             "nvnl_status",
         )
-    return tp.value, mc.value, tc.value, eb.value, uw.value
+    return tp.value, mc.value, tc.value, eb.value, (1 if uw.value else 0) | (2 if hd.value else 0)
 
 
 def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, fill_value,
@@ -162,7 +165,7 @@ def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True):
 
 
 def fill_coo(h: CellListHandle, cutoff_sq, neighbor_ptr, edge_index, shifts, num_pairs, half_fill=False,
-             index_offset=0):
+             index_offset=0, launch_hint=-1):
     """Write COO rows at neighbor_ptr (nvnl_fill_coo).  ``edge_index`` is [2, num_pairs] (or a block laid out
     as such with row stride ``num_pairs``), ``shifts`` [num_pairs, 3]."""
     L = _lib.lib()
@@ -170,7 +173,7 @@ def fill_coo(h: CellListHandle, cutoff_sq, neighbor_ptr, edge_index, shifts, num
         _lib.check(
             L.nvnl_fill_coo(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
                             int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_ptr), _ptr(edge_index),
-                            int(num_pairs), _ptr(shifts), int(index_offset), _stream(h.device)),
+                            int(num_pairs), _ptr(shifts), int(index_offset), int(launch_hint), _stream(h.device)),
             "nvnl_fill_coo",
         )
 
@@ -180,16 +183,18 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
     num, ptr = count(h, cutoff_sq, half_fill)
-    total, max_count, _cells, err, _uw = status(h)
+    total, max_count, _cells, err, hint = status(h)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
     if total > 2**31 - 1:
         raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
-    edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
-    shifts = torch.empty((total, 3), dtype=torch.int32, device=h.device)
+    # one allocation for both outputs (the GPU idles between the size sync and the first fill launch)
+    buf = torch.empty(5 * total, dtype=torch.int32, device=h.device)
+    edge_index = buf[: 2 * total].view(2, total)
+    shifts = buf[2 * total:].view(total, 3)
     if total > 0:
-        fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill)
+        fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill, launch_hint=hint)
     return edge_index, ptr, shifts, num
 
 
