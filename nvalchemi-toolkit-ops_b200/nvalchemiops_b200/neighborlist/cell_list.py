@@ -39,8 +39,32 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
 
     if cutoff_sq is None:
         cutoff_sq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
+    want_cache = cache is not None and any(v is not None for v in cache.values())
+    matrix_only = not (return_neighbor_list and neighbor_matrix is None)
+    if matrix_only and not want_cache:
+        # padded-matrix outputs: one mutation-only custom op (torch.compile keeps it in the graph, no host sync)
+        user_buffers = neighbor_matrix is not None and neighbor_matrix_shifts is not None and num_neighbors is not None
+        if max_neighbors is None and not user_buffers:
+            max_neighbors = estimate_max_neighbors(cutoff)
+        if neighbor_matrix is None:
+            neighbor_matrix = torch.empty((total_atoms, max_neighbors), dtype=torch.int32, device=device)
+        M = neighbor_matrix.shape[1]
+        if neighbor_matrix_shifts is None:
+            neighbor_matrix_shifts = torch.empty((total_atoms, M, 3), dtype=torch.int32, device=device)
+        if num_neighbors is None:
+            num_neighbors = torch.empty((total_atoms,), dtype=torch.int32, device=device)
+        from .ops import neighbor_matrix_op
+
+        neighbor_matrix_op(positions, float(cutoff), cell, pbc, batch_idx, batch_ptr, neighbor_matrix, neighbor_matrix_shifts,
+                           num_neighbors, int(fill_value), bool(half_fill), float(cutoff_sq))
+        if return_neighbor_list:
+            return get_neighbor_list_from_neighbor_matrix(
+                neighbor_matrix, num_neighbors=num_neighbors, neighbor_shift_matrix=neighbor_matrix_shifts,
+                fill_value=fill_value,
+            )
+        return neighbor_matrix, num_neighbors, neighbor_matrix_shifts
     h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
-    if cache is not None and any(v is not None for v in cache.values()):
+    if want_cache:
         cpd, rad = _engine.get_grid(h)
         if cache.get("cells_per_dimension") is not None:
             cache["cells_per_dimension"].copy_(cpd.reshape(cache["cells_per_dimension"].shape))

@@ -563,3 +563,30 @@ def test_invalid_inputs_are_reported():
     e, p, s = nl.cell_list(pos.to(DEV), 3.0, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True, max_neighbors=256)
     assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()),
                           ro.records_from_matrix(*ro.cell_list(pos, 3.0, cell, pbc, max_neighbors=256)))
+
+
+def test_torch_compile_keeps_the_matrix_op_in_the_graph():
+    """Mutation-only custom op with pre-allocated outputs under torch.compile(fullgraph=True) — the property the
+    reference tests for its build/query ops (test_cell_list.py:598-844)."""
+    import nvalchemiops_b200.neighborlist.ops  # noqa: F401  (registers nvalchemiops_b200::neighbor_matrix)
+
+    pos, cell, pbc = random_system(500, 14.0, torch.float32, seed=41)
+    pos, cell, pbc = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 4.0, cell, pbc, max_neighbors=96))
+
+    def fn(positions, nm, sh, num):
+        torch.ops.nvalchemiops_b200.neighbor_matrix(positions * 1.0, 4.0, cell, pbc.reshape(1, 3), None, None, nm, sh, num, 500,
+                                                    False, 16.0)
+        return num.sum()
+
+    nm = torch.empty((500, 96), dtype=torch.int32, device=DEV)
+    sh = torch.empty((500, 96, 3), dtype=torch.int32, device=DEV)
+    num = torch.empty((500,), dtype=torch.int32, device=DEV)
+    eager_total = fn(pos, nm, sh, num).item()
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    nm.fill_(-5); sh.fill_(-5); num.fill_(-5)
+    compiled = torch.compile(fn, fullgraph=True)
+    total = compiled(pos, nm, sh, num).item()
+    assert total == eager_total == want.shape[0]
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 500)
