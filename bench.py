@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--coo-path", default=None, choices=["rows", "masks"],
+                    help="override nvalchemiops_b200.config.coo_path (default: the package default)")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
 
@@ -224,8 +226,11 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
-    from nvalchemiops_b200 import launch_count
+    from nvalchemiops_b200 import config as nl_config, launch_count
     from nvalchemiops_b200.neighborlist import _engine, neighbor_list
+
+    if args.coo_path:
+        nl_config.coo_path = args.coo_path
     from systems import bench_batch, bench_box
 
     n = args.atoms
@@ -278,36 +283,42 @@ def main():
     st = {"build": [], "count": [], "fill_coo": []}
     edge = torch.empty((2, P), dtype=torch.int32, device=dev)
     shf = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    rows_path = nl_config.coo_path == "rows"
     for k in range(max(5, min(steps, 20))):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         flush.zero_()
         e[0].record(); h = _engine.build(pos, CUTOFF, cell, pbc)
-        e[1].record(); num, ptr = _engine.count(h, csq)
-        e[2].record(); _engine.fill_coo(h, csq, ptr, edge, shf, P)
-        e[3].record(); torch.cuda.synchronize()
+        e[1].record(); num, ptr = _engine.count(h, csq, rows=rows_path)
+        e[2].record(); hint = _engine.status(h)[4]          # the size sync of the COO path (not part of either stage)
+        assert not h.rows_overflow
+        e[3].record(); _engine.fill_coo(h, csq, ptr, edge, shf, P, launch_hint=hint, rows=rows_path)
+        e[4].record(); torch.cuda.synchronize()
         st["build"].append(e[0].elapsed_time(e[1])); st["count"].append(e[1].elapsed_time(e[2]))
-        st["fill_coo"].append(e[2].elapsed_time(e[3]))
+        st["fill_coo"].append(e[3].elapsed_time(e[4]))
     stage_ms = {k: float(np.median(v)) for k, v in st.items()}
     del edge, shf
     peak, peak_src = measured_peak_gbs()
     B = algorithmic_bytes(n, P)
     dom = max(("count", "fill_coo"), key=lambda k: stage_ms[k])
-    # the fill stage is the one that moves the API-mandated bytes; the count stage writes 128 B/atom of hit masks
+    # the fill stage is the one that moves the API-mandated bytes (rows path: k_rows_out streams them in atom order
+    # from the temporary rows the sweep left; masks path: k_fast<FILL_COO> expands hit masks into rows)
     fill_gbs = B / (stage_ms["fill_coo"] * 1e-3) / 1e9
+    kernel_name = ("nvnl::k_rows_out (nvnl_fill_rows stage: temporary rows -> edge_index/shifts in atom order)" if rows_path
+                   else "nvnl::k_fast<float, FILL_COO> (nvnl_fill_coo stage: mask expansion + COO row writes)")
     roofline = {
-        "bound": "hbm", "kernel": "nvnl::k_fast<float, FILL_COO> (nvnl_fill_coo stage: mask expansion + COO row writes)",
+        "bound": "hbm", "kernel": kernel_name, "coo_path": nl_config.coo_path,
         "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak, "traffic": None,
         "peak_source": peak_src, "algorithmic_bytes": B,
         "stages_ms": stage_ms, "longest_stage": dom,
         "pipeline": {"achieved": B / (ms_per_step * 1e-3) / 1e9, "frac": B / (ms_per_step * 1e-3) / 1e9 / peak,
                      "note": "all stages of one neighbor_list call (incl. the size sync and output allocation)"},
-        "count_stage_note": "k_fast<COUNT> is fp32-issue bound (583 distance tests/atom), not an HBM kernel: "
+        "count_stage_note": "the sweep (k_rows / k_fast<COUNT>) is fp32-issue bound (583 distance tests/atom), not an HBM kernel: "
                             f"{n * 583 / (stage_ms['count'] * 1e-3) / 1e12:.2f} T tests/s",
     }
     ncu_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(ncu_json):
         try:
-            roofline["traffic"] = json.load(open(ncu_json)).get("fill_coo_dram_bytes")
+            roofline["traffic"] = json.load(open(ncu_json)).get("rows_out_dram_bytes" if rows_path else "fill_coo_dram_bytes")
         except Exception:
             pass
 

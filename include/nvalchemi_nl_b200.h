@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NVNL_ABI_VERSION 1
+#define NVNL_ABI_VERSION 2
 #define NVNL_F32 0
 #define NVNL_F64 1
 
@@ -67,10 +67,11 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
  * found by the last nvnl_count, the largest per-atom count (what assert_max_neighbors checks,
  * neighbor_utils.py:352-359), number of cells, error bits, and whether any atom was outside the
  * primary periodic image, and whether any cell was left to the general kernel (both feed nvnl_fill_coo's
- * launch_hint).  The one sync of the COO path (the reference has three). Host pointers. */
+ * launch_hint), and whether nvnl_count_rows ran out of temporary row space (then the caller repeats the query with
+ * nvnl_count / nvnl_fill_coo).  The one sync of the COO path (the reference has three). Host pointers. */
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
                 int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, int32_t* had_deferred,
-                void* stream);
+                int32_t* rows_overflow, void* stream);
 
 /* Second half of the COO path: writes edge_index [2,num_pairs] (row 0 = source atoms, sorted),
  * shifts [num_pairs,3].  Output identical in content to cell_list(..., return_neighbor_list=True)
@@ -81,6 +82,21 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
 int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
                   int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
+
+/* Single-sweep COO path (fp32; same outputs as nvnl_count + nvnl_fill_coo, same reference interfaces:
+ * query_cell_list cell_list.py:892-1034 + get_neighbor_list_from_neighbor_matrix neighbor_utils.py:362-441).
+ * nvnl_count_rows evaluates every distance once and leaves each atom's neighbors as a compact row in a temporary
+ * buffer inside the workspace (in sweep order); nvnl_fill_rows then streams edge_index / shifts in atom order.
+ * Between the two: nvnl_status (sizes the outputs; launch_hint = bit 0 unwrapped | bit 1 had_deferred is REQUIRED
+ * here; if rows_overflow is set the temporary buffer — 160 entries per atom — was too small and the query must be
+ * repeated with nvnl_count / nvnl_fill_coo).  Inputs with atoms outside the primary periodic image are detected on
+ * the device and served by the two-pass kernels inside these same calls. */
+int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                    double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
+                    void* stream);
+int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
+                   int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
 
 /* query_cell_list / batch_query_cell_list (cell_list.py:892-1034, batch_cell_list.py:915-1067)
  * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of
@@ -133,6 +149,11 @@ int nvnl_moved_beyond(const void* reference_positions, const void* current_posit
 int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, int64_t block_stride_ints,
                          const int64_t* counts_host, int32_t* edge_index, int64_t total_pairs, int32_t* shifts,
                          void* stream);
+
+/* Size of the temporary row buffer nvnl_count_rows may use: entries_per_atom * n_atoms + slack_entries int32 entries
+ * (defaults 160 and 148*4*8*2048; negative = default).  Changes nvnl_workspace_bytes(): set it before sizing a
+ * workspace and keep it fixed while that workspace is in use.  Process-wide. */
+void nvnl_set_rows_budget(int64_t entries_per_atom, int64_t slack_entries);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t nvnl_launch_count(void);

@@ -6,6 +6,7 @@
 #include "../../include/nvalchemi_nl_b200.h"
 #include "nvnl_cache.cuh"
 #include "nvnl_fast.cuh"
+#include "nvnl_rows.cuh"
 
 using namespace nvnl;
 
@@ -28,6 +29,14 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         cudaError_t e__ = cudaGetLastError();                     \
         if (e__ != cudaSuccess) return fail(-2, what, e__);       \
     } while (0)
+
+// temporary-row budget of the single-sweep COO path (nvnl_set_rows_budget; tests shrink it to force the fallback)
+std::atomic<long long> g_rows_per_atom{kRowsPerAtom};
+std::atomic<long long> g_rows_slack{kRowsSlackEntries};
+
+WsLayout mk_layout(long long n, long long s, int rec) {
+    return make_layout(n, s, rec, g_rows_per_atom.load(), g_rows_slack.load());
+}
 
 int rec_bytes(int dtype) { return dtype == NVNL_F64 ? (int)sizeof(Rec<double>) : (int)sizeof(Rec<float>); }
 
@@ -95,6 +104,40 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
+template <bool HALF, bool FMA>
+int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
+    auto kern = k_rows<HALF, FMA>;
+    constexpr size_t smem = rows_smem_bytes();
+    static int bps[kMaxDevices] = {0};
+    int& blocks_per_sm = bps[current_device()];
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_rows)", e);
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kRowsThreads, smem);
+        if (e != cudaSuccess) return fail(-2, "occupancy(k_rows)", e);
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    long long grid = (long long)sm_count() * blocks_per_sm;
+    const long long max_items = a.L.max_cells;
+    if (grid > max_items) grid = max_items > 0 ? max_items : 1;
+    kern<<<(unsigned)grid, kRowsThreads, smem, st>>>(a);
+    NVNL_CHECK_LAUNCH("k_rows");
+    return 0;
+}
+
+// Start of every query: empty deferred list, empty temporary row buffer (and, for the single-sweep COO path,
+// row_ref = -1 for every atom).
+int launch_query_reset(unsigned char* ws, const WsLayout& L, long long n, int with_rows, cudaStream_t st) {
+    long long blocks = with_rows ? (n + 255) / 256 : 1;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_query_reset<<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, with_rows);
+    NVNL_CHECK_LAUNCH("k_query_reset");
+    return 0;
+}
+
 // Every query is three launches: the lean kernel in its wrapped and unwrapped variant (the one that does not match the
 // input retires at once) takes the cells it can and lists the rest; the general kernel takes the listed work items.
 // hint < 0: nothing known about the workspace state (launch everything).  hint >= 0 (from nvnl_status after the
@@ -124,7 +167,7 @@ int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st,
 template <typename T>
 int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const int* batch_idx, const int* batch_ptr,
             int ns, double cutoff, unsigned char* ws, cudaStream_t st) {
-    const WsLayout L = make_layout(n, ns, (int)sizeof(Rec<T>));
+    const WsLayout L = mk_layout(n, ns, (int)sizeof(Rec<T>));
     const int sms = sm_count();
     {
         long long work = L.max_cells + 2 > n ? L.max_cells + 2 : n;
@@ -181,7 +224,7 @@ SweepArgs<T> base_args(unsigned char* ws, long long n, int ns, const int* batch_
     SweepArgs<T> a;
     memset(&a, 0, sizeof(a));
     a.ws = ws;
-    a.L = make_layout(n, ns, (int)sizeof(Rec<T>));
+    a.L = mk_layout(n, ns, (int)sizeof(Rec<T>));
     a.batch_idx = batch_idx;
     a.num_systems = ns;
     a.n = n;
@@ -195,7 +238,9 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
     SweepArgs<T> a = base_args<T>(ws, n, ns, batch_idx, cutoff_sq);
     a.num_neighbors = num_neighbors;
     a.queue = 0;
-    int rc = launch_sweep<T, MODE_COUNT>(a, half_fill, fma, st);
+    int rc = launch_query_reset(ws, a.L, n, 0, st);
+    if (rc) return rc;
+    rc = launch_sweep<T, MODE_COUNT>(a, half_fill, fma, st);
     if (rc) return rc;
     if (neighbor_ptr) {
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
@@ -204,6 +249,60 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
                                                reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
                                                &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count, nullptr);
         NVNL_CHECK_LAUNCH("k_scan(neighbors)");
+    }
+    return 0;
+}
+
+template <bool HALF, bool FMA>
+int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, int* num_neighbors,
+                 int* neighbor_ptr, cudaStream_t st) {
+    SweepArgs<float> a = base_args<float>(ws, n, ns, batch_idx, cutoff_sq);
+    a.num_neighbors = num_neighbors;
+    int rc = launch_query_reset(ws, a.L, n, 1, st);
+    if (rc) return rc;
+    RowsArgs r;
+    r.ws = ws; r.L = a.L; r.batch_idx = batch_idx; r.num_systems = ns; r.n = n; r.cutoff_sq = (float)cutoff_sq;
+    r.num_neighbors = num_neighbors;
+    rc = launch_rows_t<HALF, FMA>(r, st);                                   // wrapped inputs: the single sweep
+    if (rc) return rc;
+    a.queue = 0;
+    rc = launch_fast_t<float, FAST_COUNT, HALF, FMA, true>(a, st);          // unwrapped inputs: two-pass count (else retires)
+    if (rc) return rc;
+    a.queue = 3;
+    a.keep_deferred = 1;
+    rc = launch_sweep_t<float, MODE_COUNT, HALF, FMA>(a, st);               // whatever the lean kernels deferred
+    if (rc) return rc;
+    if (neighbor_ptr) {
+        Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
+        const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
+        k_scan<<<blocks, kScanThreads, 0, st>>>(num_neighbors, neighbor_ptr, n,
+                                               reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
+                                               &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count, nullptr);
+        NVNL_CHECK_LAUNCH("k_scan(neighbors)");
+    }
+    return 0;
+}
+
+template <bool HALF, bool FMA>
+int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, const int* neighbor_ptr,
+                int* edge_index, long long num_pairs, int* shifts, int index_offset, int hint, cudaStream_t st) {
+    SweepArgs<float> a = base_args<float>(ws, n, ns, batch_idx, cutoff_sq);
+    a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+    a.index_offset = index_offset;
+    if (hint & 1) {
+        // unwrapped input: the count ran on the two-pass kernels (hit masks), so does the fill
+        a.queue = 1;
+        k_gather_ptr<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr,
+                                                                       reinterpret_cast<int*>(ws + a.L.ptr_sorted));
+        NVNL_CHECK_LAUNCH("k_gather_ptr");
+        return launch_pair<float, MODE_FILL_COO, HALF, FMA>(a, hint, st);
+    }
+    k_rows_out<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts,
+                                                           index_offset);
+    NVNL_CHECK_LAUNCH("k_rows_out");
+    if (hint & 2) {
+        a.queue = 3;  // the deferred list of the count stage was kept for this launch
+        return launch_sweep_t<float, MODE_FILL_COO, HALF, FMA>(a, st);
     }
     return 0;
 }
@@ -250,9 +349,14 @@ int nvnl_abi_version(void) { return NVNL_ABI_VERSION; }
 const char* nvnl_last_error(void) { return g_err; }
 int64_t nvnl_launch_count(void) { return (int64_t)g_launches.load(); }
 
+void nvnl_set_rows_budget(int64_t entries_per_atom, int64_t slack_entries) {
+    g_rows_per_atom.store(entries_per_atom >= 0 ? entries_per_atom : kRowsPerAtom);
+    g_rows_slack.store(slack_entries >= 0 ? slack_entries : kRowsSlackEntries);
+}
+
 size_t nvnl_workspace_bytes(int64_t n_atoms, int64_t n_systems, int dtype) {
     if (n_atoms < 0 || n_systems < 0) return 0;
-    return make_layout(n_atoms, n_systems > 0 ? n_systems : 1, rec_bytes(dtype)).total;
+    return mk_layout(n_atoms, n_systems > 0 ? n_systems : 1, rec_bytes(dtype)).total;
 }
 
 int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
@@ -290,9 +394,9 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
 
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
                 int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, int32_t* had_deferred,
-                void* stream) {
+                int32_t* rows_overflow, void* stream) {
     if (!workspace) return fail(-1, "nvnl_status: null workspace");
-    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     Ctrl h;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemcpyAsync(&h, static_cast<unsigned char*>(workspace) + L.ctrl, sizeof(Ctrl),
@@ -306,6 +410,7 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
     if (error_bits) *error_bits = h.error;
     if (unwrapped) *unwrapped = h.unwrapped;
     if (had_deferred) *had_deferred = h.had_deferred;
+    if (rows_overflow) *rows_overflow = h.rows_overflow;
     return 0;
 }
 
@@ -339,6 +444,41 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
     return fail(-1, "nvnl_fill_coo: unsupported dtype");
 }
 
+int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                    double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr, void* stream) {
+    if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count_rows: bad arguments");
+    if (dtype != NVNL_F32) return fail(-1, "nvnl_count_rows: the single-sweep path is fp32 only (use nvnl_count)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (half_fill)
+        return fma ? count_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st)
+                   : count_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st);
+    return fma ? count_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st)
+               : count_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st);
+}
+
+int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
+                   int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream) {
+    if (!workspace || !neighbor_ptr || n_atoms <= 0) return fail(-1, "nvnl_fill_rows: bad arguments");
+    if (dtype != NVNL_F32) return fail(-1, "nvnl_fill_rows: the single-sweep path is fp32 only (use nvnl_fill_coo)");
+    if (launch_hint < 0) return fail(-1, "nvnl_fill_rows: launch_hint from nvnl_status is required");
+    if (num_pairs < 0 || num_pairs > 2147483647LL) return fail(-1, "nvnl_fill_rows: num_pairs outside int32 range");
+    if (num_pairs == 0) return 0;
+    if (!edge_index || !shifts) return fail(-1, "nvnl_fill_rows: null output");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (half_fill)
+        return fma ? fill_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+                                             shifts, index_offset, launch_hint, st)
+                   : fill_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+                                              shifts, index_offset, launch_hint, st);
+    return fma ? fill_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+                                          shifts, index_offset, launch_hint, st)
+               : fill_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+                                           shifts, index_offset, launch_hint, st);
+}
+
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                      double cutoff_sq, int half_fill, int fma, int32_t* neighbor_matrix, int32_t* neighbor_matrix_shifts,
                      int32_t* num_neighbors, int32_t max_neighbors, int32_t fill_value, int32_t pad_rows, void* stream) {
@@ -348,6 +488,10 @@ int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_syst
         return fail(-1, "nvnl_fill_matrix: null output");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32 || dtype == NVNL_F64) {
+        const int rc = launch_query_reset(ws, mk_layout(n_atoms, n_systems, rec_bytes(dtype)), n_atoms, 0, st);
+        if (rc) return rc;
+    }
     if (dtype == NVNL_F32) {
         SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_matrix = neighbor_matrix; a.out_shifts = neighbor_matrix_shifts; a.num_neighbors = num_neighbors;
@@ -366,7 +510,7 @@ int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_syst
 int nvnl_get_grid(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int32_t* cells_per_dimension,
                   int32_t* neighbor_search_radius, void* stream) {
     if (!workspace || n_systems <= 0) return fail(-1, "nvnl_get_grid: bad arguments");
-    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     k_get_grid<<<(n_systems + 127) / 128, 128, 0, st>>>(static_cast<const unsigned char*>(workspace), L, n_systems,
                                                        cells_per_dimension, neighbor_search_radius);
@@ -379,7 +523,7 @@ int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_sys
                       int32_t* atom_to_cell_mapping, int32_t* atoms_per_cell_count, int32_t* cell_atom_start_indices,
                       int64_t cache_cells, int32_t* cell_atom_list, void* stream) {
     if (!workspace || n_atoms <= 0 || n_systems <= 0 || cache_cells < 0) return fail(-1, "nvnl_export_cache: bad arguments");
-    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const unsigned char* ws = static_cast<const unsigned char*>(workspace);
     long long work = n_atoms > cache_cells ? n_atoms : cache_cells;
@@ -402,7 +546,7 @@ int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_sys
 int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
                            void* stream) {
     if (!workspace || !positions || n_atoms <= 0) return fail(-1, "nvnl_refresh_positions: bad arguments");
-    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     const unsigned blocks = (unsigned)((n_atoms + 255) / 256);
@@ -419,7 +563,7 @@ int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t 
 int nvnl_cells_changed(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
                        const int32_t* batch_idx, int32_t* flag, void* stream) {
     if (!workspace || !positions || !flag || n_atoms <= 0) return fail(-1, "nvnl_cells_changed: bad arguments");
-    const WsLayout L = make_layout(n_atoms, n_systems, rec_bytes(dtype));
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const unsigned char* ws = static_cast<const unsigned char*>(workspace);
     cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);

@@ -19,13 +19,15 @@ namespace nvnl {
 // ------------------------------------------------------------------------------------------------
 struct WsLayout {
     size_t ctrl, sys, bbox, cell_count, cell_start, atom_cell, atom_rank, atom_ashift, sorted, sorted_ashift,
-        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, total;
+        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, row_ref, rows, total;
     long long max_cells;  // N + S (upper bound on the number of cells, see k_grid)
+    long long rows_cap;   // entries of the temporary row buffer (single-sweep COO path, nvnl_rows.cuh)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline WsLayout make_layout(long long n, long long s, int rec_bytes) {
+__host__ __device__ inline WsLayout make_layout(long long n, long long s, int rec_bytes, long long rows_per_atom = kRowsPerAtom,
+                                                long long rows_slack = kRowsSlackEntries) {
     WsLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -51,6 +53,14 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     // (cell, first target) work items the fast kernel leaves to the general kernel: <= #cells + N/32 entries
     L.deferred = take(sizeof(int2) * (size_t)(L.max_cells + 2 + n / 32 + 1));
     L.ptr_sorted = take(sizeof(int) * (size_t)(n + 4));     // neighbor_ptr gathered into cell-sorted atom order
+    // single-sweep COO path: row_ref[i] = (first entry << 1) | has-shift-keys, or -1; rows = compact rows in sweep
+    // order.  Budget: kRowsPerAtom entries per atom + one reservation block per resident warp; more pairs than that
+    // (very large cutoffs) make the query fall back to the two-pass path.
+    L.row_ref = take(sizeof(int) * (size_t)n);
+    L.rows_cap = rows_per_atom * n + rows_slack;
+    if (L.rows_cap < 1) L.rows_cap = 1;
+    if (L.rows_cap > (1LL << 30) - 1) L.rows_cap = (1LL << 30) - 1;
+    L.rows = take(sizeof(int) * (size_t)L.rows_cap);
     L.total = o;
     return L;
 }

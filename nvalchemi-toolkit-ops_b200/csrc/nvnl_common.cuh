@@ -20,6 +20,8 @@ constexpr int kMaxImg = 128;                       // cell images handled per ba
 constexpr int kScanItems = 8;                      // items per thread in the look-back scan
 constexpr int kScanThreads = 1024;                 // 8192-element tiles: the serial look-back chain is 4x shorter
 constexpr int kScanTile = kScanItems * kScanThreads;
+constexpr int kRowsPerAtom = 160;                  // single-sweep COO path: temporary row entries budgeted per atom
+constexpr int kRowsSlackEntries = 148 * 4 * 8 * 2048;  // + one 2048-entry reservation block per resident consumer warp
 constexpr int kSmallBlock = 256;                   // block size of the per-system / bounding-box kernels
 
 enum SweepMode { MODE_COUNT = 0, MODE_FILL_COO = 1, MODE_FILL_MATRIX = 2 };
@@ -58,6 +60,9 @@ struct Ctrl {
     int had_deferred;                // sticky since the last build: some cell was deferred
     int max_count;                   // max over atoms of num_neighbors (overflow check vs max_neighbors)
     unsigned long long total_pairs;  // 64-bit sum of num_neighbors (overflow check for int32 ptr)
+    unsigned long long rows_cursor;  // single-sweep COO path: next free entry of the temporary row buffer
+    int rows_overflow;               // single-sweep COO path: the temporary row buffer was too small (host falls back)
+    int pad0;
 };
 
 // Sorted candidate record: position + original atom index. 16 B (float) / 32 B (double) so that a

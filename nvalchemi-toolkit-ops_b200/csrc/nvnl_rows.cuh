@@ -1,0 +1,555 @@
+// nvnl_rows.cuh — single-sweep COO path for fp32 inputs inside the primary periodic image.
+//
+// Why: the two-pass COO path (nvnl_fast.cuh: count -> hit masks -> scan -> mask expansion) was issue-bound in BOTH
+// sweeps (330 + 571 warp-instructions per atom, profiles/r1_final_1m_ncu.txt) and its fill pass wrote 360-byte rows
+// at random places of the output (cell-ordered sweep over randomly labelled atoms: 0.72 ms write-pattern floor,
+// profiles/r1_microbench_write_pattern.txt).  This path computes every distance once AND compacts once:
+//
+//   k_rows      (cell order)   stencil sweep; every lane APPENDS the tile index of its own hits to a lane-private
+//                              list in shared memory (predicated 16-bit store + pointer bump: 2 instructions per
+//                              target per 32 candidates, no ballot, no popc); per target one warp scan of the 32
+//                              list lengths, then the lists are gathered (tile index -> original atom index) into a
+//                              compact row of a TEMPORARY buffer handed out in blocks by one global cursor
+//                              (rows of a warp's targets are contiguous -> sequential DRAM writes).
+//                              Emits num_neighbors[i] and row_ref[i] (row location).
+//   k_scan                     neighbor_ptr (unchanged).
+//   k_rows_out  (index order)  streams the final arrays: rows are read from the temporary buffer (random 360-byte
+//                              reads) and edge_index / shifts are written strictly sequentially.
+//
+// Cells the lean kernel cannot take (too many images / candidates / targets) go to the general kernel exactly as in
+// the two-pass path; unwrapped inputs and fp64 use the two-pass path.
+// Replaces (different algorithm, same result): cell_list.py:372-556 + neighbor_utils.py:106-147, 362-441.
+#pragma once
+#include "nvnl_fast.cuh"
+
+namespace nvnl {
+
+constexpr int kRowsCons = 8;                          // consumer warps per CTA
+constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
+constexpr int kRowsListBytes = 32 * 32 * 2;           // per target: 32 lanes x 32 slots x u16 (a lane cannot have more hits than chunks)
+constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
+
+struct RowsSmem {
+    FastStage<float> stage[kFastStages];
+    int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
+    alignas(16) unsigned short lists[kRowsCons][2][32 * 32];                // lane-private hit lists, two targets per warp
+    unsigned long long full[kFastStages], empty[kFastStages];               // mbarriers of the ring
+};
+
+constexpr size_t rows_smem_bytes() { return (size_t)kFastStages * kFastStageBytes + sizeof(RowsSmem); }
+
+struct RowsArgs {
+    unsigned char* ws;
+    WsLayout L;
+    const int* batch_idx;
+    int num_systems;
+    long long n;
+    float cutoff_sq;
+    int* num_neighbors;
+};
+
+__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ int lds_u16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return (int)v;
+}
+
+// squared distances of one candidate to the two packed targets
+template <bool FMA, bool SHIFTED>
+__device__ __forceinline__ f32x2_t rows_d2(float x, float y, float z, f32x2_t XI, f32x2_t YI, f32x2_t ZI, float Sx, float Sy,
+                                           float Sz) {
+    f32x2_t dx = sub2(pack2(x, x), XI), dy = sub2(pack2(y, y), YI), dz = sub2(pack2(z, z), ZI);
+    if (SHIFTED) {
+        dx = add2(dx, pack2(Sx, Sx));
+        dy = add2(dy, pack2(Sy, Sy));
+        dz = add2(dz, pack2(Sz, Sz));
+    }
+    f32x2_t d2;
+    if (FMA) {
+        d2 = mul2(dx, dx);
+        d2 = fma2(dy, dy, d2);
+        d2 = fma2(dz, dz, d2);
+    } else {
+        d2 = add2(mul2(dx, dx), mul2(dy, dy));
+        d2 = add2(d2, mul2(dz, dz));
+    }
+    return d2;
+}
+
+// lanes that hit append the candidate's tile index c to their private lists (predicated 16-bit store + pointer bump)
+template <bool HALF, bool TAIL>
+__device__ __forceinline__ void rows_append(f32x2_t d2, int c, int j, int iA, int iB, float rc2, bool lexpos, bool valid,
+                                            uint32_t& la, uint32_t& lb) {
+    float dA, dB;
+    unpack2(d2, dA, dB);
+    bool hA = dA < rc2, hB = dB < rc2;
+    if (TAIL) { hA = hA && valid; hB = hB && valid; }
+    if (HALF) {
+        hA = hA && (iA < j || (iA == j && lexpos));
+        hB = hB && (iB < j || (iB == j && lexpos));
+    }
+    if (hA) { sts_u16(la, c); la += 64u; }
+    if (hB) { sts_u16(lb, c); lb += 64u; }
+}
+
+// one 32-candidate chunk against two targets
+template <bool HALF, bool FMA, bool SHIFTED, bool TAIL>
+__device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
+                                            float Sx, float Sy, float Sz, float rc2, bool lexpos, bool valid,
+                                            uint32_t& la, uint32_t& lb) {
+    float x, y, z;
+    int j;
+    lds_rec(addr, x, y, z, j);
+    const f32x2_t d2 = rows_d2<FMA, SHIFTED>(x, y, z, XI, YI, ZI, Sx, Sy, Sz);
+    rows_append<HALF, TAIL>(d2, c, j, iA, iB, rc2, lexpos, valid, la, lb);
+}
+
+// four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp)
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
+                                              float rc2, uint32_t& la, uint32_t& lb) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    float x[4], y[4], z[4];
+    int j[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) lds_rec(addr + (uint32_t)u * 32u * RS, x[u], y[u], z[u], j[u]);
+    f32x2_t d2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d2[u] = rows_d2<FMA, false>(x[u], y[u], z[u], XI, YI, ZI, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rows_append<HALF, false>(d2[u], c + 32 * u, j[u], iA, iB, rc2, false, true, la, lb);
+}
+
+// Sweep of two targets over the staged tile (same chunk structure as fast_masks2).  la / lb: per-lane append pointers.
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t cand_addr, f32x2_t XI, f32x2_t YI,
+                                            f32x2_t ZI, int iA, int iB, float rc2, int lane, uint32_t& la, uint32_t& lb) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    const int total = sm.total, nchunks = sm.nchunks;
+    const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;
+    const int nzfull = zend >> 5;
+    uint32_t addr = cand_addr + (uint32_t)lane * RS;
+    int c = lane;
+    int ck = 0;
+#pragma unroll 1
+    for (; ck + 4 <= nzfull; ck += 4) {
+        rows_chunk2x4<HALF, FMA>(addr, c, XI, YI, ZI, iA, iB, rc2, la, lb);
+        addr += 128 * RS;
+        c += 128;
+    }
+#pragma unroll 1
+    for (; ck < nzfull; ++ck) {
+        rows_chunk2<HALF, FMA, false, false>(addr, c, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, la, lb);
+        addr += 32 * RS;
+        c += 32;
+    }
+    if (sm.nseg == 1 && ck < nchunks) {
+        rows_chunk2<HALF, FMA, false, true>(addr, c, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, c < total, la, lb);
+        ++ck;
+    }
+#pragma unroll 1
+    for (; ck < nchunks; ++ck) {
+        int sg = sm.chunk_seg[ck];
+        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+        bool lexpos = false;
+        if (HALF) {
+            int csx, csy, csz;
+            unpack_key(sm.seg_key[sg], csx, csy, csz);
+            lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
+        }
+        rows_chunk2<HALF, FMA, true, true>(addr, c, XI, YI, ZI, iA, iB, sm.segS[3 * sg], sm.segS[3 * sg + 1], sm.segS[3 * sg + 2],
+                                           rc2, lexpos, c < total, la, lb);
+        addr += 32 * RS;
+        c += 32;
+    }
+}
+
+// Per-warp allocator state of the temporary row buffer.
+struct RowsAlloc {
+    long long pos, end;
+};
+
+// Epilogue of one target: drop the self entry, scan the list lengths, reserve the row, gather tile index -> atom index.
+template <bool HALF>
+__device__ __forceinline__ void rows_emit(const RowsArgs& a, const FastStage<float>& sm, Ctrl* ctrl, uint32_t cand_addr,
+                                          uint32_t lbase, uint32_t lend, int self, int i, int lane, bool shifted,
+                                          RowsAlloc& al, int* __restrict__ rows, int* __restrict__ row_ref) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    int n = (int)((lend - lbase) >> 6);
+    if (!HALF) {
+        // (i, i, 0) is not a pair: the target itself (tile index `self`, zero shift, d = 0) is always in the list of
+        // lane self & 31 — replace it with that lane's last entry
+        if (lane == (self & 31)) {
+            for (int s = 0; s < n; ++s) {
+                if (lds_u16(lbase + (uint32_t)s * 64u) == self) {
+                    sts_u16(lbase + (uint32_t)s * 64u, lds_u16(lbase + (uint32_t)(n - 1) * 64u));
+                    --n;
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    const int incl = warp_incl_scan(n, lane);
+    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    const int maxn = __reduce_max_sync(0xffffffffu, n);
+    const int need = shifted ? 2 * cnt : cnt;
+    bool ok = true;
+    if (al.pos + need > al.end) {
+        const long long sz = need > kRowsBlock ? need : kRowsBlock;
+        unsigned long long b = 0ull;
+        if (lane == 0) b = atomicAdd(&ctrl->rows_cursor, (unsigned long long)sz);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if ((long long)b + sz > a.L.rows_cap) {
+            // temporary buffer exhausted: the host re-runs the query on the two-pass path (nvnl_status.rows_overflow)
+            if (lane == 0) ctrl->rows_overflow = 1;
+            al.pos = al.end = 0;
+            ok = false;
+        } else {
+            al.pos = (long long)b;
+            al.end = (long long)b + sz;
+        }
+    }
+    if (ok) {
+        const int start = (int)al.pos;
+        al.pos += need;
+        int* row = rows + start + excl;
+        for (int s = 0; s < maxn; ++s) {
+            if (s < n) {
+                const int c = lds_u16(lbase + (uint32_t)s * 64u);
+                row[s] = lds_rec_j<float>(cand_addr + (uint32_t)c * RS);
+                if (shifted) {
+                    int sg = sm.chunk_seg[c >> 5];
+                    while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+                    row[cnt + s] = sm.seg_key[sg];
+                }
+            }
+        }
+        if (lane == 0) row_ref[i] = (start << 1) | (shifted ? 1 : 0);
+    }
+    if (lane == 0) a.num_neighbors[i] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_rows: warp-specialised persistent kernel (producer identical in role to k_fast's: queue -> stencil images ->
+// shift sort -> segment/chunk tables -> TMA bulk copies into a 2-stage ring).
+// ------------------------------------------------------------------------------------------------
+template <bool HALF, bool FMA>
+__global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
+    using T = float;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kStageBytes = kFastStageBytes;
+    RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kFastStages * kStageBytes);
+    const uint32_t smem_base = smem_u32(smem_raw);
+    constexpr uint32_t RS = sizeof(Rec<T>);
+    constexpr int cap = kCandBytes / (int)RS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(a.ws + a.L.ctrl);
+
+    {
+        // re-arm the look-back scan that turns the counts into neighbor_ptr (runs after the count kernels)
+        unsigned long long* st1 = reinterpret_cast<unsigned long long*>(a.ws + a.L.scan_status1);
+        const long long nst = (a.n + 1) / kScanTile + 2;
+        for (long long k = (long long)blockIdx.x * blockDim.x + tid; k < nst; k += (long long)gridDim.x * blockDim.x)
+            st1[k] = 0ull;
+        if (blockIdx.x == 0 && tid == 0) {
+            ctrl->scan_tile[1] = 0;
+            ctrl->total_pairs = 0ull;
+            ctrl->max_count = 0;
+        }
+    }
+    // unwrapped inputs are served by the two-pass kernels launched next to this one
+    const bool active = ctrl->unwrapped == 0;
+    if (tid == 0) {
+        for (int st = 0; st < kFastStages; ++st) {
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kRowsCons);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // =========================== producer ===========================
+        const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
+        const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
+        const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
+        int2* deferred = reinterpret_cast<int2*>(a.ws + a.L.deferred);
+        const int total_cells = active ? ctrl->total_cells : 0;
+        int stage = 0;
+        uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
+        int g_next = 0;
+        if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+        for (;;) {
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
+            FastStage<T>& sg = sm.stage[stage];
+            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kStageBytes);
+            bool done = false;
+            for (;;) {
+                const int g = __shfl_sync(0xffffffffu, g_next, 0);
+                if (g >= total_cells) {
+                    done = true;
+                    break;
+                }
+                if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+                const int home_start = cell_start[g];
+                const int ntarget = cell_start[g + 1] - home_start;
+                if (ntarget == 0) continue;
+                int s = 0;
+                if (a.num_systems > 1) s = a.batch_idx[sorted[home_start].j];
+                const SysParams& sp = sys[s];
+                const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
+                const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];
+                const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
+                const int nimg = nx * ny * nzz;
+                bool ok = nimg <= 32 && ntarget <= kFastMaxTargets;
+                int st = 0, cn = 0, key = kKeyEmpty, tag = 0;
+                const int coff = sp.cell_offset;
+                if (ok && lane < nimg) {
+                    const int local = g - coff;
+                    const int cx = local % cpd0, cy = (local / cpd0) % cpd1, cz = local / (cpd0 * cpd1);
+                    const int dx = lane % nx - R0, dy = (lane / nx) % ny - R1, dz = lane / (nx * ny) - R2;
+                    int tx = cx + dx, ty = cy + dy, tz = cz + dz;
+                    bool in = true;
+                    int csx = 0, csy = 0, csz = 0;
+                    if (sp.pbc[0]) divmod_floor(tx, cpd0, csx, tx); else in = in && tx >= 0 && tx < cpd0;
+                    if (sp.pbc[1]) divmod_floor(ty, cpd1, csy, ty); else in = in && ty >= 0 && ty < cpd1;
+                    if (sp.pbc[2]) divmod_floor(tz, cpd2, csz, tz); else in = in && tz >= 0 && tz < cpd2;
+                    if (in) {
+                        const int gc = coff + tx + cpd0 * (ty + cpd1 * tz);
+                        st = cell_start[gc];
+                        cn = cell_start[gc + 1] - st;
+                        if (cn > 0) key = pack_key(csx, csy, csz);
+                    }
+                    tag = (dx == 0 && dy == 0 && dz == 0) ? 1 : 0;
+                }
+                const unsigned shiftmask = __ballot_sync(0xffffffffu, key != 0 && key != kKeyEmpty);
+                if (ok && shiftmask) {
+                    // order the images by shift: equal shifts become one contiguous segment, zero shift first
+                    int rank = 0;
+                    for (int t = 0; t < 32; ++t) {
+                        const int kt = __shfl_sync(0xffffffffu, key, t);
+                        rank += (kt < key || (kt == key && t < lane)) ? 1 : 0;
+                    }
+                    sm.e_st[rank] = st; sm.e_cn[rank] = cn; sm.e_key[rank] = key; sm.e_tag[rank] = tag;
+                    __syncwarp();
+                    st = sm.e_st[lane]; cn = sm.e_cn[lane]; key = sm.e_key[lane]; tag = sm.e_tag[lane];
+                    __syncwarp();
+                }
+                const int incl = warp_incl_scan(cn, lane);
+                const int off = incl - cn;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                ok = ok && total <= cap;
+                int nseg = 1;
+                if (ok) {
+                    if (shiftmask) {
+                        const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+                        const bool head = cn > 0 && (lane == 0 || pk != key);
+                        const unsigned hm = __ballot_sync(0xffffffffu, head);
+                        nseg = __popc(hm);
+                        if (head) {
+                            const int si = __popc(hm & ((1u << lane) - 1u));
+                            sg.seg_begin[si] = off;
+                            sg.seg_key[si] = key;
+                            int csx, csy, csz;
+                            unpack_key(key, csx, csy, csz);
+                            T cm[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
+                            T Sx, Sy, Sz;
+                            shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
+                            sg.segS[3 * si] = Sx; sg.segS[3 * si + 1] = Sy; sg.segS[3 * si + 2] = Sz;
+                        }
+                        if (lane == 0) sg.seg_begin[nseg] = total;
+                    } else if (lane == 0) {
+                        sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0;
+                    }
+                    __syncwarp();
+                    const int nchunks = (total + 31) >> 5;
+                    if (lane < nchunks) {
+                        int sgi = 0;
+                        while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
+                        sg.chunk_seg[lane] = sgi;
+                    }
+                    if (!shiftmask && lane < 3) sg.segS[lane] = (T)0;
+                    if (lane == 0) sg.nchunks = nchunks;
+                }
+                if (!ok) {
+                    // leave the cell to the general kernel as work items of kDeferTargets target atoms
+                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
+                    int base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(&ctrl->n_deferred, nitems);
+                        ctrl->had_deferred = 1;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
+                    continue;
+                }
+                const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
+                const int home_lane = __ffs(tagm) - 1;
+                const int home_off = __shfl_sync(0xffffffffu, off, home_lane);
+                if (lane == 0) {
+                    sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
+                    sg.nseg = nseg; sg.total = total; sg.next_target = 0;
+                }
+                const uint32_t tx = (uint32_t)total * RS;
+                __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
+                if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), tx);
+                __syncwarp();
+                if (cn > 0)
+                    tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                break;
+            }
+            if (done) {
+                if (lane == 0) {
+                    sg.item = -1;
+                    mbar_arrive(reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                }
+                break;
+            }
+            if (++stage == kFastStages) { stage = 0; ephase ^= 1u; }
+        }
+        // the last CTA to drain the queue re-arms it for the next launch on this workspace
+        if (lane == 0) {
+            __threadfence();
+            const int d = atomicAdd(&ctrl->done[0], 1);
+            if (d == (int)gridDim.x - 1) {
+                ctrl->work_counter[0] = 0;
+                ctrl->done[0] = 0;
+            }
+        }
+    } else {
+        // =========================== consumers ===========================
+        const int cw = warp - 1;
+        int* rows = reinterpret_cast<int*>(a.ws + a.L.rows);
+        int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
+        const uint32_t lbaseA = smem_u32(&sm.lists[cw][0][0]) + (uint32_t)lane * 2u;
+        const uint32_t lbaseB = smem_u32(&sm.lists[cw][1][0]) + (uint32_t)lane * 2u;
+        RowsAlloc al;
+        al.pos = al.end = 0;
+        const float rc2 = a.cutoff_sq;
+        int stage = 0;
+        uint32_t fphase = 0;
+        for (;;) {
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
+            FastStage<T>& sg = sm.stage[stage];
+            if (sg.item < 0) break;
+            const uint32_t cand_addr = smem_base + (uint32_t)stage * kStageBytes;
+            const int ntarget = sg.ntarget, home_off = sg.home_off;
+            const bool shifted = sg.nseg > 1 || sg.seg_key[0] != 0;
+            for (;;) {
+                // two targets per trip: they share every candidate load and every FP instruction (f32x2)
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&sg.next_target, 2);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= ntarget) break;
+                const bool two = t + 1 < ntarget;
+                const int selfA = home_off + t, selfB = two ? selfA + 1 : selfA;
+                float xa, ya, za, xb, yb, zb;
+                int iA, iB;
+                lds_rec(cand_addr + (uint32_t)selfA * RS, xa, ya, za, iA);
+                lds_rec(cand_addr + (uint32_t)selfB * RS, xb, yb, zb, iB);
+                // x + (-0) == x bit for bit: one packed add gives each target pair a home in an aligned register pair
+                const f32x2_t nz = pack2(-0.0f, -0.0f);
+                const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
+                uint32_t la = lbaseA, lb = lbaseB;
+                rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, la, lb);
+                rows_emit<HALF>(a, sg, ctrl, cand_addr, lbaseA, la, selfA, iA, lane, shifted, al, rows, row_ref);
+                if (two) rows_emit<HALF>(a, sg, ctrl, cand_addr, lbaseB, lb, selfB, iB, lane, shifted, al, rows, row_ref);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
+            if (++stage == kFastStages) { stage = 0; fphase ^= 1u; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_rows_out: the final arrays in atom-index order.  One warp per 32 consecutive atoms; rows come from the temporary
+// buffer (row_ref), everything written is sequential in the large: out_i (= i), out_j, shifts (zeros unless the row's
+// cell touched a periodic boundary, then the packed image keys stored behind the row are unpacked).
+// Atoms with row_ref < 0 were handled by the general kernel, which writes their rows itself.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int value, int lane) {
+    int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
+    head = head < n ? head : n;
+    if (lane < head) dst[lane] = value;
+    int4* v = reinterpret_cast<int4*>(dst + head);
+    const int nv = (n - head) >> 2;
+    const int4 val = make_int4(value, value, value, value);
+    for (int q = lane; q < nv; q += 32) v[q] = val;
+    const int tail = (n - head) & 3;
+    if (lane < tail) dst[head + 4 * nv + lane] = value;
+}
+
+__global__ void __launch_bounds__(256) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
+                                                  const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
+                                                  int* __restrict__ out_j, int* __restrict__ out_shifts, int index_offset) {
+    const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
+    const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
+    const int lane = threadIdx.x & 31;
+    const long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (base >= n) return;
+    const long long il = base + lane;
+    const int ref_l = il < n ? row_ref[il] : -1;
+    const int p_l = neighbor_ptr[il < n ? il : n];
+    const int pe_l = neighbor_ptr[il + 1 < n ? il + 1 : n];
+    const int na = n - base < 32 ? (int)(n - base) : 32;
+    for (int t = 0; t < na; ++t) {
+        const int ref = __shfl_sync(0xffffffffu, ref_l, t);
+        const int p = __shfl_sync(0xffffffffu, p_l, t);
+        const int cnt = __shfl_sync(0xffffffffu, pe_l, t) - p;
+        if (ref < 0 || cnt <= 0) continue;
+        const int* __restrict__ row = rows + (ref >> 1);
+        const int iv = (int)(base + t) + index_offset;
+        for (int k0 = 0; k0 < cnt; k0 += 128) {
+            int v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + lane + 32 * u;
+                v[u] = k < cnt ? row[k] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + lane + 32 * u;
+                if (k < cnt) out_j[(size_t)p + k] = v[u] + index_offset;
+            }
+        }
+        warp_fill(out_i + (size_t)p, cnt, iv, lane);
+        int* sh = out_shifts + 3 * (size_t)p;
+        if (!(ref & 1)) {
+            warp_fill(sh, 3 * cnt, 0, lane);
+        } else {
+            for (int k = lane; k < cnt; k += 32) {
+                int csx, csy, csz;
+                unpack_key(row[cnt + k], csx, csy, csz);
+                sh[3 * k] = csx;
+                sh[3 * k + 1] = csy;
+                sh[3 * k + 2] = csz;
+            }
+        }
+    }
+}
+
+// resets the per-query state of the control block and marks every atom "no temporary row"
+__global__ void k_query_reset(unsigned char* __restrict__ ws, WsLayout L, long long n, int with_rows) {
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid == 0) {
+        ctrl->n_deferred = 0;
+        ctrl->rows_cursor = 0ull;
+        ctrl->rows_overflow = 0;
+    }
+    if (with_rows) {
+        int* row_ref = reinterpret_cast<int*>(ws + L.row_ref);
+        for (long long i = gid; i < n; i += (long long)gridDim.x * blockDim.x) row_ref[i] = -1;
+    }
+}
+
+}  // namespace nvnl

@@ -41,6 +41,7 @@ struct SweepArgs {
     int index_offset;         // added to every atom index written to COO outputs (rank sharding)
     int queue;                // which Ctrl::work_counter this launch uses
     int pad;                  // FILL_MATRIX: write fill_value / zero shifts into the unused slots of every row
+    int keep_deferred;        // COUNT of the single-sweep COO path: leave the deferred list for the FILL launch (wrapped inputs)
 };
 
 constexpr int kKeyEmpty = 0x7fffffff;
@@ -602,7 +603,9 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
         if (d == (int)gridDim.x - 1) {
             ctrl->work_counter[a.queue] = 0;
             ctrl->done[a.queue] = 0;
-            ctrl->n_deferred = 0;  // consumed: the next fast launch rebuilds the list
+            // consumed: the next fast launch rebuilds the list.  The single-sweep COO path has no fast FILL launch, so
+            // its COUNT launch keeps the list for the general FILL launch (unwrapped inputs take the two-pass path).
+            if (!(a.keep_deferred && ctrl->unwrapped == 0)) ctrl->n_deferred = 0;
         }
     }
 }

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libnvalchemi_nl_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 c_void_p, c_int, c_int32, c_int64, c_double, c_size_t = (
@@ -21,6 +21,7 @@ _SIGNATURES = {
     "nvnl_abi_version": (c_int, []),
     "nvnl_last_error": (ctypes.c_char_p, []),
     "nvnl_launch_count": (c_int64, []),
+    "nvnl_set_rows_budget": (None, [c_int64, c_int64]),
     "nvnl_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "nvnl_build": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double,
                            c_void_p, c_size_t, c_void_p]),
@@ -28,7 +29,11 @@ _SIGNATURES = {
                            c_void_p]),
     "nvnl_status": (c_int, [c_void_p, c_int, c_int64, c_int32, ctypes.POINTER(c_int64), ctypes.POINTER(c_int32),
                             ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
-                            ctypes.POINTER(c_int32), c_void_p]),
+                            ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_void_p]),
+    "nvnl_count_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    "nvnl_fill_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
+                               c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_coo": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
                               c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_matrix": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p,

@@ -5,3 +5,11 @@
 #         ``fuse_fp`` (fmad=true);  False = every multiply/add rounded separately.
 # Only pairs within ~1 ulp of the cutoff can differ between the two (SURVEY.md §7 "knife-edge").
 fma: bool = True
+
+# COO output path for fp32 inputs.
+# "rows"  = single sweep: distances and compaction done once into a temporary row buffer, then the final arrays are
+#           streamed in atom order (csrc/nvnl_rows.cuh);  falls back to "masks" when the temporary buffer (160 entries
+#           per atom) is too small.
+# "masks" = two sweeps: count pass stores hit masks, fill pass expands them at neighbor_ptr (csrc/nvnl_fast.cuh).
+# fp64 inputs always take "masks".  Both produce the same sets (tests/test_gpu_parity.py runs both).
+coo_path: str = "rows"

@@ -55,11 +55,12 @@ def cutoff_sq_in_dtype(cutoff: float, dtype: torch.dtype, python_double: bool = 
 class CellListHandle:
     """Result of ``build``: the opaque device workspace plus what the queries need."""
 
-    __slots__ = ("ws", "dtype_code", "n", "ns", "batch_idx", "dtype", "device", "cutoff")
+    __slots__ = ("ws", "dtype_code", "n", "ns", "batch_idx", "dtype", "device", "cutoff", "rows_overflow")
 
     def __init__(self, ws, dtype_code, n, ns, batch_idx, dtype, device, cutoff):
         self.ws, self.dtype_code, self.n, self.ns = ws, dtype_code, n, ns
         self.batch_idx, self.dtype, self.device, self.cutoff = batch_idx, dtype, device, cutoff
+        self.rows_overflow = False
 
 
 def _stream(device) -> ctypes.c_void_p:
@@ -116,14 +117,15 @@ def status(h: CellListHandle):
     launch_hint (bit 0: atoms outside the primary image, bit 1: cells left to the general kernel) lets the fill
     stage launch only the kernels that have work."""
     L = _lib.lib()
-    tp, mc, tc, eb, uw, hd = (ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0),
-                              ctypes.c_int32(0))
+    tp, mc, tc, eb, uw, hd, ro = (ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0),
+                                  ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0))
     with torch.cuda.device(h.device):
         _lib.check(
             L.nvnl_status(_ptr(h.ws), h.dtype_code, h.n, h.ns, ctypes.byref(tp), ctypes.byref(mc), ctypes.byref(tc),
-                          ctypes.byref(eb), ctypes.byref(uw), ctypes.byref(hd), _stream(h.device)),
+                          ctypes.byref(eb), ctypes.byref(uw), ctypes.byref(hd), ctypes.byref(ro), _stream(h.device)),
             "nvnl_status",
         )
+    h.rows_overflow = bool(ro.value)
     return tp.value, mc.value, tc.value, eb.value, (1 if uw.value else 0) | (2 if hd.value else 0)
 
 
@@ -150,31 +152,41 @@ def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_
         )
 
 
-def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True):
-    """num_neighbors [N] and (optionally) neighbor_ptr [N+1] (nvnl_count); asynchronous."""
+def use_rows(h: CellListHandle) -> bool:
+    """fp32 inputs take the single-sweep COO path unless config.coo_path says otherwise."""
+    if config.coo_path not in ("rows", "masks"):
+        raise ValueError(f"config.coo_path must be 'rows' or 'masks', not {config.coo_path!r}")
+    return config.coo_path == "rows" and h.dtype == torch.float32
+
+
+def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False):
+    """num_neighbors [N] and (optionally) neighbor_ptr [N+1] (nvnl_count / nvnl_count_rows); asynchronous.
+    ``rows=True`` also leaves every atom's neighbors in the workspace's temporary row buffer for ``fill_coo(rows=True)``."""
     num = torch.empty(h.n, dtype=torch.int32, device=h.device)
     ptr = torch.empty(h.n + 1, dtype=torch.int32, device=h.device) if want_ptr else None
     L = _lib.lib()
+    fn, name = (L.nvnl_count_rows, "nvnl_count_rows") if rows else (L.nvnl_count, "nvnl_count")
     with torch.cuda.device(h.device):
         _lib.check(
-            L.nvnl_count(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq), int(bool(half_fill)),
-                         int(bool(config.fma)), _ptr(num), _ptr(ptr), _stream(h.device)),
-            "nvnl_count",
+            fn(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq), int(bool(half_fill)),
+               int(bool(config.fma)), _ptr(num), _ptr(ptr), _stream(h.device)),
+            name,
         )
     return num, ptr
 
 
 def fill_coo(h: CellListHandle, cutoff_sq, neighbor_ptr, edge_index, shifts, num_pairs, half_fill=False,
-             index_offset=0, launch_hint=-1):
-    """Write COO rows at neighbor_ptr (nvnl_fill_coo).  ``edge_index`` is [2, num_pairs] (or a block laid out
-    as such with row stride ``num_pairs``), ``shifts`` [num_pairs, 3]."""
+             index_offset=0, launch_hint=-1, rows=False):
+    """Write COO rows at neighbor_ptr (nvnl_fill_coo, or nvnl_fill_rows after ``count(rows=True)``).  ``edge_index``
+    is [2, num_pairs] (or a block laid out as such with row stride ``num_pairs``), ``shifts`` [num_pairs, 3]."""
     L = _lib.lib()
+    fn, name = (L.nvnl_fill_rows, "nvnl_fill_rows") if rows else (L.nvnl_fill_coo, "nvnl_fill_coo")
     with torch.cuda.device(h.device):
         _lib.check(
-            L.nvnl_fill_coo(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
-                            int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_ptr), _ptr(edge_index),
-                            int(num_pairs), _ptr(shifts), int(index_offset), int(launch_hint), _stream(h.device)),
-            "nvnl_fill_coo",
+            fn(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
+               int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_ptr), _ptr(edge_index),
+               int(num_pairs), _ptr(shifts), int(index_offset), int(launch_hint), _stream(h.device)),
+            name,
         )
 
 
@@ -182,8 +194,7 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     """COO outputs ``(neighbor_list [2,P], neighbor_ptr [N+1], shifts [P,3])``: count -> scan -> one sync for the
     size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
-    num, ptr = count(h, cutoff_sq, half_fill)
-    total, max_count, _cells, err, hint = status(h)
+    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
@@ -194,8 +205,23 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     edge_index = buf[: 2 * total].view(2, total)
     shifts = buf[2 * total:].view(total, 3)
     if total > 0:
-        fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill, launch_hint=hint)
+        fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill, launch_hint=hint, rows=rows)
     return edge_index, ptr, shifts, num
+
+
+def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False):
+    """Count stage + the one host sync: ``(num, ptr, total, max_count, error_bits, launch_hint, rows)``.  ``rows``
+    tells ``fill_coo`` which path the count ran on (single sweep unless fp64 / configured off / its temporary row
+    buffer overflowed, in which case the count is repeated on the two-pass path)."""
+    rows = use_rows(h)
+    num, ptr = count(h, cutoff_sq, half_fill, rows=rows)
+    total, max_count, _cells, err, hint = status(h)
+    if rows and h.rows_overflow:
+        rows = False
+        num, ptr = count(h, cutoff_sq, half_fill)
+        total, max_count, _cells, err, hint = status(h)
+        h.rows_overflow = True  # sticky: this query did not fit the temporary row buffer
+    return num, ptr, total, max_count, err, hint, rows
 
 
 def get_grid(h: CellListHandle):

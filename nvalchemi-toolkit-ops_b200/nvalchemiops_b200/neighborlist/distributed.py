@@ -49,14 +49,13 @@ def _default_local_coo(positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_
 
     h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
     csq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
-    num, ptr = _engine.count(h, csq, half_fill)
-    total, max_count, _c, err, hint = _engine.status(h)
+    num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, csq, half_fill)
     _engine._raise_on_error_bits(err)
 
     def fill(block, pmax):
         if total > 0:
             _engine.fill_coo(h, csq, ptr, block[: 2 * pmax], block[2 * pmax: 5 * pmax], pmax, half_fill, index_offset,
-                             launch_hint=hint)
+                             launch_hint=hint, rows=rows)
 
     return num, total, max_count, fill
 

@@ -590,3 +590,140 @@ def test_torch_compile_keeps_the_matrix_op_in_the_graph():
     assert total == eager_total == want.shape[0]
     assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
     _check_matrix_padding(nm, num, sh, 500)
+
+
+# ----------------------------------------------------------------------------------------------
+# the two COO paths (config.coo_path): "rows" = single sweep + streamed output (default for fp32),
+# "masks" = count -> hit masks -> fill.  Everything above runs on the default; these pin both.
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(params=["rows", "masks"])
+def coo_path(request):
+    from nvalchemiops_b200 import config
+
+    old = config.coo_path
+    config.coo_path = request.param
+    yield request.param
+    config.coo_path = old
+
+
+@pytest.mark.parametrize("pbc_flag", [[True, True, True], [True, False, True], [False, False, False]])
+def test_coo_paths_medium_box(coo_path, pbc_flag):
+    """6000 atoms in a 40 A box (7 cells per periodic dim: interior cells, boundary cells with image shifts, open
+    faces): COO full and half fill, both fma modes, sorted sources, CSR consistency."""
+    from nvalchemiops_b200 import config
+
+    pos, cell, pbc = random_system(6000, 40.0, torch.float32, seed=31, pbc_flag=pbc_flag)
+    try:
+        for fma in (True, False):
+            config.fma = fma
+            o = ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=256, nthreads=8, fma_mode=int(fma))
+            assert o[1].max() <= 256
+            want = ro.records_from_matrix(*o)
+            e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256,
+                                      return_neighbor_list=True)
+            assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), (coo_path, fma)
+            assert (e[0, 1:] >= e[0, :-1]).all()
+            assert torch.equal(torch.bincount(e[0].long(), minlength=6000).to(torch.int32), p[1:] - p[:-1])
+            assert np.array_equal(o[1], (p[1:] - p[:-1]).cpu().numpy())
+    finally:
+        config.fma = True
+    eh, ph, sh = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256, half_fill=True,
+                                 return_neighbor_list=True)
+    assert 2 * eh.shape[1] == want.shape[0]
+    assert np.array_equal(ro.canonical_undirected(ro.records_from_coo(eh.cpu(), sh.cpu())),
+                          np.unique(ro.canonical_undirected(want), axis=0))
+
+
+def test_coo_paths_coincident_atoms_and_small_periodic_box(coo_path):
+    """Distinct atoms at identical coordinates are neighbors (d = 0 < rc) while (i, i, 0) is not; a periodic box
+    with two cells per dimension makes every stencil hold the same cells under several image shifts."""
+    pos, cell, pbc = random_system(1500, 25.0, torch.float32, seed=5)
+    pos[100] = pos[7]
+    pos[101] = pos[7]
+    pos[900] = pos[899]
+    for rc in (6.0, 4.0):
+        o = ro.cell_list(pos, rc, cell, pbc, max_neighbors=256, nthreads=8)
+        want = ro.records_from_matrix(*o)
+        e, p, s = _nl().cell_list(pos.to(DEV), rc, cell.to(DEV), pbc.to(DEV), max_neighbors=256, return_neighbor_list=True)
+        got = ro.records_from_coo(e.cpu(), s.cpu())
+        assert np.array_equal(got, want), (coo_path, rc)
+        assert not ((got[:, 0] == got[:, 1]) & (got[:, 2:] == 0).all(1)).any()
+        assert ((got[:, 0] == 100) & (got[:, 1] == 7) & (got[:, 2:] == 0).all(1)).any()
+    pos, cell, pbc = random_system(400, 12.5, torch.float32, seed=6)     # cpd = 2: images of the same cells
+    want = ro.records_from_matrix(*ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=512, nthreads=8))
+    e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=512, return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), coo_path
+
+
+def test_coo_paths_batch_and_sharded_blocks(coo_path):
+    """Batched mixed-PBC systems through the public API, and the rank-sharded fill (index_offset, block layout)."""
+    from nvalchemiops_b200.neighborlist import _engine
+
+    pos, cell, pbc, bidx, bptr = bench_batch(12, 300, 900, seed=21, mixed_pbc=True)
+    want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1024))
+    d = [t.to(DEV) for t in (pos, cell, pbc, bidx, bptr)]
+    e, p, s = _nl().batch_cell_list(d[0], 6.0, d[1], d[2], d[3], return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), coo_path
+    # sharded block: second half of the systems as a "rank" with global indices
+    s0, s1 = 6, 12
+    a0, a1 = int(bptr[s0]), int(bptr[s1])
+    lptr = (d[4][s0:s1 + 1] - a0).to(torch.int32)
+    lidx = (d[3][a0:a1] - s0).to(torch.int32)
+    h = _engine.build(d[0][a0:a1], 6.0, d[1][s0:s1], d[2][s0:s1], batch_idx=lidx, batch_ptr=lptr)
+    num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, 36.0)
+    assert rows == (coo_path == "rows")
+    pmax = total + 5
+    block = torch.full((5 * pmax,), -7, dtype=torch.int32, device=DEV)
+    _engine.fill_coo(h, 36.0, ptr, block[:2 * pmax], block[2 * pmax:], pmax, False, a0, launch_hint=hint, rows=rows)
+    torch.cuda.synchronize()
+    edge = torch.stack([block[:total], block[pmax:pmax + total]])
+    shifts = block[2 * pmax:2 * pmax + 3 * total].reshape(total, 3)
+    sel = (want[:, 0] >= a0) & (want[:, 0] < a1)
+    assert np.array_equal(ro.records_from_coo(edge.cpu(), shifts.cpu()), want[sel]), coo_path
+    assert (block[total:pmax] == -7).all() and (block[2 * pmax + 3 * total:] == -7).all()
+
+
+def test_rows_path_overflow_falls_back_to_masks():
+    """A temporary row buffer that is too small must not change the result: the engine repeats the query on the
+    two-pass path (nvnl_status.rows_overflow)."""
+    from nvalchemiops_b200 import _lib, config
+    from nvalchemiops_b200.neighborlist import _engine
+
+    assert config.coo_path == "rows"
+    pos, cell, pbc = random_system(6000, 40.0, torch.float32, seed=33)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=256, nthreads=8))
+    L = _lib.lib()
+    L.nvnl_set_rows_budget(8, 0)
+    try:
+        h = _engine.build(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV))
+        num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, 36.0)
+        assert h.rows_overflow and not rows
+        e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=256, return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    finally:
+        L.nvnl_set_rows_budget(-1, -1)
+    h = _engine.build(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV))
+    num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, 36.0)
+    assert rows and not h.rows_overflow and total == want.shape[0]
+
+
+def test_config4_1m_atoms_masks_path_matches_rows_path():
+    """Config 4 at full size on both COO paths: identical (i, j, s) sets."""
+    from nvalchemiops_b200 import config
+
+    n = 1_000_000
+    pos, cell, pbc = bench_box(n, seed=4)
+    pos, cell, pbc = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    keys = {}
+    old = config.coo_path
+    try:
+        for path in ("rows", "masks"):
+            config.coo_path = path
+            e, ptr, s = _nl().neighbor_list(pos, 6.0, cell=cell, pbc=pbc, return_neighbor_list=True)
+            assert (e[0, 1:] >= e[0, :-1]).all()
+            keys[path] = (torch.sort(_keys(e[0], e[1], s, n)).values, ptr.clone())
+            del e, s
+    finally:
+        config.coo_path = old
+    assert torch.equal(keys["rows"][0], keys["masks"][0])
+    assert torch.equal(keys["rows"][1], keys["masks"][1])
