@@ -107,10 +107,12 @@ __device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, f32x2_t XI, f3
     rows_append<HALF, TAIL>(d2, c, j, iA, iB, rc2, lexpos, valid, la, lb);
 }
 
-// four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp)
-template <bool HALF, bool FMA>
-__device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
-                                              float rc2, uint32_t& la, uint32_t& lb) {
+// four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp).
+// MASKED: the group may run past the end of the tile — candidates with index >= limit are ignored (whatever the
+// stage buffer holds there is read but never recorded).
+template <bool HALF, bool FMA, bool MASKED>
+__device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA,
+                                              int iB, float rc2, uint32_t& la, uint32_t& lb) {
     constexpr uint32_t RS = sizeof(Rec<float>);
     float x[4], y[4], z[4];
     int j[4];
@@ -120,23 +122,39 @@ __device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, f32x2_t XI, 
 #pragma unroll
     for (int u = 0; u < 4; ++u) d2[u] = rows_d2<FMA, false>(x[u], y[u], z[u], XI, YI, ZI, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) rows_append<HALF, false>(d2[u], c + 32 * u, j[u], iA, iB, rc2, false, true, la, lb);
+    for (int u = 0; u < 4; ++u)
+        rows_append<HALF, MASKED>(d2[u], c + 32 * u, j[u], iA, iB, rc2, false, c + 32 * u < limit, la, lb);
 }
 
-// Sweep of two targets over the staged tile (same chunk structure as fast_masks2).  la / lb: per-lane append pointers.
+// Sweep of two targets over the staged tile.  la / lb: per-lane append pointers.
+//   interior cell (one zero-shift segment): groups of four chunks, the last group masked;
+//   cell at a periodic boundary: full zero-shift chunks in groups of four, then every other chunk with its shift vector
+//   picked per lane (a chunk may straddle segments).
 template <bool HALF, bool FMA>
 __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t cand_addr, f32x2_t XI, f32x2_t YI,
                                             f32x2_t ZI, int iA, int iB, float rc2, int lane, uint32_t& la, uint32_t& lb) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    const int total = sm.total, nchunks = sm.nchunks;
-    const int zend = sm.seg_key[0] == 0 ? sm.seg_begin[1] : 0;
-    const int nzfull = zend >> 5;
+    const int total = sm.total, nchunks = sm.nchunks, nseg = sm.nseg;
+    const bool zero0 = sm.seg_key[0] == 0;
     uint32_t addr = cand_addr + (uint32_t)lane * RS;
     int c = lane;
+    if (nseg == 1 && zero0) {
+        const int ngroups = total >> 7;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            rows_chunk2x4<HALF, FMA, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, la, lb);
+            addr += 128 * RS;
+            c += 128;
+        }
+        if (total & 127) rows_chunk2x4<HALF, FMA, true>(addr, c, total, XI, YI, ZI, iA, iB, rc2, la, lb);
+        return;
+    }
+    const int zend = zero0 ? sm.seg_begin[1] : 0;
+    const int nzfull = zend >> 5;
     int ck = 0;
 #pragma unroll 1
     for (; ck + 4 <= nzfull; ck += 4) {
-        rows_chunk2x4<HALF, FMA>(addr, c, XI, YI, ZI, iA, iB, rc2, la, lb);
+        rows_chunk2x4<HALF, FMA, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, la, lb);
         addr += 128 * RS;
         c += 128;
     }
@@ -146,14 +164,10 @@ __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t
         addr += 32 * RS;
         c += 32;
     }
-    if (sm.nseg == 1 && ck < nchunks) {
-        rows_chunk2<HALF, FMA, false, true>(addr, c, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, c < total, la, lb);
-        ++ck;
-    }
 #pragma unroll 1
     for (; ck < nchunks; ++ck) {
         int sg = sm.chunk_seg[ck];
-        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+        while (sg + 1 < nseg && c >= sm.seg_begin[sg + 1]) ++sg;
         bool lexpos = false;
         if (HALF) {
             int csx, csy, csz;
@@ -172,32 +186,46 @@ struct RowsAlloc {
     long long pos, end;
 };
 
-// Epilogue of one target: drop the self entry, scan the list lengths, reserve the row, gather tile index -> atom index.
+// Epilogue of a target pair: drop the self entries, ONE packed warp scan of both targets' list lengths, ONE row
+// reservation, then the lists are gathered (tile index -> original atom index) into the two compact rows.
 template <bool HALF>
-__device__ __forceinline__ void rows_emit(const RowsArgs& a, const FastStage<float>& sm, Ctrl* ctrl, uint32_t cand_addr,
-                                          uint32_t lbase, uint32_t lend, int self, int i, int lane, bool shifted,
-                                          RowsAlloc& al, int* __restrict__ rows, int* __restrict__ row_ref) {
+__device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<float>& sm, Ctrl* ctrl, uint32_t cand_addr,
+                                           uint32_t lbaseA, uint32_t lbaseB, uint32_t la, uint32_t lb, int selfA, int selfB,
+                                           int iA, int iB, bool two, int lane, bool shifted, RowsAlloc& al,
+                                           int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    int n = (int)((lend - lbase) >> 6);
+    int nA = (int)((la - lbaseA) >> 6);
+    int nB = two ? (int)((lb - lbaseB) >> 6) : 0;
     if (!HALF) {
         // (i, i, 0) is not a pair: the target itself (tile index `self`, zero shift, d = 0) is always in the list of
-        // lane self & 31 — replace it with that lane's last entry
-        if (lane == (self & 31)) {
+        // lane self & 31 — replace it with that lane's last entry.  selfB = selfA + 1: two different lanes.
+        const bool mineA = lane == (selfA & 31);
+        const bool mineB = two && lane == (selfB & 31);
+        if (mineA || mineB) {
+            const uint32_t base = mineA ? lbaseA : lbaseB;
+            const int self = mineA ? selfA : selfB;
+            int n = mineA ? nA : nB;
             for (int s = 0; s < n; ++s) {
-                if (lds_u16(lbase + (uint32_t)s * 64u) == self) {
-                    sts_u16(lbase + (uint32_t)s * 64u, lds_u16(lbase + (uint32_t)(n - 1) * 64u));
+                if (lds_u16(base + (uint32_t)s * 64u) == self) {
+                    sts_u16(base + (uint32_t)s * 64u, lds_u16(base + (uint32_t)(n - 1) * 64u));
                     --n;
                     break;
                 }
             }
+            if (mineA) nA = n; else nB = n;
         }
         __syncwarp();
     }
-    const int incl = warp_incl_scan(n, lane);
-    const int cnt = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - n;
-    const int maxn = __reduce_max_sync(0xffffffffu, n);
-    const int need = shifted ? 2 * cnt : cnt;
+    // list lengths are <= 32 per lane, their sums <= 1024: both scans fit one 32-bit word
+    const int packed = nA | (nB << 16);
+    const int incl = warp_incl_scan(packed, lane);
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int cntA = tot & 0xffff, cntB = tot >> 16;
+    const int excl = incl - packed;
+    const int exA = excl & 0xffff, exB = excl >> 16;
+    const int maxn = __reduce_max_sync(0xffffffffu, nA > nB ? nA : nB);
+    const int mul = shifted ? 2 : 1;
+    const int need = (cntA + cntB) * mul;
     bool ok = true;
     if (al.pos + need > al.end) {
         const long long sz = need > kRowsBlock ? need : kRowsBlock;
@@ -214,24 +242,48 @@ __device__ __forceinline__ void rows_emit(const RowsArgs& a, const FastStage<flo
             al.end = (long long)b + sz;
         }
     }
+    int startA = 0, startB = 0;
     if (ok) {
-        const int start = (int)al.pos;
+        startA = (int)al.pos;
+        startB = startA + cntA * mul;
         al.pos += need;
-        int* row = rows + start + excl;
-        for (int s = 0; s < maxn; ++s) {
-            if (s < n) {
-                const int c = lds_u16(lbase + (uint32_t)s * 64u);
-                row[s] = lds_rec_j<float>(cand_addr + (uint32_t)c * RS);
-                if (shifted) {
-                    int sg = sm.chunk_seg[c >> 5];
-                    while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
-                    row[cnt + s] = sm.seg_key[sg];
+        int* __restrict__ rowA = rows + startA + exA;
+        int* __restrict__ rowB = rows + startB + exB;
+        // two slots of both lists per trip: four independent index -> atom gathers in flight.  Slots past a list's
+        // length hold stale (valid) tile indices — the lists are zero-initialised — and are read but not stored.
+#pragma unroll 1
+        for (int s = 0; s < maxn; s += 2) {
+            const uint32_t o = (uint32_t)s * 64u;
+            const int cA0 = lds_u16(lbaseA + o), cA1 = lds_u16(lbaseA + o + 64u);
+            const int cB0 = lds_u16(lbaseB + o), cB1 = lds_u16(lbaseB + o + 64u);
+            const int jA0 = lds_rec_j<float>(cand_addr + (uint32_t)cA0 * RS), jA1 = lds_rec_j<float>(cand_addr + (uint32_t)cA1 * RS);
+            const int jB0 = lds_rec_j<float>(cand_addr + (uint32_t)cB0 * RS), jB1 = lds_rec_j<float>(cand_addr + (uint32_t)cB1 * RS);
+            if (s < nA) rowA[s] = jA0;
+            if (s + 1 < nA) rowA[s + 1] = jA1;
+            if (s < nB) rowB[s] = jB0;
+            if (s + 1 < nB) rowB[s + 1] = jB1;
+        }
+        if (shifted) {
+            // cell at a periodic boundary: the packed image key of every entry goes behind the row
+#pragma unroll 1
+            for (int s = 0; s < maxn; ++s) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    if (s < (w ? nB : nA)) {
+                        const int c = lds_u16((w ? lbaseB : lbaseA) + (uint32_t)s * 64u);
+                        int sg = sm.chunk_seg[c >> 5];
+                        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
+                        (w ? rowB : rowA)[(w ? cntB : cntA) + s] = sm.seg_key[sg];
+                    }
                 }
             }
         }
-        if (lane == 0) row_ref[i] = (start << 1) | (shifted ? 1 : 0);
     }
-    if (lane == 0) a.num_neighbors[i] = cnt;
+    if (lane < 2 && (lane == 0 || two)) {
+        const int i = lane ? iB : iA;
+        if (ok) row_ref[i] = ((lane ? startB : startA) << 1) | (shifted ? 1 : 0);
+        a.num_neighbors[i] = lane ? cntB : cntA;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +315,9 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
             ctrl->max_count = 0;
         }
     }
+    // stale list slots are read (never stored) by the epilogue: they must hold valid tile indices from the start
+    for (int k = tid; k < (int)(sizeof(sm.lists) / sizeof(unsigned)); k += kRowsThreads)
+        reinterpret_cast<unsigned*>(&sm.lists[0][0][0])[k] = 0u;
     // unwrapped inputs are served by the two-pass kernels launched next to this one
     const bool active = ctrl->unwrapped == 0;
     if (tid == 0) {
@@ -286,19 +341,21 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
         int g_next = 0;
         if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
         for (;;) {
-            mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
-            FastStage<T>& sg = sm.stage[stage];
-            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kStageBytes);
-            bool done = false;
+            // ---- 1. prepare the next cell entirely in registers (dependent global loads, image enumeration, shift
+            //         sort) BEFORE waiting for a ring stage: after the consumers release a stage only the table
+            //         writes and the TMA issue remain on the critical path ----
+            bool have = false;
+            int g = 0, home_start = 0, ntarget = 0, st = 0, cn = 0, key = kKeyEmpty, off = 0, total = 0, nseg = 1;
+            int home_off = 0, si = 0;
+            unsigned shiftmask = 0u;
+            bool head = false;
+            T Sx = (T)0, Sy = (T)0, Sz = (T)0;
             for (;;) {
-                const int g = __shfl_sync(0xffffffffu, g_next, 0);
-                if (g >= total_cells) {
-                    done = true;
-                    break;
-                }
+                g = __shfl_sync(0xffffffffu, g_next, 0);
+                if (g >= total_cells) break;
                 if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
-                const int home_start = cell_start[g];
-                const int ntarget = cell_start[g + 1] - home_start;
+                home_start = cell_start[g];
+                ntarget = cell_start[g + 1] - home_start;
                 if (ntarget == 0) continue;
                 int s = 0;
                 if (a.num_systems > 1) s = a.batch_idx[sorted[home_start].j];
@@ -308,7 +365,8 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
                 const int nimg = nx * ny * nzz;
                 bool ok = nimg <= 32 && ntarget <= kFastMaxTargets;
-                int st = 0, cn = 0, key = kKeyEmpty, tag = 0;
+                int tag = 0;
+                st = 0; cn = 0; key = kKeyEmpty;
                 const int coff = sp.cell_offset;
                 if (ok && lane < nimg) {
                     const int local = g - coff;
@@ -328,7 +386,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                     }
                     tag = (dx == 0 && dy == 0 && dz == 0) ? 1 : 0;
                 }
-                const unsigned shiftmask = __ballot_sync(0xffffffffu, key != 0 && key != kKeyEmpty);
+                shiftmask = __ballot_sync(0xffffffffu, key != 0 && key != kKeyEmpty);
                 if (ok && shiftmask) {
                     // order the images by shift: equal shifts become one contiguous segment, zero shift first
                     int rank = 0;
@@ -342,43 +400,9 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                     __syncwarp();
                 }
                 const int incl = warp_incl_scan(cn, lane);
-                const int off = incl - cn;
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                off = incl - cn;
+                total = __shfl_sync(0xffffffffu, incl, 31);
                 ok = ok && total <= cap;
-                int nseg = 1;
-                if (ok) {
-                    if (shiftmask) {
-                        const int pk = __shfl_up_sync(0xffffffffu, key, 1);
-                        const bool head = cn > 0 && (lane == 0 || pk != key);
-                        const unsigned hm = __ballot_sync(0xffffffffu, head);
-                        nseg = __popc(hm);
-                        if (head) {
-                            const int si = __popc(hm & ((1u << lane) - 1u));
-                            sg.seg_begin[si] = off;
-                            sg.seg_key[si] = key;
-                            int csx, csy, csz;
-                            unpack_key(key, csx, csy, csz);
-                            T cm[9];
-#pragma unroll
-                            for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
-                            T Sx, Sy, Sz;
-                            shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
-                            sg.segS[3 * si] = Sx; sg.segS[3 * si + 1] = Sy; sg.segS[3 * si + 2] = Sz;
-                        }
-                        if (lane == 0) sg.seg_begin[nseg] = total;
-                    } else if (lane == 0) {
-                        sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0;
-                    }
-                    __syncwarp();
-                    const int nchunks = (total + 31) >> 5;
-                    if (lane < nchunks) {
-                        int sgi = 0;
-                        while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
-                        sg.chunk_seg[lane] = sgi;
-                    }
-                    if (!shiftmask && lane < 3) sg.segS[lane] = (T)0;
-                    if (lane == 0) sg.nchunks = nchunks;
-                }
                 if (!ok) {
                     // leave the cell to the general kernel as work items of kDeferTargets target atoms
                     const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
@@ -391,28 +415,69 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                     for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
                     continue;
                 }
+                nseg = 1;
+                head = false;
+                if (shiftmask) {
+                    const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+                    head = cn > 0 && (lane == 0 || pk != key);
+                    const unsigned hm = __ballot_sync(0xffffffffu, head);
+                    nseg = __popc(hm);
+                    if (head) {
+                        si = __popc(hm & ((1u << lane) - 1u));
+                        int csx, csy, csz;
+                        unpack_key(key, csx, csy, csz);
+                        T cm[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
+                        shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
+                    }
+                }
                 const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
                 const int home_lane = __ffs(tagm) - 1;
-                const int home_off = __shfl_sync(0xffffffffu, off, home_lane);
-                if (lane == 0) {
-                    sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
-                    sg.nseg = nseg; sg.total = total; sg.next_target = 0;
-                }
-                const uint32_t tx = (uint32_t)total * RS;
-                __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
-                if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), tx);
-                __syncwarp();
-                if (cn > 0)
-                    tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                home_off = __shfl_sync(0xffffffffu, off, home_lane);
+                have = true;
                 break;
             }
-            if (done) {
+            // ---- 2. wait until the consumers have released this ring stage, then publish the tables and issue the copies ----
+            mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
+            FastStage<T>& sg = sm.stage[stage];
+            if (!have) {
                 if (lane == 0) {
                     sg.item = -1;
                     mbar_arrive(reinterpret_cast<uint64_t*>(&sm.full[stage]));
                 }
                 break;
             }
+            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kStageBytes);
+            if (shiftmask) {
+                if (head) {
+                    sg.seg_begin[si] = off;
+                    sg.seg_key[si] = key;
+                    sg.segS[3 * si] = Sx; sg.segS[3 * si + 1] = Sy; sg.segS[3 * si + 2] = Sz;
+                }
+                if (lane == 0) sg.seg_begin[nseg] = total;
+            } else {
+                if (lane == 0) { sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0; }
+                if (lane < 3) sg.segS[lane] = (T)0;
+            }
+            __syncwarp();
+            const int nchunks = (total + 31) >> 5;
+            if (lane < nchunks) {
+                int sgi = 0;
+                while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
+                sg.chunk_seg[lane] = sgi;
+            }
+            if (lane == 0) {
+                sg.nchunks = nchunks;
+                sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
+                sg.nseg = nseg; sg.total = total; sg.next_target = 0;
+            }
+            const uint32_t tx = (uint32_t)total * RS;
+            __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
+            if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), tx);
+            __syncwarp();
+            if (cn > 0)
+                tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
             if (++stage == kFastStages) { stage = 0; ephase ^= 1u; }
         }
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
@@ -460,8 +525,8 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
                 uint32_t la = lbaseA, lb = lbaseB;
                 rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, la, lb);
-                rows_emit<HALF>(a, sg, ctrl, cand_addr, lbaseA, la, selfA, iA, lane, shifted, al, rows, row_ref);
-                if (two) rows_emit<HALF>(a, sg, ctrl, cand_addr, lbaseB, lb, selfB, iB, lane, shifted, al, rows, row_ref);
+                rows_emit2<HALF>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
+                                 rows, row_ref);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
@@ -488,7 +553,7 @@ __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int valu
     if (lane < tail) dst[head + 4 * nv + lane] = value;
 }
 
-__global__ void __launch_bounds__(256) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
+__global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
                                                   const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
                                                   int* __restrict__ out_j, int* __restrict__ out_shifts, int index_offset) {
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
@@ -501,39 +566,56 @@ __global__ void __launch_bounds__(256) k_rows_out(const unsigned char* __restric
     const int p_l = neighbor_ptr[il < n ? il : n];
     const int pe_l = neighbor_ptr[il + 1 < n ? il + 1 : n];
     const int na = n - base < 32 ? (int)(n - base) : 32;
+    // software pipeline: the row of atom t + 1 is in flight while atom t is written
+    int ref = __shfl_sync(0xffffffffu, ref_l, 0);
+    int p = __shfl_sync(0xffffffffu, p_l, 0);
+    int cnt = __shfl_sync(0xffffffffu, pe_l, 0) - p;
+    int v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int k = lane + 32 * u;
+        v[u] = (ref >= 0 && k < cnt) ? rows[(ref >> 1) + k] : 0;
+    }
     for (int t = 0; t < na; ++t) {
-        const int ref = __shfl_sync(0xffffffffu, ref_l, t);
-        const int p = __shfl_sync(0xffffffffu, p_l, t);
-        const int cnt = __shfl_sync(0xffffffffu, pe_l, t) - p;
-        if (ref < 0 || cnt <= 0) continue;
-        const int* __restrict__ row = rows + (ref >> 1);
-        const int iv = (int)(base + t) + index_offset;
-        for (int k0 = 0; k0 < cnt; k0 += 128) {
-            int v[4];
+        int nref = -1, np = 0, ncnt = 0;
+        int nv[4] = {0, 0, 0, 0};
+        if (t + 1 < na) {
+            nref = __shfl_sync(0xffffffffu, ref_l, t + 1);
+            np = __shfl_sync(0xffffffffu, p_l, t + 1);
+            ncnt = __shfl_sync(0xffffffffu, pe_l, t + 1) - np;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int k = k0 + lane + 32 * u;
-                v[u] = k < cnt ? row[k] : 0;
+                const int k = lane + 32 * u;
+                nv[u] = (nref >= 0 && k < ncnt) ? rows[(nref >> 1) + k] : 0;
             }
+        }
+        if (ref >= 0 && cnt > 0) {
+            const int* __restrict__ row = rows + (ref >> 1);
+            const int iv = (int)(base + t) + index_offset;
+            int* __restrict__ oj = out_j + (size_t)p;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int k = k0 + lane + 32 * u;
-                if (k < cnt) out_j[(size_t)p + k] = v[u] + index_offset;
+                const int k = lane + 32 * u;
+                if (k < cnt) oj[k] = v[u] + index_offset;
+            }
+            for (int k = 128 + lane; k < cnt; k += 32) oj[k] = row[k] + index_offset;  // rows longer than 128 (rare)
+            warp_fill(out_i + (size_t)p, cnt, iv, lane);
+            int* sh = out_shifts + 3 * (size_t)p;
+            if (!(ref & 1)) {
+                warp_fill(sh, 3 * cnt, 0, lane);
+            } else {
+                for (int k = lane; k < cnt; k += 32) {
+                    int csx, csy, csz;
+                    unpack_key(row[cnt + k], csx, csy, csz);
+                    sh[3 * k] = csx;
+                    sh[3 * k + 1] = csy;
+                    sh[3 * k + 2] = csz;
+                }
             }
         }
-        warp_fill(out_i + (size_t)p, cnt, iv, lane);
-        int* sh = out_shifts + 3 * (size_t)p;
-        if (!(ref & 1)) {
-            warp_fill(sh, 3 * cnt, 0, lane);
-        } else {
-            for (int k = lane; k < cnt; k += 32) {
-                int csx, csy, csz;
-                unpack_key(row[cnt + k], csx, csy, csz);
-                sh[3 * k] = csx;
-                sh[3 * k + 1] = csy;
-                sh[3 * k + 2] = csz;
-            }
-        }
+        ref = nref; p = np; cnt = ncnt;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = nv[u];
     }
 }
 
