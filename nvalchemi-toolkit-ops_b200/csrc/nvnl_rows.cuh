@@ -79,40 +79,43 @@ __device__ __forceinline__ f32x2_t rows_d2(float x, float y, float z, f32x2_t XI
     return d2;
 }
 
-// lanes that hit append the candidate's tile index c to their private lists (predicated 16-bit store + pointer bump)
-template <bool HALF, bool TAIL>
-__device__ __forceinline__ void rows_append(f32x2_t d2, int c, int j, int iA, int iB, float rc2, bool lexpos, bool valid,
-                                            uint32_t& la, uint32_t& lb) {
+// lanes that hit append `val` = tile index | segment << 10 to their private lists (predicated 16-bit store + pointer
+// bump).  EXCL: the targets themselves (tile indices selfA / selfB, zero shift, d = 0) are not recorded — (i, i, 0) is
+// not a pair; half fill needs no such test (i < j fails).
+template <bool HALF, bool TAIL, bool EXCL>
+__device__ __forceinline__ void rows_append(f32x2_t d2, int c, int val, int j, int iA, int iB, float rc2, bool lexpos,
+                                            bool valid, int selfA, int selfB, uint32_t& la, uint32_t& lb) {
     float dA, dB;
     unpack2(d2, dA, dB);
     bool hA = dA < rc2, hB = dB < rc2;
     if (TAIL) { hA = hA && valid; hB = hB && valid; }
+    if (EXCL) { hA = hA && c != selfA; hB = hB && c != selfB; }
     if (HALF) {
         hA = hA && (iA < j || (iA == j && lexpos));
         hB = hB && (iB < j || (iB == j && lexpos));
     }
-    if (hA) { sts_u16(la, c); la += 64u; }
-    if (hB) { sts_u16(lb, c); lb += 64u; }
+    if (hA) { sts_u16(la, val); la += 64u; }
+    if (hB) { sts_u16(lb, val); lb += 64u; }
 }
 
-// one 32-candidate chunk against two targets
+// one 32-candidate chunk against two targets (boundary cells: single chunks and chunks with image shifts)
 template <bool HALF, bool FMA, bool SHIFTED, bool TAIL>
-__device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
-                                            float Sx, float Sy, float Sz, float rc2, bool lexpos, bool valid,
-                                            uint32_t& la, uint32_t& lb) {
+__device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, int sg, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
+                                            float Sx, float Sy, float Sz, float rc2, bool lexpos, bool valid, int selfA,
+                                            int selfB, uint32_t& la, uint32_t& lb) {
     float x, y, z;
     int j;
     lds_rec(addr, x, y, z, j);
     const f32x2_t d2 = rows_d2<FMA, SHIFTED>(x, y, z, XI, YI, ZI, Sx, Sy, Sz);
-    rows_append<HALF, TAIL>(d2, c, j, iA, iB, rc2, lexpos, valid, la, lb);
+    rows_append<HALF, TAIL, !HALF>(d2, c, c | (sg << 10), j, iA, iB, rc2, lexpos, valid, selfA, selfB, la, lb);
 }
 
 // four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp).
 // MASKED: the group may run past the end of the tile — candidates with index >= limit are ignored (whatever the
 // stage buffer holds there is read but never recorded).
-template <bool HALF, bool FMA, bool MASKED>
+template <bool HALF, bool FMA, bool MASKED, bool EXCL>
 __device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA,
-                                              int iB, float rc2, uint32_t& la, uint32_t& lb) {
+                                              int iB, float rc2, int selfA, int selfB, uint32_t& la, uint32_t& lb) {
     constexpr uint32_t RS = sizeof(Rec<float>);
     float x[4], y[4], z[4];
     int j[4];
@@ -123,30 +126,38 @@ __device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f
     for (int u = 0; u < 4; ++u) d2[u] = rows_d2<FMA, false>(x[u], y[u], z[u], XI, YI, ZI, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-        rows_append<HALF, MASKED>(d2[u], c + 32 * u, j[u], iA, iB, rc2, false, c + 32 * u < limit, la, lb);
+        rows_append<HALF, MASKED, EXCL>(d2[u], c + 32 * u, c + 32 * u, j[u], iA, iB, rc2, false, c + 32 * u < limit, selfA, selfB,
+                                        la, lb);
 }
 
 // Sweep of two targets over the staged tile.  la / lb: per-lane append pointers.
 //   interior cell (one zero-shift segment): groups of four chunks, the last group masked;
 //   cell at a periodic boundary: full zero-shift chunks in groups of four, then every other chunk with its shift vector
 //   picked per lane (a chunk may straddle segments).
+// Only the group(s) holding the targets themselves pay for the self-exclusion test.
 template <bool HALF, bool FMA>
 __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t cand_addr, f32x2_t XI, f32x2_t YI,
-                                            f32x2_t ZI, int iA, int iB, float rc2, int lane, uint32_t& la, uint32_t& lb) {
+                                            f32x2_t ZI, int iA, int iB, float rc2, int lane, int selfA, int selfB,
+                                            uint32_t& la, uint32_t& lb) {
     constexpr uint32_t RS = sizeof(Rec<float>);
+    constexpr bool EX = !HALF;
     const int total = sm.total, nchunks = sm.nchunks, nseg = sm.nseg;
     const bool zero0 = sm.seg_key[0] == 0;
+    const int gA = selfA >> 7, gB = selfB >> 7;
     uint32_t addr = cand_addr + (uint32_t)lane * RS;
     int c = lane;
     if (nseg == 1 && zero0) {
         const int ngroups = total >> 7;
 #pragma unroll 1
         for (int g = 0; g < ngroups; ++g) {
-            rows_chunk2x4<HALF, FMA, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, la, lb);
+            if (EX && (g == gA || g == gB))
+                rows_chunk2x4<HALF, FMA, false, true>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
+            else
+                rows_chunk2x4<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
             addr += 128 * RS;
             c += 128;
         }
-        if (total & 127) rows_chunk2x4<HALF, FMA, true>(addr, c, total, XI, YI, ZI, iA, iB, rc2, la, lb);
+        if (total & 127) rows_chunk2x4<HALF, FMA, true, EX>(addr, c, total, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
         return;
     }
     const int zend = zero0 ? sm.seg_begin[1] : 0;
@@ -154,13 +165,17 @@ __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t
     int ck = 0;
 #pragma unroll 1
     for (; ck + 4 <= nzfull; ck += 4) {
-        rows_chunk2x4<HALF, FMA, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, la, lb);
+        const int g = ck >> 2;
+        if (EX && (g == gA || g == gB))
+            rows_chunk2x4<HALF, FMA, false, true>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
+        else
+            rows_chunk2x4<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
         addr += 128 * RS;
         c += 128;
     }
 #pragma unroll 1
     for (; ck < nzfull; ++ck) {
-        rows_chunk2<HALF, FMA, false, false>(addr, c, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, la, lb);
+        rows_chunk2<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, selfA, selfB, la, lb);
         addr += 32 * RS;
         c += 32;
     }
@@ -174,8 +189,8 @@ __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t
             unpack_key(sm.seg_key[sg], csx, csy, csz);
             lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
         }
-        rows_chunk2<HALF, FMA, true, true>(addr, c, XI, YI, ZI, iA, iB, sm.segS[3 * sg], sm.segS[3 * sg + 1], sm.segS[3 * sg + 2],
-                                           rc2, lexpos, c < total, la, lb);
+        rows_chunk2<HALF, FMA, true, true>(addr, c, sg, XI, YI, ZI, iA, iB, sm.segS[3 * sg], sm.segS[3 * sg + 1],
+                                           sm.segS[3 * sg + 2], rc2, lexpos, c < total, selfA, selfB, la, lb);
         addr += 32 * RS;
         c += 32;
     }
@@ -196,26 +211,6 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     constexpr uint32_t RS = sizeof(Rec<float>);
     int nA = (int)((la - lbaseA) >> 6);
     int nB = two ? (int)((lb - lbaseB) >> 6) : 0;
-    if (!HALF) {
-        // (i, i, 0) is not a pair: the target itself (tile index `self`, zero shift, d = 0) is always in the list of
-        // lane self & 31 — replace it with that lane's last entry.  selfB = selfA + 1: two different lanes.
-        const bool mineA = lane == (selfA & 31);
-        const bool mineB = two && lane == (selfB & 31);
-        if (mineA || mineB) {
-            const uint32_t base = mineA ? lbaseA : lbaseB;
-            const int self = mineA ? selfA : selfB;
-            int n = mineA ? nA : nB;
-            for (int s = 0; s < n; ++s) {
-                if (lds_u16(base + (uint32_t)s * 64u) == self) {
-                    sts_u16(base + (uint32_t)s * 64u, lds_u16(base + (uint32_t)(n - 1) * 64u));
-                    --n;
-                    break;
-                }
-            }
-            if (mineA) nA = n; else nB = n;
-        }
-        __syncwarp();
-    }
     // list lengths are <= 32 per lane, their sums <= 1024: both scans fit one 32-bit word
     const int packed = nA | (nB << 16);
     const int incl = warp_incl_scan(packed, lane);
@@ -250,32 +245,32 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
         int* __restrict__ rowA = rows + startA + exA;
         int* __restrict__ rowB = rows + startB + exB;
         // two slots of both lists per trip: four independent index -> atom gathers in flight.  Slots past a list's
-        // length hold stale (valid) tile indices — the lists are zero-initialised — and are read but not stored.
+        // length hold stale (valid) entries — the lists are zero-initialised — and are read but not stored.
+        if (!shifted) {
 #pragma unroll 1
-        for (int s = 0; s < maxn; s += 2) {
-            const uint32_t o = (uint32_t)s * 64u;
-            const int cA0 = lds_u16(lbaseA + o), cA1 = lds_u16(lbaseA + o + 64u);
-            const int cB0 = lds_u16(lbaseB + o), cB1 = lds_u16(lbaseB + o + 64u);
-            const int jA0 = lds_rec_j<float>(cand_addr + (uint32_t)cA0 * RS), jA1 = lds_rec_j<float>(cand_addr + (uint32_t)cA1 * RS);
-            const int jB0 = lds_rec_j<float>(cand_addr + (uint32_t)cB0 * RS), jB1 = lds_rec_j<float>(cand_addr + (uint32_t)cB1 * RS);
-            if (s < nA) rowA[s] = jA0;
-            if (s + 1 < nA) rowA[s + 1] = jA1;
-            if (s < nB) rowB[s] = jB0;
-            if (s + 1 < nB) rowB[s + 1] = jB1;
-        }
-        if (shifted) {
-            // cell at a periodic boundary: the packed image key of every entry goes behind the row
+            for (int s = 0; s < maxn; s += 2) {
+                const uint32_t o = (uint32_t)s * 64u;
+                // & 1023: a stale slot may hold an entry (with segment bits) of an earlier boundary cell
+                const int cA0 = lds_u16(lbaseA + o) & 1023, cA1 = lds_u16(lbaseA + o + 64u) & 1023;
+                const int cB0 = lds_u16(lbaseB + o) & 1023, cB1 = lds_u16(lbaseB + o + 64u) & 1023;
+                const int jA0 = lds_rec_j<float>(cand_addr + (uint32_t)cA0 * RS), jA1 = lds_rec_j<float>(cand_addr + (uint32_t)cA1 * RS);
+                const int jB0 = lds_rec_j<float>(cand_addr + (uint32_t)cB0 * RS), jB1 = lds_rec_j<float>(cand_addr + (uint32_t)cB1 * RS);
+                if (s < nA) rowA[s] = jA0;
+                if (s + 1 < nA) rowA[s + 1] = jA1;
+                if (s < nB) rowB[s] = jB0;
+                if (s + 1 < nB) rowB[s + 1] = jB1;
+            }
+        } else {
+            // cell at a periodic boundary: entries carry their segment; its packed image key goes behind the row
 #pragma unroll 1
             for (int s = 0; s < maxn; ++s) {
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    if (s < (w ? nB : nA)) {
-                        const int c = lds_u16((w ? lbaseB : lbaseA) + (uint32_t)s * 64u);
-                        int sg = sm.chunk_seg[c >> 5];
-                        while (sg + 1 < sm.nseg && c >= sm.seg_begin[sg + 1]) ++sg;
-                        (w ? rowB : rowA)[(w ? cntB : cntA) + s] = sm.seg_key[sg];
-                    }
-                }
+                const uint32_t o = (uint32_t)s * 64u;
+                const int vA = lds_u16(lbaseA + o), vB = lds_u16(lbaseB + o);
+                const int jA = lds_rec_j<float>(cand_addr + (uint32_t)(vA & 1023) * RS);
+                const int jB = lds_rec_j<float>(cand_addr + (uint32_t)(vB & 1023) * RS);
+                const int kA = sm.seg_key[vA >> 10], kB = sm.seg_key[vB >> 10];
+                if (s < nA) { rowA[s] = jA; rowA[cntA + s] = kA; }
+                if (s < nB) { rowB[s] = jB; rowB[cntB + s] = kB; }
             }
         }
     }
@@ -524,7 +519,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 const f32x2_t nz = pack2(-0.0f, -0.0f);
                 const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
                 uint32_t la = lbaseA, lb = lbaseB;
-                rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, la, lb);
+                rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, selfA, selfB, la, lb);
                 rows_emit2<HALF>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
                                  rows, row_ref);
             }
