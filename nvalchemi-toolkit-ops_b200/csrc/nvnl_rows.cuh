@@ -26,17 +26,20 @@ namespace nvnl {
 
 constexpr int kRowsCons = 8;                          // consumer warps per CTA
 constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
-constexpr int kRowsListBytes = 32 * 32 * 2;           // per target: 32 lanes x 32 slots x u16 (a lane cannot have more hits than chunks)
+constexpr int kRowsStages = 3;                        // TMA ring depth (consumers may run up to two cells apart)
+constexpr int kRowsMaxSeg = 8;                        // image segments per stencil the lean kernel takes (3 bits in a list entry)
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
 
 struct RowsSmem {
-    FastStage<float> stage[kFastStages];
+    FastStage<float> stage[kRowsStages];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
-    alignas(16) unsigned short lists[kRowsCons][2][32 * 32];                // lane-private hit lists, two targets per warp
-    unsigned long long full[kFastStages], empty[kFastStages];               // mbarriers of the ring
+    // lane-private hit lists, two targets per warp: slot s of lane l is byte s * 32 + l; an entry is
+    // chunk | segment << 5 (the candidate's tile index is chunk * 32 + l); a lane cannot have more hits than chunks
+    alignas(16) unsigned char lists[kRowsCons][2][32 * 32];
+    unsigned long long full[kRowsStages], empty[kRowsStages];               // mbarriers of the ring
 };
 
-constexpr size_t rows_smem_bytes() { return (size_t)kFastStages * kFastStageBytes + sizeof(RowsSmem); }
+constexpr size_t rows_smem_bytes() { return (size_t)kRowsStages * kFastStageBytes + sizeof(RowsSmem); }
 
 struct RowsArgs {
     unsigned char* ws;
@@ -48,13 +51,28 @@ struct RowsArgs {
     int* num_neighbors;
 };
 
-__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+__device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ int lds_u16(uint32_t addr) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-    return (int)v;
+__device__ __forceinline__ int lds_u8(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+// the k_rows barriers are polled with a short sleep between tries: a spinning warp would otherwise take issue slots
+// from the sweeping warps of its scheduler (ncu: 13 % of the issued instructions were the bare try_wait loop)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NVNL_BDONE_%=;\n\t"
+        "NVNL_BWAIT_%=:\n\t"
+        "nanosleep.u32 64;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra NVNL_BWAIT_%=;\n\t"
+        "NVNL_BDONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // squared distances of one candidate to the two packed targets
@@ -79,7 +97,7 @@ __device__ __forceinline__ f32x2_t rows_d2(float x, float y, float z, f32x2_t XI
     return d2;
 }
 
-// lanes that hit append `val` = tile index | segment << 10 to their private lists (predicated 16-bit store + pointer
+// lanes that hit append `val` = chunk | segment << 5 to their private lists (predicated 8-bit store + pointer
 // bump).  EXCL: the targets themselves (tile indices selfA / selfB, zero shift, d = 0) are not recorded — (i, i, 0) is
 // not a pair; half fill needs no such test (i < j fails).
 template <bool HALF, bool TAIL, bool EXCL>
@@ -94,8 +112,8 @@ __device__ __forceinline__ void rows_append(f32x2_t d2, int c, int val, int j, i
         hA = hA && (iA < j || (iA == j && lexpos));
         hB = hB && (iB < j || (iB == j && lexpos));
     }
-    if (hA) { sts_u16(la, val); la += 64u; }
-    if (hB) { sts_u16(lb, val); lb += 64u; }
+    if (hA) { sts_u8(la, val); la += 32u; }
+    if (hB) { sts_u8(lb, val); lb += 32u; }
 }
 
 // one 32-candidate chunk against two targets (boundary cells: single chunks and chunks with image shifts)
@@ -107,7 +125,7 @@ __device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, int sg, f32x2_
     int j;
     lds_rec(addr, x, y, z, j);
     const f32x2_t d2 = rows_d2<FMA, SHIFTED>(x, y, z, XI, YI, ZI, Sx, Sy, Sz);
-    rows_append<HALF, TAIL, !HALF>(d2, c, c | (sg << 10), j, iA, iB, rc2, lexpos, valid, selfA, selfB, la, lb);
+    rows_append<HALF, TAIL, !HALF>(d2, c, (c >> 5) | (sg << 5), j, iA, iB, rc2, lexpos, valid, selfA, selfB, la, lb);
 }
 
 // four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp).
@@ -126,8 +144,8 @@ __device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f
     for (int u = 0; u < 4; ++u) d2[u] = rows_d2<FMA, false>(x[u], y[u], z[u], XI, YI, ZI, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-        rows_append<HALF, MASKED, EXCL>(d2[u], c + 32 * u, c + 32 * u, j[u], iA, iB, rc2, false, c + 32 * u < limit, selfA, selfB,
-                                        la, lb);
+        rows_append<HALF, MASKED, EXCL>(d2[u], c + 32 * u, (c >> 5) + u, j[u], iA, iB, rc2, false, c + 32 * u < limit, selfA,
+                                        selfB, la, lb);
 }
 
 // Sweep of two targets over the staged tile.  la / lb: per-lane append pointers.
@@ -209,8 +227,8 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
                                            int iA, int iB, bool two, int lane, bool shifted, RowsAlloc& al,
                                            int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    int nA = (int)((la - lbaseA) >> 6);
-    int nB = two ? (int)((lb - lbaseB) >> 6) : 0;
+    const int nA = (int)((la - lbaseA) >> 5);
+    const int nB = two ? (int)((lb - lbaseB) >> 5) : 0;
     // list lengths are <= 32 per lane, their sums <= 1024: both scans fit one 32-bit word
     const int packed = nA | (nB << 16);
     const int incl = warp_incl_scan(packed, lane);
@@ -246,15 +264,19 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
         int* __restrict__ rowB = rows + startB + exB;
         // two slots of both lists per trip: four independent index -> atom gathers in flight.  Slots past a list's
         // length hold stale (valid) entries — the lists are zero-initialised — and are read but not stored.
+        // entry -> record address: tile index = chunk * 32 + lane
+        const uint32_t cand_lane = cand_addr + (uint32_t)lane * RS;
         if (!shifted) {
 #pragma unroll 1
             for (int s = 0; s < maxn; s += 2) {
-                const uint32_t o = (uint32_t)s * 64u;
-                // & 1023: a stale slot may hold an entry (with segment bits) of an earlier boundary cell
-                const int cA0 = lds_u16(lbaseA + o) & 1023, cA1 = lds_u16(lbaseA + o + 64u) & 1023;
-                const int cB0 = lds_u16(lbaseB + o) & 1023, cB1 = lds_u16(lbaseB + o + 64u) & 1023;
-                const int jA0 = lds_rec_j<float>(cand_addr + (uint32_t)cA0 * RS), jA1 = lds_rec_j<float>(cand_addr + (uint32_t)cA1 * RS);
-                const int jB0 = lds_rec_j<float>(cand_addr + (uint32_t)cB0 * RS), jB1 = lds_rec_j<float>(cand_addr + (uint32_t)cB1 * RS);
+                const uint32_t o = (uint32_t)s * 32u;
+                // & 31: a stale slot may hold an entry (with segment bits) of an earlier boundary cell
+                const int cA0 = lds_u8(lbaseA + o) & 31, cA1 = lds_u8(lbaseA + o + 32u) & 31;
+                const int cB0 = lds_u8(lbaseB + o) & 31, cB1 = lds_u8(lbaseB + o + 32u) & 31;
+                const int jA0 = lds_rec_j<float>(cand_lane + (uint32_t)cA0 * (32u * RS));
+                const int jA1 = lds_rec_j<float>(cand_lane + (uint32_t)cA1 * (32u * RS));
+                const int jB0 = lds_rec_j<float>(cand_lane + (uint32_t)cB0 * (32u * RS));
+                const int jB1 = lds_rec_j<float>(cand_lane + (uint32_t)cB1 * (32u * RS));
                 if (s < nA) rowA[s] = jA0;
                 if (s + 1 < nA) rowA[s + 1] = jA1;
                 if (s < nB) rowB[s] = jB0;
@@ -264,11 +286,11 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
             // cell at a periodic boundary: entries carry their segment; its packed image key goes behind the row
 #pragma unroll 1
             for (int s = 0; s < maxn; ++s) {
-                const uint32_t o = (uint32_t)s * 64u;
-                const int vA = lds_u16(lbaseA + o), vB = lds_u16(lbaseB + o);
-                const int jA = lds_rec_j<float>(cand_addr + (uint32_t)(vA & 1023) * RS);
-                const int jB = lds_rec_j<float>(cand_addr + (uint32_t)(vB & 1023) * RS);
-                const int kA = sm.seg_key[vA >> 10], kB = sm.seg_key[vB >> 10];
+                const uint32_t o = (uint32_t)s * 32u;
+                const int vA = lds_u8(lbaseA + o), vB = lds_u8(lbaseB + o);
+                const int jA = lds_rec_j<float>(cand_lane + (uint32_t)(vA & 31) * (32u * RS));
+                const int jB = lds_rec_j<float>(cand_lane + (uint32_t)(vB & 31) * (32u * RS));
+                const int kA = sm.seg_key[vA >> 5], kB = sm.seg_key[vB >> 5];
                 if (s < nA) { rowA[s] = jA; rowA[cntA + s] = kA; }
                 if (s < nB) { rowB[s] = jB; rowB[cntB + s] = kB; }
             }
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kStageBytes = kFastStageBytes;
-    RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kFastStages * kStageBytes);
+    RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kRowsStages * kStageBytes);
     const uint32_t smem_base = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
     constexpr int cap = kCandBytes / (int)RS;
@@ -316,7 +338,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
     // unwrapped inputs are served by the two-pass kernels launched next to this one
     const bool active = ctrl->unwrapped == 0;
     if (tid == 0) {
-        for (int st = 0; st < kFastStages; ++st) {
+        for (int st = 0; st < kRowsStages; ++st) {
             mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kRowsCons);
         }
@@ -398,6 +420,17 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 off = incl - cn;
                 total = __shfl_sync(0xffffffffu, incl, 31);
                 ok = ok && total <= cap;
+                // segments = runs of equal shift among the non-empty images (sorted by shift above)
+                nseg = 1;
+                head = false;
+                unsigned hm = 0u;
+                if (shiftmask) {
+                    const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+                    head = cn > 0 && (lane == 0 || pk != key);
+                    hm = __ballot_sync(0xffffffffu, head);
+                    nseg = __popc(hm);
+                    ok = ok && nseg <= kRowsMaxSeg;  // a list entry has 3 bits for the segment (boxes < 3 cells wide: general kernel)
+                }
                 if (!ok) {
                     // leave the cell to the general kernel as work items of kDeferTargets target atoms
                     const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
@@ -410,13 +443,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                     for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
                     continue;
                 }
-                nseg = 1;
-                head = false;
                 if (shiftmask) {
-                    const int pk = __shfl_up_sync(0xffffffffu, key, 1);
-                    head = cn > 0 && (lane == 0 || pk != key);
-                    const unsigned hm = __ballot_sync(0xffffffffu, head);
-                    nseg = __popc(hm);
                     if (head) {
                         si = __popc(hm & ((1u << lane) - 1u));
                         int csx, csy, csz;
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 break;
             }
             // ---- 2. wait until the consumers have released this ring stage, then publish the tables and issue the copies ----
-            mbar_wait(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
+            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
             FastStage<T>& sg = sm.stage[stage];
             if (!have) {
                 if (lane == 0) {
@@ -473,7 +500,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
             __syncwarp();
             if (cn > 0)
                 tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
-            if (++stage == kFastStages) { stage = 0; ephase ^= 1u; }
+            if (++stage == kRowsStages) { stage = 0; ephase ^= 1u; }
         }
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
         if (lane == 0) {
@@ -489,15 +516,15 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
         const int cw = warp - 1;
         int* rows = reinterpret_cast<int*>(a.ws + a.L.rows);
         int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
-        const uint32_t lbaseA = smem_u32(&sm.lists[cw][0][0]) + (uint32_t)lane * 2u;
-        const uint32_t lbaseB = smem_u32(&sm.lists[cw][1][0]) + (uint32_t)lane * 2u;
+        const uint32_t lbaseA = smem_u32(&sm.lists[cw][0][0]) + (uint32_t)lane;
+        const uint32_t lbaseB = smem_u32(&sm.lists[cw][1][0]) + (uint32_t)lane;
         RowsAlloc al;
         al.pos = al.end = 0;
         const float rc2 = a.cutoff_sq;
         int stage = 0;
         uint32_t fphase = 0;
         for (;;) {
-            mbar_wait(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
+            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
             FastStage<T>& sg = sm.stage[stage];
             if (sg.item < 0) break;
             const uint32_t cand_addr = smem_base + (uint32_t)stage * kStageBytes;
@@ -525,7 +552,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
-            if (++stage == kFastStages) { stage = 0; fphase ^= 1u; }
+            if (++stage == kRowsStages) { stage = 0; fphase ^= 1u; }
         }
     }
 }

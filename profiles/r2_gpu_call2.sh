@@ -5,4 +5,5 @@ timeout 300 python profiles/cfg4_calls.py 4 rows > gpurun_out/${T}_rows.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/${T}_pytest.log
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${T}_bench_rows.json 2> gpurun_out/${T}_bench_rows.err; echo "bench rc=$?"; cat gpurun_out/${T}_bench_rows.json
+timeout 300 python profiles/configs_api_time.py gpurun_out/${T}_configs.json > gpurun_out/${T}_configs.log 2>&1; tail -22 gpurun_out/${T}_configs.log
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_rows' -s 2 -c 2 -o gpurun_out/${T}_rows_full -f python profiles/cfg4_calls.py 2 rows > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu rc=$?"
