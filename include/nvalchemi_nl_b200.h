@@ -90,7 +90,9 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
  * Between the two: nvnl_status (sizes the outputs; launch_hint = bit 0 unwrapped | bit 1 had_deferred is REQUIRED
  * here; if rows_overflow is set the temporary buffer — 160 entries per atom — was too small and the query must be
  * repeated with nvnl_count / nvnl_fill_coo).  Inputs with atoms outside the primary periodic image are detected on
- * the device and served by the two-pass kernels inside these same calls. */
+ * the device and served by the two-pass kernels inside these same calls.  launch_hint bit 2 (value 4) of
+ * nvnl_fill_rows: `shifts` is already zero — only rows of cells at a periodic boundary write their image shifts.
+ * Atom indices must be below 2^28 on this path. */
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
                     void* stream);

@@ -298,7 +298,7 @@ int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, do
         return launch_pair<float, MODE_FILL_COO, HALF, FMA>(a, hint, st);
     }
     k_rows_out<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts,
-                                                           index_offset);
+                                                           index_offset, (hint & 4) ? 1 : 0);
     NVNL_CHECK_LAUNCH("k_rows_out");
     if (hint & 2) {
         a.queue = 3;  // the deferred list of the count stage was kept for this launch
@@ -448,6 +448,7 @@ int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_syste
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr, void* stream) {
     if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count_rows: bad arguments");
     if (dtype != NVNL_F32) return fail(-1, "nvnl_count_rows: the single-sweep path is fp32 only (use nvnl_count)");
+    if (n_atoms >= (1LL << 28)) return fail(-1, "nvnl_count_rows: the single-sweep path takes fewer than 2^28 atoms (use nvnl_count)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (half_fill)

@@ -237,8 +237,9 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     const int excl = incl - packed;
     const int exA = excl & 0xffff, exB = excl >> 16;
     const int maxn = __reduce_max_sync(0xffffffffu, nA > nB ? nA : nB);
-    const int mul = shifted ? 2 : 1;
-    const int need = (cntA + cntB) * mul;
+    // row of a cell at a periodic boundary: [kRowsMaxSeg packed image keys][entries = atom | segment << 28]
+    const int hdr = shifted ? kRowsMaxSeg : 0;
+    const int need = cntA + cntB + 2 * hdr;
     bool ok = true;
     if (al.pos + need > al.end) {
         const long long sz = need > kRowsBlock ? need : kRowsBlock;
@@ -258,10 +259,10 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     int startA = 0, startB = 0;
     if (ok) {
         startA = (int)al.pos;
-        startB = startA + cntA * mul;
+        startB = startA + hdr + cntA;
         al.pos += need;
-        int* __restrict__ rowA = rows + startA + exA;
-        int* __restrict__ rowB = rows + startB + exB;
+        int* __restrict__ rowA = rows + startA + hdr + exA;
+        int* __restrict__ rowB = rows + startB + hdr + exB;
         // two slots of both lists per trip: four independent index -> atom gathers in flight.  Slots past a list's
         // length hold stale (valid) entries — the lists are zero-initialised — and are read but not stored.
         // entry -> record address: tile index = chunk * 32 + lane
@@ -283,16 +284,26 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
                 if (s + 1 < nB) rowB[s + 1] = jB1;
             }
         } else {
-            // cell at a periodic boundary: entries carry their segment; its packed image key goes behind the row
+            // cell at a periodic boundary: the row starts with the stencil's packed image keys, every entry carries
+            // its segment in the top bits (atom indices < 2^28 on this path)
+            if (lane < kRowsMaxSeg) {
+                const int key = lane < sm.nseg ? sm.seg_key[lane] : 0;
+                rows[startA + lane] = key;
+                rows[startB + lane] = key;
+            }
 #pragma unroll 1
-            for (int s = 0; s < maxn; ++s) {
+            for (int s = 0; s < maxn; s += 2) {
                 const uint32_t o = (uint32_t)s * 32u;
-                const int vA = lds_u8(lbaseA + o), vB = lds_u8(lbaseB + o);
-                const int jA = lds_rec_j<float>(cand_lane + (uint32_t)(vA & 31) * (32u * RS));
-                const int jB = lds_rec_j<float>(cand_lane + (uint32_t)(vB & 31) * (32u * RS));
-                const int kA = sm.seg_key[vA >> 5], kB = sm.seg_key[vB >> 5];
-                if (s < nA) { rowA[s] = jA; rowA[cntA + s] = kA; }
-                if (s < nB) { rowB[s] = jB; rowB[cntB + s] = kB; }
+                const int vA0 = lds_u8(lbaseA + o), vA1 = lds_u8(lbaseA + o + 32u);
+                const int vB0 = lds_u8(lbaseB + o), vB1 = lds_u8(lbaseB + o + 32u);
+                const int jA0 = lds_rec_j<float>(cand_lane + (uint32_t)(vA0 & 31) * (32u * RS));
+                const int jA1 = lds_rec_j<float>(cand_lane + (uint32_t)(vA1 & 31) * (32u * RS));
+                const int jB0 = lds_rec_j<float>(cand_lane + (uint32_t)(vB0 & 31) * (32u * RS));
+                const int jB1 = lds_rec_j<float>(cand_lane + (uint32_t)(vB1 & 31) * (32u * RS));
+                if (s < nA) rowA[s] = jA0 | ((vA0 >> 5) << 28);
+                if (s + 1 < nA) rowA[s + 1] = jA1 | ((vA1 >> 5) << 28);
+                if (s < nB) rowB[s] = jB0 | ((vB0 >> 5) << 28);
+                if (s + 1 < nB) rowB[s + 1] = jB1 | ((vB1 >> 5) << 28);
             }
         }
     }
@@ -576,8 +587,9 @@ __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int valu
 }
 
 __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
-                                                  const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
-                                                  int* __restrict__ out_j, int* __restrict__ out_shifts, int index_offset) {
+                                                     const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
+                                                     int* __restrict__ out_j, int* __restrict__ out_shifts, int index_offset,
+                                                     int shifts_zeroed) {
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
     const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
     const int lane = threadIdx.x & 31;
@@ -588,7 +600,8 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
     const int p_l = neighbor_ptr[il < n ? il : n];
     const int pe_l = neighbor_ptr[il + 1 < n ? il + 1 : n];
     const int na = n - base < 32 ? (int)(n - base) : 32;
-    // software pipeline: the row of atom t + 1 is in flight while atom t is written
+    // software pipeline: the row of atom t + 1 is in flight while atom t is written.  entries of a row start behind
+    // its header (boundary rows: kRowsMaxSeg image keys)
     int ref = __shfl_sync(0xffffffffu, ref_l, 0);
     int p = __shfl_sync(0xffffffffu, p_l, 0);
     int cnt = __shfl_sync(0xffffffffu, pe_l, 0) - p;
@@ -596,7 +609,7 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int k = lane + 32 * u;
-        v[u] = (ref >= 0 && k < cnt) ? rows[(ref >> 1) + k] : 0;
+        v[u] = (ref >= 0 && k < cnt) ? rows[(ref >> 1) + ((ref & 1) ? kRowsMaxSeg : 0) + k] : 0;
     }
     for (int t = 0; t < na; ++t) {
         int nref = -1, np = 0, ncnt = 0;
@@ -608,31 +621,48 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = lane + 32 * u;
-                nv[u] = (nref >= 0 && k < ncnt) ? rows[(nref >> 1) + k] : 0;
+                nv[u] = (nref >= 0 && k < ncnt) ? rows[(nref >> 1) + ((nref & 1) ? kRowsMaxSeg : 0) + k] : 0;
             }
         }
         if (ref >= 0 && cnt > 0) {
-            const int* __restrict__ row = rows + (ref >> 1);
             const int iv = (int)(base + t) + index_offset;
             int* __restrict__ oj = out_j + (size_t)p;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = lane + 32 * u;
-                if (k < cnt) oj[k] = v[u] + index_offset;
-            }
-            for (int k = 128 + lane; k < cnt; k += 32) oj[k] = row[k] + index_offset;  // rows longer than 128 (rare)
-            warp_fill(out_i + (size_t)p, cnt, iv, lane);
             int* sh = out_shifts + 3 * (size_t)p;
+            warp_fill(out_i + (size_t)p, cnt, iv, lane);
             if (!(ref & 1)) {
-                warp_fill(sh, 3 * cnt, 0, lane);
-            } else {
-                for (int k = lane; k < cnt; k += 32) {
-                    int csx, csy, csz;
-                    unpack_key(row[cnt + k], csx, csy, csz);
-                    sh[3 * k] = csx;
-                    sh[3 * k + 1] = csy;
-                    sh[3 * k + 2] = csz;
+                const int* __restrict__ row = rows + (ref >> 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = lane + 32 * u;
+                    if (k < cnt) oj[k] = v[u] + index_offset;
                 }
+                for (int k = 128 + lane; k < cnt; k += 32) oj[k] = row[k] + index_offset;  // rows longer than 128 (rare)
+                if (!shifts_zeroed) warp_fill(sh, 3 * cnt, 0, lane);
+            } else {
+                const int* __restrict__ hdr = rows + (ref >> 1);
+                const int* __restrict__ row = hdr + kRowsMaxSeg;
+                const int keyl = lane < kRowsMaxSeg ? hdr[lane] : 0;
+                if (!shifts_zeroed) {
+                    warp_fill(sh, 3 * cnt, 0, lane);
+                    __syncwarp();  // the zeros of other lanes precede the image shifts written below
+                }
+                auto emit = [&](int e, int k) {
+                    const int key = __shfl_sync(0xffffffffu, keyl, ((unsigned)e >> 28) & (kRowsMaxSeg - 1));
+                    if (k < cnt) {
+                        oj[k] = (e & 0x0fffffff) + index_offset;
+                        if (key != 0) {
+                            int csx, csy, csz;
+                            unpack_key(key, csx, csy, csz);
+                            sh[3 * k] = csx;
+                            sh[3 * k + 1] = csy;
+                            sh[3 * k + 2] = csz;
+                        }
+                    }
+                };
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (32 * u < cnt) emit(v[u], 32 * u + lane);
+                for (int k0 = 128; k0 < cnt; k0 += 32) emit(k0 + lane < cnt ? row[k0 + lane] : 0, k0 + lane);
             }
         }
         ref = nref; p = np; cnt = ncnt;

@@ -13,3 +13,8 @@ fma: bool = True
 # "masks" = two sweeps: count pass stores hit masks, fill pass expands them at neighbor_ptr (csrc/nvnl_fast.cuh).
 # fp64 inputs always take "masks".  Both produce the same sets (tests/test_gpu_parity.py runs both).
 coo_path: str = "rows"
+
+# Single-sweep COO path: zero the shifts output on a side stream while the sweep runs, sized from the pair count of the
+# previous query with the same (device, atoms, systems, cutoff, half_fill) signature.  False = always zero after the
+# size sync (inside the output kernel).
+prezero_shifts: bool = True

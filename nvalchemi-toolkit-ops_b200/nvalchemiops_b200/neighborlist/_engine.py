@@ -156,7 +156,39 @@ def use_rows(h: CellListHandle) -> bool:
     """fp32 inputs take the single-sweep COO path unless config.coo_path says otherwise."""
     if config.coo_path not in ("rows", "masks"):
         raise ValueError(f"config.coo_path must be 'rows' or 'masks', not {config.coo_path!r}")
-    return config.coo_path == "rows" and h.dtype == torch.float32
+    return config.coo_path == "rows" and h.dtype == torch.float32 and h.n < (1 << 28)
+
+
+# Pair count of the last COO query per (device, atoms, systems, cutoff^2, half_fill): lets the next query with the same
+# signature (MD steps, repeated evaluations) zero its shifts buffer on a side stream WHILE the sweep runs instead of
+# after the size sync.  Only a size is remembered — never an output; a wrong guess costs nothing but the overlap.
+_pair_history: dict = {}
+_side_streams: dict = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index or 0
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _prezero_shifts(h: CellListHandle, key):
+    """Speculatively allocate and zero (on the side stream) a shifts buffer sized from the last query with this
+    signature.  Returns (buffer, event) or (None, None)."""
+    guess = _pair_history.get(key)
+    if not config.prezero_shifts or not guess:
+        return None, None
+    cap = int(guess * 1.02) + 1024
+    cur = torch.cuda.current_stream(h.device)
+    side = _side_stream(h.device)
+    buf = torch.empty(3 * cap, dtype=torch.int32, device=h.device)
+    side.wait_stream(cur)       # the allocator may hand out memory that kernels already queued on `cur` still write
+    with torch.cuda.stream(side):
+        buf.zero_()
+        ev = side.record_event()
+    buf.record_stream(side)     # if the guess is dropped, the block is not reused before the memset has run
+    return buf, ev
 
 
 def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False):
@@ -194,16 +226,28 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     """COO outputs ``(neighbor_list [2,P], neighbor_ptr [N+1], shifts [P,3])``: count -> scan -> one sync for the
     size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
+    key = (torch.device(h.device).index or 0, h.n, h.ns, float(cutoff_sq), bool(half_fill))
+    zbuf, zev = _prezero_shifts(h, key) if use_rows(h) else (None, None)
     num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
     if total > 2**31 - 1:
         raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
-    # one allocation for both outputs (the GPU idles between the size sync and the first fill launch)
-    buf = torch.empty(5 * total, dtype=torch.int32, device=h.device)
-    edge_index = buf[: 2 * total].view(2, total)
-    shifts = buf[2 * total:].view(total, 3)
+    if len(_pair_history) > 256:
+        _pair_history.clear()
+    _pair_history[key] = total
+    if rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel() and not (hint & 1):
+        # the speculative buffer fits: shifts is its (contiguous) prefix, already zero when the fill starts
+        edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
+        shifts = zbuf[: 3 * total].view(total, 3)
+        torch.cuda.current_stream(h.device).wait_event(zev)
+        hint |= 4
+    else:
+        # one allocation for both outputs (the GPU idles between the size sync and the first fill launch)
+        buf = torch.empty(5 * total, dtype=torch.int32, device=h.device)
+        edge_index = buf[: 2 * total].view(2, total)
+        shifts = buf[2 * total:].view(total, 3)
     if total > 0:
         fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill, launch_hint=hint, rows=rows)
     return edge_index, ptr, shifts, num

@@ -727,3 +727,42 @@ def test_config4_1m_atoms_masks_path_matches_rows_path():
         config.coo_path = old
     assert torch.equal(keys["rows"][0], keys["masks"][0])
     assert torch.equal(keys["rows"][1], keys["masks"][1])
+
+
+def test_rows_path_prezeroed_shifts_on_repeated_queries():
+    """Second and later COO queries with the same (atoms, cutoff) signature zero the shifts buffer on a side stream
+    while the sweep runs (sized from the previous pair count).  Results must not depend on it: same positions, more
+    pairs than guessed (falls back), far fewer pairs than guessed (falls back), boundary rows, deferred cells."""
+    from nvalchemiops_b200 import config
+    from nvalchemiops_b200.neighborlist import _engine
+
+    assert config.coo_path == "rows" and config.prezero_shifts
+    _engine._pair_history.clear()
+    n = 6000
+    base, cell, pbc = random_system(n, 40.0, torch.float32, seed=41)
+    dense = base.clone()
+    dense[: n // 2] = dense[: n // 2] * 0.25 + 15.0           # half of the atoms squeezed into a (10 A)^3 corner
+    sparse = base.clone()
+    sparse[:, 0] = torch.linspace(0.0, 39.9, n)               # same count, very different pair total
+    sparse[:, 1:] *= 0.02
+    seq = [base, base, base * 1.0, dense, dense, sparse, sparse, base]
+    for k, pos in enumerate(seq):
+        o = ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=4096, nthreads=8)
+        assert o[1].max() <= 4096
+        want = ro.records_from_matrix(*o)
+        e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=4096, return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), k
+        assert e.is_contiguous() and s.is_contiguous() and s.shape == (want.shape[0], 3)
+    # batch of small systems: everything deferred to the general kernel, buffer still pre-zeroed on the second call
+    bp, bc, bb, bi, bptr = bench_batch(16, 150, 250, seed=3)
+    want = ro.records_from_matrix(*ro.batch_cell_list(bp, 6.0, bc, bb, bi, max_neighbors=1024))
+    for _ in range(3):
+        e, p, s = _nl().batch_cell_list(bp.to(DEV), 6.0, bc.to(DEV), bb.to(DEV), bi.to(DEV), return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    config.prezero_shifts = False
+    try:
+        e, p, s = _nl().cell_list(base.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=4096, return_neighbor_list=True)
+        want = ro.records_from_matrix(*ro.cell_list(base, 6.0, cell, pbc, max_neighbors=4096, nthreads=8))
+        assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    finally:
+        config.prezero_shifts = True
