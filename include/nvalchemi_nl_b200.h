@@ -90,12 +90,15 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
  * Between the two: nvnl_status (sizes the outputs; launch_hint = bit 0 unwrapped | bit 1 had_deferred is REQUIRED
  * here; if rows_overflow is set the temporary buffer — 160 entries per atom — was too small and the query must be
  * repeated with nvnl_count / nvnl_fill_coo).  Inputs with atoms outside the primary periodic image are detected on
- * the device and served by the two-pass kernels inside these same calls.  launch_hint bit 2 (value 4) of
+ * the device and served by the two-pass kernels inside these same calls.
+ * prezero / prezero_ints (optional, 16-byte aligned): a buffer the sweep kernel zero-fills while it runs — the sweep is
+ * issue-bound, the zero_() of the shifts output (cell_list.py:1358-1373) is pure HBM writes.  A caller that can guess
+ * the pair count (e.g. from its previous query) passes its shifts buffer here and sets launch_hint bit 2 (value 4) of
  * nvnl_fill_rows: `shifts` is already zero — only rows of cells at a periodic boundary write their image shifts.
  * Atom indices must be below 2^28 on this path. */
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
-                    void* stream);
+                    int32_t* prezero, int64_t prezero_ints, void* stream);
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                    double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
                    int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);

@@ -1,6 +1,7 @@
 // nvnl_api.cu — C ABI (include/nvalchemi_nl_b200.h) over the sm_100a kernels.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/nvalchemi_nl_b200.h"
@@ -255,7 +256,7 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
 
 template <bool HALF, bool FMA>
 int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, int* num_neighbors,
-                 int* neighbor_ptr, cudaStream_t st) {
+                 int* neighbor_ptr, int* prezero, long long prezero_ints, cudaStream_t st) {
     SweepArgs<float> a = base_args<float>(ws, n, ns, batch_idx, cutoff_sq);
     a.num_neighbors = num_neighbors;
     int rc = launch_query_reset(ws, a.L, n, 1, st);
@@ -263,6 +264,8 @@ int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, d
     RowsArgs r;
     r.ws = ws; r.L = a.L; r.batch_idx = batch_idx; r.num_systems = ns; r.n = n; r.cutoff_sq = (float)cutoff_sq;
     r.num_neighbors = num_neighbors;
+    r.prezero = prezero_ints > 0 ? prezero : nullptr;
+    r.prezero_ints = prezero_ints > 0 ? prezero_ints : 0;
     rc = launch_rows_t<HALF, FMA>(r, st);                                   // wrapped inputs: the single sweep
     if (rc) return rc;
     a.queue = 0;
@@ -445,17 +448,20 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
 }
 
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
-                    double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr, void* stream) {
+                    double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
+                    int32_t* prezero, int64_t prezero_ints, void* stream) {
     if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count_rows: bad arguments");
     if (dtype != NVNL_F32) return fail(-1, "nvnl_count_rows: the single-sweep path is fp32 only (use nvnl_count)");
     if (n_atoms >= (1LL << 28)) return fail(-1, "nvnl_count_rows: the single-sweep path takes fewer than 2^28 atoms (use nvnl_count)");
+    if (prezero_ints < 0 || (prezero_ints > 0 && (!prezero || reinterpret_cast<uintptr_t>(prezero) % 16)))
+        return fail(-1, "nvnl_count_rows: prezero must be a 16-byte aligned device pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (half_fill)
-        return fma ? count_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st)
-                   : count_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st);
-    return fma ? count_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st)
-               : count_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, st);
+        return fma ? count_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st)
+                   : count_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st);
+    return fma ? count_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st)
+               : count_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st);
 }
 
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,

@@ -49,6 +49,8 @@ struct RowsArgs {
     long long n;
     float cutoff_sq;
     int* num_neighbors;
+    int* prezero;             // optional: buffer the kernel zero-fills while it sweeps (the shifts output, sized by the caller's guess)
+    long long prezero_ints;
 };
 
 __device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
@@ -368,6 +370,34 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
         uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
         int g_next = 0;
         if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+        // Zero-fill of the caller's shifts buffer, fused into the sweep: the sweep is issue-bound and leaves HBM idle, the
+        // zero-fill is pure HBM writes.  Every CTA owns one slice; its producer warp writes a quota of it per published
+        // cell (paced over the kernel's lifetime) and the rest when the queue is drained.  A separate memset kernel does
+        // not do: next to this kernel's 72 KB CTAs it only runs if the SM already has the large shared-memory carve-out,
+        // otherwise the two serialise (profiles/r2_zero_overlap.txt).
+        int4* const zbase = reinterpret_cast<int4*>(a.prezero);
+        long long zpos = 0, zend = 0, zquota = 0;
+        if (a.prezero) {
+            const long long n16 = a.prezero_ints >> 2;
+            const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
+            zpos = (long long)blockIdx.x * slice;
+            zend = zpos + slice < n16 ? zpos + slice : n16;
+            if (zpos > zend) zpos = zend;
+            const long long cells_here = total_cells / (int)gridDim.x > 0 ? total_cells / (int)gridDim.x : 1;
+            zquota = (zend - zpos) / cells_here + 32;
+            if (blockIdx.x == 0 && lane < (int)(a.prezero_ints & 3)) a.prezero[(n16 << 2) + lane] = 0;
+        }
+        auto zero_some = [&](long long quota) {
+            long long e = zpos + quota;
+            e = e < zend ? e : zend;
+            const int4 z4 = make_int4(0, 0, 0, 0);
+            long long k = zpos + lane;
+            for (; k + 96 < e; k += 128) {
+                zbase[k] = z4; zbase[k + 32] = z4; zbase[k + 64] = z4; zbase[k + 96] = z4;
+            }
+            for (; k < e; k += 32) zbase[k] = z4;
+            zpos = e;
+        };
         for (;;) {
             // ---- 1. prepare the next cell entirely in registers (dependent global loads, image enumeration, shift
             //         sort) BEFORE waiting for a ring stage: after the consumers release a stage only the table
@@ -471,6 +501,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 have = true;
                 break;
             }
+            if (zpos < zend) zero_some(have ? zquota : zend - zpos);
             // ---- 2. wait until the consumers have released this ring stage, then publish the tables and issue the copies ----
             mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
             FastStage<T>& sg = sm.stage[stage];

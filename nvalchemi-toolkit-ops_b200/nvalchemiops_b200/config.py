@@ -18,3 +18,4 @@ coo_path: str = "rows"
 # previous query with the same (device, atoms, systems, cutoff, half_fill) signature.  False = always zero after the
 # size sync (inside the output kernel).
 prezero_shifts: bool = True
+prezero_min_pairs: int = 1_000_000   # below this the extra launch + event cost more than the overlap saves

@@ -160,50 +160,40 @@ def use_rows(h: CellListHandle) -> bool:
 
 
 # Pair count of the last COO query per (device, atoms, systems, cutoff^2, half_fill): lets the next query with the same
-# signature (MD steps, repeated evaluations) zero its shifts buffer on a side stream WHILE the sweep runs instead of
-# after the size sync.  Only a size is remembered — never an output; a wrong guess costs nothing but the overlap.
+# signature (MD steps, repeated evaluations) hand the sweep kernel a shifts buffer to zero-fill WHILE it sweeps, instead
+# of zero-filling after the size sync.  Only a size is remembered — never an output; a wrong guess costs nothing but
+# the overlap.
 _pair_history: dict = {}
-_side_streams: dict = {}
 
 
-def _side_stream(device):
-    key = torch.device(device).index or 0
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    return _side_streams[key]
-
-
-def _prezero_shifts(h: CellListHandle, key):
-    """Speculatively allocate and zero (on the side stream) a shifts buffer sized from the last query with this
-    signature.  Returns (buffer, event) or (None, None)."""
+def _guess_shifts_buffer(h: CellListHandle, key):
+    """Speculatively allocate a shifts buffer sized from the last query with this signature (or None)."""
     guess = _pair_history.get(key)
-    if not config.prezero_shifts or not guess:
-        return None, None
-    cap = int(guess * 1.02) + 1024
-    cur = torch.cuda.current_stream(h.device)
-    side = _side_stream(h.device)
-    buf = torch.empty(3 * cap, dtype=torch.int32, device=h.device)
-    side.wait_stream(cur)       # the allocator may hand out memory that kernels already queued on `cur` still write
-    with torch.cuda.stream(side):
-        buf.zero_()
-        ev = side.record_event()
-    buf.record_stream(side)     # if the guess is dropped, the block is not reused before the memset has run
-    return buf, ev
+    if not config.prezero_shifts or not guess or guess < config.prezero_min_pairs:
+        return None
+    return torch.empty(3 * (int(guess * 1.02) + 1024), dtype=torch.int32, device=h.device)
 
 
-def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False):
+def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False, prezero=None):
     """num_neighbors [N] and (optionally) neighbor_ptr [N+1] (nvnl_count / nvnl_count_rows); asynchronous.
     ``rows=True`` also leaves every atom's neighbors in the workspace's temporary row buffer for ``fill_coo(rows=True)``."""
     num = torch.empty(h.n, dtype=torch.int32, device=h.device)
     ptr = torch.empty(h.n + 1, dtype=torch.int32, device=h.device) if want_ptr else None
     L = _lib.lib()
-    fn, name = (L.nvnl_count_rows, "nvnl_count_rows") if rows else (L.nvnl_count, "nvnl_count")
     with torch.cuda.device(h.device):
-        _lib.check(
-            fn(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq), int(bool(half_fill)),
-               int(bool(config.fma)), _ptr(num), _ptr(ptr), _stream(h.device)),
-            name,
-        )
+        if rows:
+            _lib.check(
+                L.nvnl_count_rows(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
+                                  int(bool(half_fill)), int(bool(config.fma)), _ptr(num), _ptr(ptr), _ptr(prezero),
+                                  prezero.numel() if prezero is not None else 0, _stream(h.device)),
+                "nvnl_count_rows",
+            )
+        else:
+            _lib.check(
+                L.nvnl_count(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
+                             int(bool(half_fill)), int(bool(config.fma)), _ptr(num), _ptr(ptr), _stream(h.device)),
+                "nvnl_count",
+            )
     return num, ptr
 
 
@@ -227,8 +217,8 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
     key = (torch.device(h.device).index or 0, h.n, h.ns, float(cutoff_sq), bool(half_fill))
-    zbuf, zev = _prezero_shifts(h, key) if use_rows(h) else (None, None)
-    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill)
+    zbuf = _guess_shifts_buffer(h, key) if use_rows(h) else None
+    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill, prezero=zbuf)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
@@ -241,7 +231,6 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
         # the speculative buffer fits: shifts is its (contiguous) prefix, already zero when the fill starts
         edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
         shifts = zbuf[: 3 * total].view(total, 3)
-        torch.cuda.current_stream(h.device).wait_event(zev)
         hint |= 4
     else:
         # one allocation for both outputs (the GPU idles between the size sync and the first fill launch)
@@ -253,12 +242,12 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     return edge_index, ptr, shifts, num
 
 
-def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False):
+def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None):
     """Count stage + the one host sync: ``(num, ptr, total, max_count, error_bits, launch_hint, rows)``.  ``rows``
     tells ``fill_coo`` which path the count ran on (single sweep unless fp64 / configured off / its temporary row
     buffer overflowed, in which case the count is repeated on the two-pass path)."""
     rows = use_rows(h)
-    num, ptr = count(h, cutoff_sq, half_fill, rows=rows)
+    num, ptr = count(h, cutoff_sq, half_fill, rows=rows, prezero=prezero if rows else None)
     total, max_count, _cells, err, hint = status(h)
     if rows and h.rows_overflow:
         rows = False

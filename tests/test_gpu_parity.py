@@ -738,6 +738,7 @@ def test_rows_path_prezeroed_shifts_on_repeated_queries():
 
     assert config.coo_path == "rows" and config.prezero_shifts
     _engine._pair_history.clear()
+    old_min, config.prezero_min_pairs = config.prezero_min_pairs, 1
     n = 6000
     base, cell, pbc = random_system(n, 40.0, torch.float32, seed=41)
     dense = base.clone()
@@ -766,3 +767,4 @@ def test_rows_path_prezeroed_shifts_on_repeated_queries():
         assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
     finally:
         config.prezero_shifts = True
+        config.prezero_min_pairs = old_min
