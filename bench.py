@@ -312,6 +312,9 @@ def main():
         "stages_ms": stage_ms, "longest_stage": dom,
         "pipeline": {"achieved": B / (ms_per_step * 1e-3) / 1e9, "frac": B / (ms_per_step * 1e-3) / 1e9 / peak,
                      "note": "all stages of one neighbor_list call (incl. the size sync and output allocation)"},
+        "api_note": "stages_ms times nvnl_fill_rows writing every output byte itself (the kernel the roofline line is about); in "
+                    "the public-API loop above, repeated queries let the sweep kernel zero-fill the shifts buffer while it "
+                    "sweeps (fused into k_rows' producer warps), so ms_per_step is below the sum of the stages",
         "count_stage_note": "the sweep (k_rows / k_fast<COUNT>) is fp32-issue bound (583 distance tests/atom), not an HBM kernel: "
                             f"{n * 583 / (stage_ms['count'] * 1e-3) / 1e12:.2f} T tests/s",
     }

@@ -659,15 +659,22 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
             const int iv = (int)(base + t) + index_offset;
             int* __restrict__ oj = out_j + (size_t)p;
             int* sh = out_shifts + 3 * (size_t)p;
-            warp_fill(out_i + (size_t)p, cnt, iv, lane);
+            int* __restrict__ oi = out_i + (size_t)p;
             if (!(ref & 1)) {
                 const int* __restrict__ row = rows + (ref >> 1);
+                int* __restrict__ ojl = oj + lane;   // per-lane bases: the four stores below differ by immediates only
+                int* __restrict__ oil = oi + lane;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int k = lane + 32 * u;
-                    if (k < cnt) oj[k] = v[u] + index_offset;
+                    if (lane + 32 * u < cnt) {
+                        ojl[32 * u] = v[u] + index_offset;
+                        oil[32 * u] = iv;
+                    }
                 }
-                for (int k = 128 + lane; k < cnt; k += 32) oj[k] = row[k] + index_offset;  // rows longer than 128 (rare)
+                for (int k = 128 + lane; k < cnt; k += 32) {  // rows longer than 128 (rare)
+                    oj[k] = row[k] + index_offset;
+                    oi[k] = iv;
+                }
                 if (!shifts_zeroed) warp_fill(sh, 3 * cnt, 0, lane);
             } else {
                 const int* __restrict__ hdr = rows + (ref >> 1);
@@ -681,6 +688,7 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
                     const int key = __shfl_sync(0xffffffffu, keyl, ((unsigned)e >> 28) & (kRowsMaxSeg - 1));
                     if (k < cnt) {
                         oj[k] = (e & 0x0fffffff) + index_offset;
+                        oi[k] = iv;
                         if (key != 0) {
                             int csx, csy, csz;
                             unpack_key(key, csx, csy, csz);
