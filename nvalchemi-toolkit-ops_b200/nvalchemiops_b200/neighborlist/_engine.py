@@ -168,8 +168,9 @@ _pair_history: dict = {}
 
 def _guess_shifts_buffer(h: CellListHandle, key):
     """Speculatively allocate a shifts buffer sized from the last query with this signature (or None)."""
-    guess = _pair_history.get(key)
-    if not config.prezero_shifts or not guess or guess < config.prezero_min_pairs:
+    guess, last_hint = _pair_history.get(key, (0, 0))
+    # (inputs that were outside the primary periodic image last time take the two-pass kernels: nothing to overlap)
+    if not config.prezero_shifts or not guess or guess < config.prezero_min_pairs or (last_hint & 1):
         return None
     return torch.empty(3 * (int(guess * 1.02) + 1024), dtype=torch.int32, device=h.device)
 
@@ -226,7 +227,7 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
         raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
     if len(_pair_history) > 256:
         _pair_history.clear()
-    _pair_history[key] = total
+    _pair_history[key] = (total, hint)
     if rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel() and not (hint & 1):
         # the speculative buffer fits: shifts is its (contiguous) prefix, already zero when the fill starts
         edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
