@@ -168,3 +168,110 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "reference_oracle" not in src and "nl_oracle" not in src, f
+
+
+def test_rows_path_c_abi_argument_validation_and_budget():
+    """nvnl_count_rows / nvnl_fill_rows reject bad arguments before touching CUDA; nvnl_set_rows_budget sizes the
+    temporary row buffer inside the workspace."""
+    from nvalchemiops_b200 import _lib
+
+    lib = _lib.lib()
+    dummy = ctypes.c_void_p(4096)          # never dereferenced: validation fails first
+    assert lib.nvnl_count_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
+    assert b"fp32 only" in lib.nvnl_last_error()
+    assert lib.nvnl_count_rows(dummy, 0, 1 << 28, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
+    assert b"2^28" in lib.nvnl_last_error()
+    assert lib.nvnl_count_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, ctypes.c_void_p(4100), 64, None) != 0
+    assert b"16-byte aligned" in lib.nvnl_last_error()
+    assert lib.nvnl_fill_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, dummy, 0, -1, None) != 0
+    assert b"launch_hint" in lib.nvnl_last_error()
+    assert lib.nvnl_fill_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, dummy, 0, 0, None) != 0
+    base = lib.nvnl_workspace_bytes(100000, 1, 0)
+    try:
+        lib.nvnl_set_rows_budget(8, 0)
+        small = lib.nvnl_workspace_bytes(100000, 1, 0)
+        lib.nvnl_set_rows_budget(320, -1)
+        big = lib.nvnl_workspace_bytes(100000, 1, 0)
+    finally:
+        lib.nvnl_set_rows_budget(-1, -1)
+    assert small < base < big
+    assert base - small >= (160 - 8) * 100000 * 4
+    assert lib.nvnl_workspace_bytes(100000, 1, 0) == base
+
+
+def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
+    """Host logic of the COO query (no GPU): which path runs, the repeat on rows_overflow, and when the speculatively
+    sized shifts buffer is handed to the sweep / accepted as the output (launch_hint bit 2)."""
+    from nvalchemiops_b200 import config
+    from nvalchemiops_b200.neighborlist import _engine
+
+    class H:
+        ws = None; dtype_code = 0; ns = 1; batch_idx = None; device = torch.device("cpu"); cutoff = 6.0
+        rows_overflow = False
+
+        def __init__(self, n, dtype=torch.float32):
+            self.n, self.dtype = n, dtype
+
+    assert _engine.use_rows(H(1000)) and not _engine.use_rows(H(1000, torch.float64)) and not _engine.use_rows(H(1 << 28))
+    monkeypatch.setattr(config, "coo_path", "masks")
+    assert not _engine.use_rows(H(1000))
+    monkeypatch.setattr(config, "coo_path", "bogus")
+    with pytest.raises(ValueError):
+        _engine.use_rows(H(1000))
+    monkeypatch.setattr(config, "coo_path", "rows")
+
+    calls = []
+    state = {"total": 5_000_000, "hint": 0, "overflow_once": False}
+
+    def fake_count(h, csq, half_fill=False, want_ptr=True, rows=False, prezero=None):
+        calls.append(("count", rows, None if prezero is None else prezero.numel()))
+        return torch.zeros(h.n, dtype=torch.int32), torch.zeros(h.n + 1, dtype=torch.int32)
+
+    def fake_status(h):
+        h.rows_overflow = state["overflow_once"] and calls[-1][1]
+        return state["total"], 100, 10, 0, state["hint"]
+
+    def fake_fill(h, csq, ptr, edge, shifts, total, half_fill=False, index_offset=0, launch_hint=-1, rows=False):
+        calls.append(("fill", rows, launch_hint, tuple(edge.shape), tuple(shifts.shape), shifts.is_contiguous()))
+
+    monkeypatch.setattr(_engine, "count", fake_count)
+    monkeypatch.setattr(_engine, "status", fake_status)
+    monkeypatch.setattr(_engine, "fill_coo", fake_fill)
+    _engine._pair_history.clear()
+    h = H(60_000)
+    # first query: nothing known -> no speculative buffer, the output kernel zero-fills (bit 2 clear)
+    _engine.query_coo(h, 36.0)
+    assert calls == [("count", True, None), ("fill", True, 0, (2, 5_000_000), (5_000_000, 3), True)]
+    # second query, same signature: buffer of the last size + 2 % goes to the sweep and becomes the output
+    calls.clear()
+    e, p, s, num = _engine.query_coo(h, 36.0)
+    assert calls[0] == ("count", True, 3 * (int(5_000_000 * 1.02) + 1024))
+    assert calls[1] == ("fill", True, 4, (2, 5_000_000), (5_000_000, 3), True) and s.shape == (5_000_000, 3)
+    # more pairs than guessed: the guess is dropped
+    calls.clear(); state["total"] = 5_500_000
+    _engine.query_coo(h, 36.0)
+    assert calls[0][2] is not None and calls[1][2] == 0
+    # far fewer pairs than guessed: do not pin a mostly unused buffer
+    calls.clear(); state["total"] = 1_200_000
+    _engine.query_coo(h, 36.0)
+    assert calls[0][2] is not None and calls[1][2] == 0
+    # a different cutoff has its own history
+    calls.clear()
+    _engine.query_coo(h, 25.0)
+    assert calls[0] == ("count", True, None)
+    # unwrapped inputs: two-pass kernels served the query -> never "pre-zeroed", and no speculation next time
+    calls.clear(); state["hint"] = 1
+    _engine.query_coo(h, 36.0)
+    assert calls[1][2] == 1
+    calls.clear()
+    _engine.query_coo(h, 36.0)
+    assert calls[0] == ("count", True, None) and calls[1][2] == 1
+    # temporary rows overflow: the count is repeated on the two-pass path and the fill follows it
+    calls.clear(); state.update(hint=0, overflow_once=True)
+    _engine.query_coo(h, 36.0)
+    assert [c[:2] for c in calls] == [("count", True), ("count", False), ("fill", False)] and h.rows_overflow
+    # small results are not worth the extra buffer
+    calls.clear(); state.update(total=10_000, overflow_once=False)
+    _engine.query_coo(h, 4.0); _engine.query_coo(h, 4.0)
+    assert calls[2] == ("count", True, None)
+    _engine._pair_history.clear()
