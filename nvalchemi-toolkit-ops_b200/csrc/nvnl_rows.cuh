@@ -26,20 +26,22 @@ namespace nvnl {
 
 constexpr int kRowsCons = 8;                          // consumer warps per CTA
 constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
-constexpr int kRowsStages = 3;                        // TMA ring depth (consumers may run up to two cells apart)
+constexpr int kRowsStages = 3;                        // default TMA ring depth (consumers may run up to two cells apart)
 constexpr int kRowsMaxSeg = 8;                        // image segments per stencil the lean kernel takes (3 bits in a list entry)
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
 
+template <int STAGES>
 struct RowsSmem {
-    FastStage<float> stage[kRowsStages];
+    FastStage<float> stage[STAGES];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
     // lane-private hit lists, two targets per warp: slot s of lane l is byte s * 32 + l; an entry is
     // chunk | segment << 5 (the candidate's tile index is chunk * 32 + l); a lane cannot have more hits than chunks
     alignas(16) unsigned char lists[kRowsCons][2][32 * 32];
-    unsigned long long full[kRowsStages], empty[kRowsStages];               // mbarriers of the ring
+    unsigned long long full[STAGES], empty[STAGES];                         // mbarriers of the ring
 };
 
-constexpr size_t rows_smem_bytes() { return (size_t)kRowsStages * kFastStageBytes + sizeof(RowsSmem); }
+template <int STAGES>
+constexpr size_t rows_smem_bytes() { return (size_t)STAGES * kFastStageBytes + sizeof(RowsSmem<STAGES>); }
 
 struct RowsArgs {
     unsigned char* ws;
@@ -223,7 +225,9 @@ struct RowsAlloc {
 
 // Epilogue of a target pair: drop the self entries, ONE packed warp scan of both targets' list lengths, ONE row
 // reservation, then the lists are gathered (tile index -> original atom index) into the two compact rows.
-template <bool HALF>
+// PAD: every row starts on a 128-byte boundary and is padded to a multiple of 32 entries (the output kernel then reads
+// whole lines; experiment, see k_rows).
+template <bool HALF, bool PAD>
 __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<float>& sm, Ctrl* ctrl, uint32_t cand_addr,
                                            uint32_t lbaseA, uint32_t lbaseB, uint32_t la, uint32_t lb, int selfA, int selfB,
                                            int iA, int iB, bool two, int lane, bool shifted, RowsAlloc& al,
@@ -240,8 +244,9 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     const int exA = excl & 0xffff, exB = excl >> 16;
     const int maxn = __reduce_max_sync(0xffffffffu, nA > nB ? nA : nB);
     // row of a cell at a periodic boundary: [kRowsMaxSeg packed image keys][entries = atom | segment << 28]
-    const int hdr = shifted ? kRowsMaxSeg : 0;
-    const int need = cntA + cntB + 2 * hdr;
+    const int hdr = shifted ? (PAD ? 32 : kRowsMaxSeg) : 0;
+    const int lenA = PAD ? ((cntA + 31) & ~31) : cntA, lenB = PAD ? ((cntB + 31) & ~31) : cntB;
+    const int need = lenA + lenB + 2 * hdr;
     bool ok = true;
     if (al.pos + need > al.end) {
         const long long sz = need > kRowsBlock ? need : kRowsBlock;
@@ -261,7 +266,7 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     int startA = 0, startB = 0;
     if (ok) {
         startA = (int)al.pos;
-        startB = startA + hdr + cntA;
+        startB = startA + hdr + lenA;
         al.pos += need;
         int* __restrict__ rowA = rows + startA + hdr + exA;
         int* __restrict__ rowB = rows + startB + hdr + exB;
@@ -290,8 +295,8 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
             // its segment in the top bits (atom indices < 2^28 on this path)
             if (lane < kRowsMaxSeg) {
                 const int key = lane < sm.nseg ? sm.seg_key[lane] : 0;
-                rows[startA + lane] = key;
-                rows[startB + lane] = key;
+                rows[startA + (PAD ? hdr - kRowsMaxSeg : 0) + lane] = key;   // the keys sit right in front of the entries
+                rows[startB + (PAD ? hdr - kRowsMaxSeg : 0) + lane] = key;
             }
 #pragma unroll 1
             for (int s = 0; s < maxn; s += 2) {
@@ -311,7 +316,7 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
     }
     if (lane < 2 && (lane == 0 || two)) {
         const int i = lane ? iB : iA;
-        if (ok) row_ref[i] = ((lane ? startB : startA) << 1) | (shifted ? 1 : 0);
+        if (ok) row_ref[i] = (((lane ? startB : startA) + (PAD && shifted ? hdr - kRowsMaxSeg : 0)) << 1) | (shifted ? 1 : 0);
         a.num_neighbors[i] = lane ? cntB : cntA;
     }
 }
@@ -320,12 +325,15 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
 // k_rows: warp-specialised persistent kernel (producer identical in role to k_fast's: queue -> stencil images ->
 // shift sort -> segment/chunk tables -> TMA bulk copies into a 2-stage ring).
 // ------------------------------------------------------------------------------------------------
-template <bool HALF, bool FMA>
-__global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
+// STAGES / MINB: ring depth and CTAs per SM.  <3, 3> (72 KB, <= 72 registers) is the measured default; <2, 4> (54 KB,
+// 56 registers, no spills) trades ring depth for 36 instead of 27 resident warps — compiled, selectable with
+// NVNL_ROWS_CONFIG=1, not yet measured.  PAD (NVNL_ROWS_CONFIG=2, or 3 with both): 128-byte aligned, padded temporary rows.
+template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD>
+__global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kStageBytes = kFastStageBytes;
-    RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kRowsStages * kStageBytes);
+    RowsSmem<STAGES>& sm = *reinterpret_cast<RowsSmem<STAGES>*>(smem_raw + (size_t)STAGES * kStageBytes);
     const uint32_t smem_base = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
     constexpr int cap = kCandBytes / (int)RS;
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
     // unwrapped inputs are served by the two-pass kernels launched next to this one
     const bool active = ctrl->unwrapped == 0;
     if (tid == 0) {
-        for (int st = 0; st < kRowsStages; ++st) {
+        for (int st = 0; st < STAGES; ++st) {
             mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kRowsCons);
         }
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
             __syncwarp();
             if (cn > 0)
                 tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
-            if (++stage == kRowsStages) { stage = 0; ephase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; ephase ^= 1u; }
         }
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
         if (lane == 0) {
@@ -589,12 +597,12 @@ __global__ void __launch_bounds__(kRowsThreads, 3) k_rows(const RowsArgs a) {
                 const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
                 uint32_t la = lbaseA, lb = lbaseB;
                 rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, selfA, selfB, la, lb);
-                rows_emit2<HALF>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
+                rows_emit2<HALF, PAD>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
                                  rows, row_ref);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
-            if (++stage == kRowsStages) { stage = 0; fphase ^= 1u; }
+            if (++stage == STAGES) { stage = 0; fphase ^= 1u; }
         }
     }
 }
