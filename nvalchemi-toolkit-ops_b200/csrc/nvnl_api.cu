@@ -105,9 +105,9 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
-template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD>
+template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD, bool UNI>
 int launch_rows_cfg(const RowsArgs& a, cudaStream_t st) {
-    auto kern = k_rows<HALF, FMA, STAGES, MINB, PAD>;
+    auto kern = k_rows<HALF, FMA, STAGES, MINB, PAD, UNI>;
     constexpr size_t smem = rows_smem_bytes<STAGES>();
     static int bps[kMaxDevices] = {0};
     int& blocks_per_sm = bps[current_device()];
@@ -129,13 +129,19 @@ int launch_rows_cfg(const RowsArgs& a, cudaStream_t st) {
 
 template <bool HALF, bool FMA>
 int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
-    // experiment switch (read once): 0 = 3-stage ring, 3 CTAs/SM, compact rows (the measured default);
-    // bit 0 = 2-stage ring, 4 CTAs/SM; bit 1 = 128-byte aligned, padded temporary rows
+    // experiment switch (read once): 0 = 3-stage ring, 3 CTAs/SM, compact rows, per-lane shifts (the measured default);
+    // bit 0 = 2-stage ring, 4 CTAs/SM; bit 1 = 128-byte aligned, padded temporary rows; bit 2 = grouped uniform-shift chunks
     static const int cfg = [] { const char* e = getenv("NVNL_ROWS_CONFIG"); return e ? atoi(e) : 0; }();
-    if (cfg == 1) return launch_rows_cfg<HALF, FMA, 2, 4, false>(a, st);
-    if (cfg == 2) return launch_rows_cfg<HALF, FMA, kRowsStages, 3, true>(a, st);
-    if (cfg == 3) return launch_rows_cfg<HALF, FMA, 2, 4, true>(a, st);
-    return launch_rows_cfg<HALF, FMA, kRowsStages, 3, false>(a, st);
+    switch (cfg & 7) {
+        case 1: return launch_rows_cfg<HALF, FMA, 2, 4, false, false>(a, st);
+        case 2: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, true, false>(a, st);
+        case 3: return launch_rows_cfg<HALF, FMA, 2, 4, true, false>(a, st);
+        case 4: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, false, true>(a, st);
+        case 5: return launch_rows_cfg<HALF, FMA, 2, 4, false, true>(a, st);
+        case 6: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, true, true>(a, st);
+        case 7: return launch_rows_cfg<HALF, FMA, 2, 4, true, true>(a, st);
+        default: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, false, false>(a, st);
+    }
 }
 
 // Start of every query: empty deferred list, empty temporary row buffer (and, for the single-sweep COO path,

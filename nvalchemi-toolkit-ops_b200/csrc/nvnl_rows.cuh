@@ -152,12 +152,43 @@ __device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f
                                         selfB, la, lb);
 }
 
+// four chunks that each lie entirely inside ONE image segment (warp-uniform shift vector per chunk): same structure as
+// rows_chunk2x4 plus the three packed adds of the shift.  Experiment (UNI), see k_rows.
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void rows_chunk2x4_shift(const FastStage<float>& sm, uint32_t addr, int c, int ck, f32x2_t XI,
+                                                    f32x2_t YI, f32x2_t ZI, int iA, int iB, float rc2, int selfA, int selfB,
+                                                    uint32_t& la, uint32_t& lb) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    float x[4], y[4], z[4];
+    int j[4], sgv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) lds_rec(addr + (uint32_t)u * 32u * RS, x[u], y[u], z[u], j[u]);
+    f32x2_t d2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        sgv[u] = sm.chunk_seg[ck + u];
+        d2[u] = rows_d2<FMA, true>(x[u], y[u], z[u], XI, YI, ZI, sm.segS[3 * sgv[u]], sm.segS[3 * sgv[u] + 1],
+                                   sm.segS[3 * sgv[u] + 2]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        bool lexpos = false;
+        if (HALF) {
+            int csx, csy, csz;
+            unpack_key(sm.seg_key[sgv[u]], csx, csy, csz);
+            lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
+        }
+        rows_append<HALF, false, !HALF>(d2[u], c + 32 * u, (ck + u) | (sgv[u] << 5), j[u], iA, iB, rc2, lexpos, true, selfA,
+                                        selfB, la, lb);
+    }
+}
+
 // Sweep of two targets over the staged tile.  la / lb: per-lane append pointers.
 //   interior cell (one zero-shift segment): groups of four chunks, the last group masked;
 //   cell at a periodic boundary: full zero-shift chunks in groups of four, then every other chunk with its shift vector
 //   picked per lane (a chunk may straddle segments).
 // Only the group(s) holding the targets themselves pay for the self-exclusion test.
-template <bool HALF, bool FMA>
+template <bool HALF, bool FMA, bool UNI>
 __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t cand_addr, f32x2_t XI, f32x2_t YI,
                                             f32x2_t ZI, int iA, int iB, float rc2, int lane, int selfA, int selfB,
                                             uint32_t& la, uint32_t& lb) {
@@ -201,8 +232,16 @@ __device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t
         addr += 32 * RS;
         c += 32;
     }
+    const unsigned um = UNI ? (unsigned)sm.qrow[0] : 0u;  // chunks lying entirely inside one segment (producer)
 #pragma unroll 1
     for (; ck < nchunks; ++ck) {
+        if (UNI && ck + 4 <= nchunks && ((um >> ck) & 15u) == 15u) {
+            rows_chunk2x4_shift<HALF, FMA>(sm, addr, c, ck, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
+            addr += 128 * RS;
+            c += 128;
+            ck += 3;
+            continue;
+        }
         int sg = sm.chunk_seg[ck];
         while (sg + 1 < nseg && c >= sm.seg_begin[sg + 1]) ++sg;
         bool lexpos = false;
@@ -327,8 +366,9 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
 // ------------------------------------------------------------------------------------------------
 // STAGES / MINB: ring depth and CTAs per SM.  <3, 3> (72 KB, <= 72 registers) is the measured default; <2, 4> (54 KB,
 // 56 registers, no spills) trades ring depth for 36 instead of 27 resident warps — compiled, selectable with
-// NVNL_ROWS_CONFIG=1, not yet measured.  PAD (NVNL_ROWS_CONFIG=2, or 3 with both): 128-byte aligned, padded temporary rows.
-template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD>
+// NVNL_ROWS_CONFIG bit 0, not yet measured.  PAD (bit 1): 128-byte aligned, padded temporary rows.  UNI (bit 2): chunks
+// of boundary cells that lie inside one image segment are swept in groups of four with a warp-uniform shift vector.
+template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD, bool UNI>
 __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -534,10 +574,19 @@ __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
             }
             __syncwarp();
             const int nchunks = (total + 31) >> 5;
+            bool uni_chunk = false;
             if (lane < nchunks) {
                 int sgi = 0;
                 while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
                 sg.chunk_seg[lane] = sgi;
+                if (UNI) {
+                    const int last = (lane << 5) + 31;
+                    uni_chunk = last < total && (sgi + 1 >= nseg || last < sg.seg_begin[sgi + 1]);
+                }
+            }
+            if (UNI) {
+                const unsigned umask = __ballot_sync(0xffffffffu, uni_chunk);
+                if (lane == 0) sg.qrow[0] = (int)umask;  // (qrow is unused on this path)
             }
             if (lane == 0) {
                 sg.nchunks = nchunks;
@@ -596,7 +645,7 @@ __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
                 const f32x2_t nz = pack2(-0.0f, -0.0f);
                 const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
                 uint32_t la = lbaseA, lb = lbaseB;
-                rows_sweep2<HALF, FMA>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, selfA, selfB, la, lb);
+                rows_sweep2<HALF, FMA, UNI>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, selfA, selfB, la, lb);
                 rows_emit2<HALF, PAD>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
                                  rows, row_ref);
             }
