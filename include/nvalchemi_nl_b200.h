@@ -103,6 +103,17 @@ int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_system
                    double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
                    int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
 
+/* EXPERIMENTAL (compiled, not yet measured on hardware; nvalchemiops_b200.config.speculative_fill, off by default):
+ * the output kernel of the single-sweep path launched BEFORE the size sync, into buffers sized from a guess
+ * (edge_buffer: 2 * capacity_pairs int32, shifts_zeroed: 3 * capacity_pairs int32, already zero — e.g. the prezero
+ * buffer of nvnl_count_rows).  The kernel reads the pair count P on the device: if P <= capacity_pairs (and the query was
+ * not served by the two-pass kernels) it writes edge_index as the [2,P] prefix of edge_buffer and the image shifts, else
+ * nothing.  The caller then reads nvnl_status and either takes the prefixes (running nvnl_fill_rows with launch_hint
+ * bits 2|3 = 12 set if had_deferred, which then only launches the general kernel) or repeats the fill the regular way. */
+int nvnl_fill_rows_speculative(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* neighbor_ptr,
+                               int32_t* edge_buffer, int64_t capacity_pairs, int32_t* shifts_zeroed, int32_t index_offset,
+                               void* stream);
+
 /* query_cell_list / batch_query_cell_list (cell_list.py:892-1034, batch_cell_list.py:915-1067)
  * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of
  * neighbor_matrix [n_atoms,max_neighbors], neighbor_matrix_shifts [n_atoms,max_neighbors,3] and

@@ -317,9 +317,11 @@ int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, do
         NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_pair<float, MODE_FILL_COO, HALF, FMA>(a, hint, st);
     }
-    k_rows_out<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts,
-                                                           index_offset, (hint & 4) ? 1 : 0);
-    NVNL_CHECK_LAUNCH("k_rows_out");
+    if (!(hint & 8)) {  // bit 3: nvnl_fill_rows_speculative already wrote the rows of the lean kernel
+        k_rows_out<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts,
+                                                                      index_offset, (hint & 4) ? 1 : 0, 0);
+        NVNL_CHECK_LAUNCH("k_rows_out");
+    }
     if (hint & 2) {
         a.queue = 3;  // the deferred list of the count stage was kept for this launch
         return launch_sweep_t<float, MODE_FILL_COO, HALF, FMA>(a, st);
@@ -501,6 +503,22 @@ int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_system
                                           shifts, index_offset, launch_hint, st)
                : fill_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
                                            shifts, index_offset, launch_hint, st);
+}
+
+int nvnl_fill_rows_speculative(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* neighbor_ptr,
+                               int32_t* edge_buffer, int64_t capacity_pairs, int32_t* shifts_zeroed, int32_t index_offset,
+                               void* stream) {
+    if (!workspace || !neighbor_ptr || !edge_buffer || !shifts_zeroed || n_atoms <= 0)
+        return fail(-1, "nvnl_fill_rows_speculative: bad arguments");
+    if (dtype != NVNL_F32) return fail(-1, "nvnl_fill_rows_speculative: the single-sweep path is fp32 only");
+    if (capacity_pairs <= 0 || capacity_pairs > 2147483647LL) return fail(-1, "nvnl_fill_rows_speculative: capacity outside int32 range");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
+    k_rows_out<true><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, L, n_atoms, neighbor_ptr, edge_buffer, nullptr,
+                                                                       shifts_zeroed, index_offset, 1, capacity_pairs);
+    NVNL_CHECK_LAUNCH("k_rows_out<speculative>");
+    return 0;
 }
 
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,

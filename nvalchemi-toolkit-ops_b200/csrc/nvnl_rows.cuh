@@ -674,10 +674,21 @@ __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int valu
     if (lane < tail) dst[head + 4 * nv + lane] = value;
 }
 
+// SPEC (experiment): launched BEFORE the host knows the pair count, into buffers sized from a guess — the kernel reads
+// the count itself, places row 1 of edge_index behind it, and does nothing if the guess was too small or the query was
+// served by the two-pass kernels (the host then repeats the fill the regular way).
+template <bool SPEC>
 __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
                                                      const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
-                                                     int* __restrict__ out_j, int* __restrict__ out_shifts, int index_offset,
-                                                     int shifts_zeroed) {
+                                                     int* __restrict__ out_j_arg, int* __restrict__ out_shifts,
+                                                     int index_offset, int shifts_zeroed, long long spec_cap) {
+    int* __restrict__ out_j = out_j_arg;
+    if (SPEC) {
+        const Ctrl* ctrl = reinterpret_cast<const Ctrl*>(ws + L.ctrl);
+        const unsigned long long total = ctrl->total_pairs;
+        if (ctrl->unwrapped != 0 || ctrl->rows_overflow != 0 || total > (unsigned long long)spec_cap) return;
+        out_j = out_i + total;
+    }
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
     const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
     const int lane = threadIdx.x & 31;

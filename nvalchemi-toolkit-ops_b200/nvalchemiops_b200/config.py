@@ -19,3 +19,8 @@ coo_path: str = "rows"
 # size sync (inside the output kernel).
 prezero_shifts: bool = True
 prezero_min_pairs: int = 1_000_000   # below this the extra launch + event cost more than the overlap saves
+
+# EXPERIMENTAL, off: with a speculative shifts buffer in hand, also launch the output kernel BEFORE the size sync, into an
+# edge_index buffer of the guessed size (nvnl_fill_rows_speculative); the host then only creates the views.  Removes the
+# ~25 us the GPU idles at the sync.  Compiled and covered by host-logic tests, not yet measured on hardware.
+speculative_fill: bool = False

@@ -219,7 +219,10 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
     key = (torch.device(h.device).index or 0, h.n, h.ns, float(cutoff_sq), bool(half_fill))
     zbuf = _guess_shifts_buffer(h, key) if use_rows(h) else None
-    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill, prezero=zbuf)
+    ebuf = None
+    if zbuf is not None and config.speculative_fill:
+        ebuf = torch.empty(2 * (zbuf.numel() // 3), dtype=torch.int32, device=h.device)
+    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill, prezero=zbuf, spec_edge=ebuf)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
@@ -228,7 +231,15 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     if len(_pair_history) > 256:
         _pair_history.clear()
     _pair_history[key] = (total, hint)
-    if rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel() and not (hint & 1):
+    fits = rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel() and not (hint & 1)
+    if fits and ebuf is not None:
+        # the output kernel already ran (before the sync) into the speculative buffers: the outputs are their prefixes
+        edge_index = ebuf[: 2 * total].view(2, total)
+        shifts = zbuf[: 3 * total].view(total, 3)
+        if total > 0 and (hint & 2):   # only the rows of the general kernel are still missing
+            fill_coo(h, cutoff_sq, ptr, edge_index, shifts, total, half_fill, launch_hint=hint | 4 | 8, rows=True)
+        return edge_index, ptr, shifts, num
+    if fits:
         # the speculative buffer fits: shifts is its (contiguous) prefix, already zero when the fill starts
         edge_index = torch.empty((2, total), dtype=torch.int32, device=h.device)
         shifts = zbuf[: 3 * total].view(total, 3)
@@ -243,12 +254,26 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     return edge_index, ptr, shifts, num
 
 
-def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None):
+def fill_rows_speculative(h: CellListHandle, neighbor_ptr, edge_buffer, shifts_zeroed, index_offset=0):
+    """EXPERIMENTAL: launch the single-sweep path's output kernel before the pair count is known on the host
+    (nvnl_fill_rows_speculative); ``edge_buffer`` holds 2 * cap and ``shifts_zeroed`` 3 * cap int32."""
+    L = _lib.lib()
+    with torch.cuda.device(h.device):
+        _lib.check(
+            L.nvnl_fill_rows_speculative(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(neighbor_ptr), _ptr(edge_buffer),
+                                         edge_buffer.numel() // 2, _ptr(shifts_zeroed), int(index_offset), _stream(h.device)),
+            "nvnl_fill_rows_speculative",
+        )
+
+
+def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, spec_edge=None):
     """Count stage + the one host sync: ``(num, ptr, total, max_count, error_bits, launch_hint, rows)``.  ``rows``
     tells ``fill_coo`` which path the count ran on (single sweep unless fp64 / configured off / its temporary row
     buffer overflowed, in which case the count is repeated on the two-pass path)."""
     rows = use_rows(h)
     num, ptr = count(h, cutoff_sq, half_fill, rows=rows, prezero=prezero if rows else None)
+    if rows and prezero is not None and spec_edge is not None:
+        fill_rows_speculative(h, ptr, spec_edge, prezero)      # runs while the host waits for the size
     total, max_count, _cells, err, hint = status(h)
     if rows and h.rows_overflow:
         rows = False

@@ -768,3 +768,37 @@ def test_rows_path_prezeroed_shifts_on_repeated_queries():
     finally:
         config.prezero_shifts = True
         config.prezero_min_pairs = old_min
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("NVNL_EXPERIMENTAL"),
+                    reason="experimental path (config.speculative_fill), not yet validated on hardware: set NVNL_EXPERIMENTAL=1")
+def test_experimental_speculative_fill_matches_the_regular_path():
+    """The output kernel launched before the size sync (nvnl_fill_rows_speculative) must give the same COO outputs:
+    interior/boundary cells, a batch with cells left to the general kernel, a guess that is too small, unwrapped input."""
+    from nvalchemiops_b200 import config
+    from nvalchemiops_b200.neighborlist import _engine
+
+    old_min, old_spec = config.prezero_min_pairs, config.speculative_fill
+    config.prezero_min_pairs, config.speculative_fill = 1, True
+    _engine._pair_history.clear()
+    try:
+        n = 6000
+        base, cell, pbc = random_system(n, 40.0, torch.float32, seed=51)
+        dense = base.clone()
+        dense[: n // 2] = dense[: n // 2] * 0.25 + 15.0
+        unw = base + 40.0 * (torch.arange(n) % 3 - 1).float()[:, None]
+        for k, pos in enumerate([base, base, base, dense, dense, base, unw, unw, base, base]):
+            o = ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=4096, nthreads=8)
+            want = ro.records_from_matrix(*o)
+            e, p, s = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), max_neighbors=4096, return_neighbor_list=True)
+            assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), k
+            assert e.is_contiguous() and s.is_contiguous() and e.shape == (2, want.shape[0])
+            assert np.array_equal(o[1], (p[1:] - p[:-1]).cpu().numpy())
+        bp, bc, bb, bi, bptr = bench_batch(24, 150, 900, seed=13)
+        want = ro.records_from_matrix(*ro.batch_cell_list(bp, 6.0, bc, bb, bi, max_neighbors=1024))
+        for _ in range(3):
+            e, p, s = _nl().batch_cell_list(bp.to(DEV), 6.0, bc.to(DEV), bb.to(DEV), bi.to(DEV), return_neighbor_list=True)
+            assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    finally:
+        config.prezero_min_pairs, config.speculative_fill = old_min, old_spec
+        _engine._pair_history.clear()

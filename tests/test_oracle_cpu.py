@@ -274,4 +274,22 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     calls.clear(); state.update(total=10_000, overflow_once=False)
     _engine.query_coo(h, 4.0); _engine.query_coo(h, 4.0)
     assert calls[2] == ("count", True, None)
+    # experimental: output kernel launched before the size sync into buffers of the guessed size
+    monkeypatch.setattr(config, "speculative_fill", True)
+    monkeypatch.setattr(_engine, "fill_rows_speculative",
+                        lambda h, ptr, ebuf, zbuf, index_offset=0: calls.append(("spec", ebuf.numel(), zbuf.numel())))
+    _engine._pair_history.clear()
+    state.update(total=5_000_000, hint=0)
+    _engine.query_coo(h, 36.0)                      # no history yet: regular path
+    calls.clear()
+    e, p, s, num = _engine.query_coo(h, 36.0)       # guess fits: no fill launch after the sync at all
+    cap = int(5_000_000 * 1.02) + 1024
+    assert calls == [("count", True, 3 * cap), ("spec", 2 * cap, 3 * cap)]
+    assert e.shape == (2, 5_000_000) and e.is_contiguous() and s.shape == (5_000_000, 3) and s.is_contiguous()
+    calls.clear(); state["hint"] = 2                # cells left to the general kernel: only that launch remains (bits 2|3)
+    _engine.query_coo(h, 36.0)
+    assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 2 | 4 | 8)
+    calls.clear(); state.update(total=6_000_000, hint=0)   # guess too small: the regular fill, nothing pre-zeroed
+    _engine.query_coo(h, 36.0)
+    assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 0) and calls[2][3] == (2, 6_000_000)
     _engine._pair_history.clear()
