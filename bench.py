@@ -7,7 +7,9 @@
 Metric (BASELINE.json): directed neighbor pairs/s (and atoms/s) of the cell-list build for a single periodic box
 of 1,000,000 atoms, density 0.1 /A^3, r_cut = 6 A, COO output (config 4).  A "step" is one complete
 ``neighbor_list(positions, 6.0, cell, pbc, return_neighbor_list=True)`` call through the public API: grid + hash +
-counting sort + count sweep + scan + (the one size sync) + output allocation + fill sweep.
+counting sort + the stencil sweep (k_rows: every distance once, compact temporary rows) + scan + (the one size sync) +
+output allocation + the output kernel (k_rows_out: edge_index / shifts in atom order).  ``--coo-path masks`` times the
+older two-pass path (count sweep -> hit masks -> fill sweep).
 
 * N = 1: config 4.  N > 1 (torchrun): the single box does not shard ("replicas only"), so
   every rank runs its own config-4 replica (weak scaling, no data-path collective); the line also carries a
