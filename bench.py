@@ -46,6 +46,23 @@ METRIC = "neighbor_pairs_per_s (cell_list build, 1M atoms, r_cut=6A, COO)"
 
 
 # ------------------------------------------------------------------------------------------------
+def _ensure_library():
+    """The CUDA library is built in-tree (git-ignored, shipped with the snapshot): build it if it is missing."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("nvnl_build_script", os.path.join(ROOT, "nvalchemi-toolkit-ops_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not os.path.exists(mod.LIB):
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            mod.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(mod.LIB):
+                    break
+                time.sleep(0.5)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -228,6 +245,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
+    _ensure_library()
     from nvalchemiops_b200 import config as nl_config, launch_count
     from nvalchemiops_b200.neighborlist import _engine, neighbor_list
 
