@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NVNL_ABI_VERSION 2
+#define NVNL_ABI_VERSION 3
 #define NVNL_F32 0
 #define NVNL_F64 1
 
@@ -35,6 +35,7 @@ extern "C" {
 #define NVNL_ERR_IMAGE_RANGE 1   /* atom more than 1e6 periodic images away, or search radius >= 64 cells */
 #define NVNL_ERR_BAD_BATCH_IDX 2 /* batch_idx outside [0, num_systems) */
 #define NVNL_ERR_SINGULAR_CELL 4 /* cell matrix not invertible */
+#define NVNL_ERR_BAD_CACHE 8     /* nvnl_import_cache: cache tensors inconsistent (not produced by a build of this library) */
 
 int nvnl_abi_version(void);
 const char* nvnl_last_error(void);
@@ -48,9 +49,13 @@ size_t nvnl_workspace_bytes(int64_t n_atoms, int64_t n_systems, int dtype);
 /* build_cell_list / batch_build_cell_list (cell_list.py:725-889, batch_cell_list.py:739-912):
  * grid selection, atom->cell hash, counting sort of positions into per-cell float4 runs.
  *   positions [n_atoms,3], cell [n_systems,3,3] (rows = lattice vectors), pbc [n_systems,3] (bytes),
- *   batch_idx [n_atoms] int32 or NULL (single system), batch_ptr [n_systems+1] int32 or NULL. */
+ *   batch_idx [n_atoms] int32 or NULL (single system), batch_ptr [n_systems+1] int32 or NULL.
+ *   max_cells: 0 = grid bounded only by #cells <= #atoms per system; > 0 = total cell capacity of the caller's
+ *   reference-shaped cache (the length of atoms_per_cell_count from estimate_cell_list_sizes / allocate_cell_list,
+ *   cell_list.py:639-722): every system's grid is halved until it has at most max_cells / n_systems cells, exactly
+ *   the contract of _cell_list_construct_bin_size (cell_list.py:131-150, batch_cell_list.py:162-176). */
 int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
-               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff,
+               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff, int64_t max_cells,
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* First half of the COO path: per-atom neighbor counts and their exclusive scan.
@@ -140,6 +145,18 @@ int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_sys
                       int32_t* atom_to_cell_mapping, int32_t* atoms_per_cell_count, int32_t* cell_atom_start_indices,
                       int64_t cache_cells, int32_t* cell_atom_list, void* stream);
 
+/* query_cell_list / batch_query_cell_list from the cache VALUES (cell_list.py:892-1034, batch_cell_list.py:915-1067):
+ * rebuilds the workspace from the seven reference-shaped cache tensors nvnl_export_cache wrote (possibly cloned, moved
+ * or reloaded since) and the CURRENT positions — the stale-cache MD query needs no hidden state.  `cutoff` is the
+ * query cutoff (<= the build cutoff); the stencil radius used is max(cached radius, what `cutoff` needs on the cached
+ * grid).  Inconsistent tensors set NVNL_ERR_BAD_CACHE (nvnl_status). */
+int nvnl_import_cache(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+                      const int32_t* batch_idx, int32_t n_systems, double cutoff, const int32_t* cells_per_dimension,
+                      const int32_t* neighbor_search_radius, const int32_t* atom_periodic_shifts,
+                      const int32_t* atom_to_cell_mapping, const int32_t* atoms_per_cell_count,
+                      const int32_t* cell_atom_start_indices, int64_t cache_cells, const int32_t* cell_atom_list,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* query_cell_list with moved atoms (cell_list.py:1108-1192): re-gathers `positions` into the cell-sorted records
  * without re-binning, so the next nvnl_count / nvnl_fill_* evaluates distances with the current coordinates against
  * the cell assignment of the last nvnl_build (valid while no atom moved more than (cell width - cutoff)/2). */
@@ -150,6 +167,13 @@ int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t 
  * the grid of the last nvnl_build differs from its stored cell, else 0. */
 int nvnl_cells_changed(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
                        const int32_t* batch_idx, int32_t* flag, void* stream);
+
+/* cell_list_needs_rebuild from the cache VALUES (same reference lines; no workspace): re-hashes `positions` on the grid
+ * (cell, pbc, cells_per_dimension) of a capped build (nvnl_build with max_cells > 0) and compares with
+ * atom_to_cell_mapping [n_atoms,3].  cells_per_dimension [n_systems,3]. */
+int nvnl_cells_changed_cache(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+                             const int32_t* batch_idx, int32_t n_systems, const int32_t* cells_per_dimension,
+                             const int32_t* atom_to_cell_mapping, int32_t* flag, void* stream);
 
 /* neighbor_list_needs_rebuild (rebuild_detection.py:168-217, 386-503): *flag = 1 if any atom moved farther than
  * `threshold` from its reference position.  No workspace involved. */

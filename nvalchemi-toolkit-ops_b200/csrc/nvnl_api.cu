@@ -105,12 +105,12 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
-template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD, bool UNI>
-int launch_rows_cfg(const RowsArgs& a, cudaStream_t st) {
-    auto kern = k_rows<HALF, FMA, STAGES, MINB, PAD, UNI>;
-    constexpr size_t smem = rows_smem_bytes<STAGES>();
-    static int bps[kMaxDevices] = {0};
-    int& blocks_per_sm = bps[current_device()];
+template <bool HALF, bool FMA>
+int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
+    auto kern = k_rows<HALF, FMA>;
+    constexpr size_t smem = rows_smem_bytes();
+    static std::atomic<int> bps[kMaxDevices];
+    int blocks_per_sm = bps[current_device()].load(std::memory_order_relaxed);
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_rows)", e);
@@ -118,6 +118,7 @@ int launch_rows_cfg(const RowsArgs& a, cudaStream_t st) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kRowsThreads, smem);
         if (e != cudaSuccess) return fail(-2, "occupancy(k_rows)", e);
         blocks_per_sm = b > 0 ? b : 1;
+        bps[current_device()].store(blocks_per_sm, std::memory_order_relaxed);
     }
     long long grid = (long long)sm_count() * blocks_per_sm;
     const long long max_items = a.L.max_cells;
@@ -127,31 +128,36 @@ int launch_rows_cfg(const RowsArgs& a, cudaStream_t st) {
     return 0;
 }
 
-template <bool HALF, bool FMA>
-int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
-    // experiment switch (read once): 0 = 3-stage ring, 3 CTAs/SM, compact rows, per-lane shifts (the measured default);
-    // bit 0 = 2-stage ring, 4 CTAs/SM; bit 1 = 128-byte aligned, padded temporary rows; bit 2 = grouped uniform-shift chunks
-    static const int cfg = [] { const char* e = getenv("NVNL_ROWS_CONFIG"); return e ? atoi(e) : 0; }();
-    switch (cfg & 7) {
-        case 1: return launch_rows_cfg<HALF, FMA, 2, 4, false, false>(a, st);
-        case 2: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, true, false>(a, st);
-        case 3: return launch_rows_cfg<HALF, FMA, 2, 4, true, false>(a, st);
-        case 4: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, false, true>(a, st);
-        case 5: return launch_rows_cfg<HALF, FMA, 2, 4, false, true>(a, st);
-        case 6: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, true, true>(a, st);
-        case 7: return launch_rows_cfg<HALF, FMA, 2, 4, true, true>(a, st);
-        default: return launch_rows_cfg<HALF, FMA, kRowsStages, 3, false, false>(a, st);
+template <bool SPEC>
+int launch_rows_out(const unsigned char* ws, const WsLayout& L, long long n, const int* neighbor_ptr, int* out_i, int* out_j,
+                    int* out_shifts, int index_offset, int shifts_zeroed, long long spec_cap, cudaStream_t st) {
+    auto kern = k_rows_out<SPEC>;
+    constexpr size_t smem = sizeof(RowsOutSmem);
+    static std::atomic<int> bps[kMaxDevices];
+    int blocks_per_sm = bps[current_device()].load(std::memory_order_relaxed);
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(-2, "cudaFuncSetAttribute(k_rows_out)", e);
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kOutWarps * 32, smem);
+        if (e != cudaSuccess) return fail(-2, "occupancy(k_rows_out)", e);
+        blocks_per_sm = b > 0 ? b : 1;
+        bps[current_device()].store(blocks_per_sm, std::memory_order_relaxed);
     }
+    long long grid = (n + kOutWarps * 32 - 1) / (kOutWarps * 32);
+    const long long cap = (long long)sm_count() * blocks_per_sm * 4;   // a few waves: the tail is short
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kOutWarps * 32, smem, st>>>(ws, L, n, neighbor_ptr, out_i, out_j, out_shifts, index_offset,
+                                                      shifts_zeroed, spec_cap);
+    NVNL_CHECK_LAUNCH("k_rows_out");
+    return 0;
 }
 
 // Start of every query: empty deferred list, empty temporary row buffer (and, for the single-sweep COO path,
 // row_ref = -1 for every atom).
 int launch_query_reset(unsigned char* ws, const WsLayout& L, long long n, int with_rows, cudaStream_t st) {
-    long long blocks = with_rows ? (n + 255) / 256 : 1;
-    const long long cap = (long long)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    k_query_reset<<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, with_rows);
+    k_query_reset<<<1, 32, 0, st>>>(ws, L, n, with_rows);
     NVNL_CHECK_LAUNCH("k_query_reset");
     return 0;
 }
@@ -184,7 +190,7 @@ int launch_sweep(const SweepArgs<T>& a, int half_fill, int fma, cudaStream_t st,
 
 template <typename T>
 int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const int* batch_idx, const int* batch_ptr,
-            int ns, double cutoff, unsigned char* ws, cudaStream_t st) {
+            int ns, double cutoff, long long max_cells, unsigned char* ws, cudaStream_t st) {
     const WsLayout L = mk_layout(n, ns, (int)sizeof(Rec<T>));
     const int sms = sm_count();
     {
@@ -203,7 +209,7 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         k_bbox<T><<<(unsigned)blocks, kSmallBlock, 0, st>>>(ws, L, n, ns, pos, batch_idx, need_counts);
         NVNL_CHECK_LAUNCH("k_bbox");
     }
-    k_grid<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff);
+    k_grid<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff, max_cells > 0 ? (max_cells / ns > 0 ? max_cells / ns : 1) : 0);
     NVNL_CHECK_LAUNCH("k_grid");
     const bool vec = (reinterpret_cast<uintptr_t>(pos) % 16) == 0;
     {
@@ -233,6 +239,34 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         else
             k_scatter<T, false><<<blocks, 256, 0, st>>>(ws, L, n, pos);
         NVNL_CHECK_LAUNCH("k_scatter");
+    }
+    return 0;
+}
+
+template <typename T>
+int import_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const int* batch_idx, int ns, double cutoff,
+             const int* cpd, const int* radius, const int* atom_shifts, const int* atom_cell_map, const int* cell_count,
+             const int* cell_start, long long cache_cells, const int* cell_atom_list, unsigned char* ws, cudaStream_t st) {
+    const WsLayout L = mk_layout(n, ns, (int)sizeof(Rec<T>));
+    const int sms = sm_count();
+    {
+        long long work = L.max_cells + 2 > n ? L.max_cells + 2 : n;
+        long long blocks = (work + 255) / 256;
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+        if (blocks < 1) blocks = 1;
+        k_init<T><<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, ns, cell, pbc, nullptr, nullptr);
+        NVNL_CHECK_LAUNCH("k_init");
+    }
+    k_import_sys<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff, cpd, radius, cache_cells);
+    NVNL_CHECK_LAUNCH("k_import_sys");
+    {
+        long long work = n > cache_cells ? n : cache_cells;
+        long long blocks = (work + 255) / 256;
+        if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+        if (blocks < 1) blocks = 1;
+        k_import_atoms<T><<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, ns, pos, batch_idx, atom_shifts, atom_cell_map, cell_count,
+                                                            cell_start, cell_atom_list);
+        NVNL_CHECK_LAUNCH("k_import_atoms");
     }
     return 0;
 }
@@ -318,9 +352,9 @@ int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, do
         return launch_pair<float, MODE_FILL_COO, HALF, FMA>(a, hint, st);
     }
     if (!(hint & 8)) {  // bit 3: nvnl_fill_rows_speculative already wrote the rows of the lean kernel
-        k_rows_out<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts,
-                                                                      index_offset, (hint & 4) ? 1 : 0, 0);
-        NVNL_CHECK_LAUNCH("k_rows_out");
+        const int rc = launch_rows_out<false>(ws, a.L, n, neighbor_ptr, a.out_i, a.out_j, a.out_shifts, index_offset,
+                                              (hint & 4) ? 1 : 0, 0, st);
+        if (rc) return rc;
     }
     if (hint & 2) {
         a.queue = 3;  // the deferred list of the count stage was kept for this launch
@@ -382,11 +416,12 @@ size_t nvnl_workspace_bytes(int64_t n_atoms, int64_t n_systems, int dtype) {
 }
 
 int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
-               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff, void* workspace,
-               size_t workspace_bytes, void* stream) {
+               const int32_t* batch_idx, const int32_t* batch_ptr, int32_t n_systems, double cutoff, int64_t max_cells,
+               void* workspace, size_t workspace_bytes, void* stream) {
     if (n_atoms <= 0 || n_systems <= 0) return fail(-1, "nvnl_build: n_atoms and n_systems must be positive");
     if (n_atoms > 2000000000LL) return fail(-1, "nvnl_build: n_atoms exceeds the int32 index range");
     if (!(cutoff > 0.0)) return fail(-1, "nvnl_build: cutoff must be positive");
+    if (max_cells < 0 || (max_cells > 0 && max_cells < n_systems)) return fail(-1, "nvnl_build: max_cells must be 0 (no cap) or at least n_systems");
     if (!positions || !cell || !pbc || !workspace) return fail(-1, "nvnl_build: null pointer");
     if (n_systems > 1 && !batch_idx) return fail(-1, "nvnl_build: batch_idx is required for n_systems > 1");
     if (dtype != NVNL_F32 && dtype != NVNL_F64) return fail(-1, "nvnl_build: unsupported dtype");
@@ -397,9 +432,9 @@ int nvnl_build(const void* positions, int dtype, int64_t n_atoms, const void* ce
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (dtype == NVNL_F32)
         return build_t<float>(static_cast<const float*>(positions), n_atoms, static_cast<const float*>(cell), pbc,
-                              batch_idx, batch_ptr, n_systems, cutoff, ws, st);
+                              batch_idx, batch_ptr, n_systems, cutoff, max_cells, ws, st);
     return build_t<double>(static_cast<const double*>(positions), n_atoms, static_cast<const double*>(cell), pbc,
-                           batch_idx, batch_ptr, n_systems, cutoff, ws, st);
+                           batch_idx, batch_ptr, n_systems, cutoff, max_cells, ws, st);
 }
 
 int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
@@ -471,7 +506,7 @@ int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_syste
                     int32_t* prezero, int64_t prezero_ints, void* stream) {
     if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count_rows: bad arguments");
     if (dtype != NVNL_F32) return fail(-1, "nvnl_count_rows: the single-sweep path is fp32 only (use nvnl_count)");
-    if (n_atoms >= (1LL << 28)) return fail(-1, "nvnl_count_rows: the single-sweep path takes fewer than 2^28 atoms (use nvnl_count)");
+    if (n_atoms >= (1LL << 27)) return fail(-1, "nvnl_count_rows: the single-sweep path takes fewer than 2^27 atoms (use nvnl_count)");
     if (prezero_ints < 0 || (prezero_ints > 0 && (!prezero || reinterpret_cast<uintptr_t>(prezero) % 16)))
         return fail(-1, "nvnl_count_rows: prezero must be a 16-byte aligned device pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -515,10 +550,8 @@ int nvnl_fill_rows_speculative(void* workspace, int dtype, int64_t n_atoms, int3
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
-    k_rows_out<true><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, L, n_atoms, neighbor_ptr, edge_buffer, nullptr,
-                                                                       shifts_zeroed, index_offset, 1, capacity_pairs);
-    NVNL_CHECK_LAUNCH("k_rows_out<speculative>");
-    return 0;
+    return launch_rows_out<true>(ws, L, n_atoms, neighbor_ptr, edge_buffer, nullptr, shifts_zeroed, index_offset, 1,
+                                 capacity_pairs, st);
 }
 
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
@@ -585,6 +618,33 @@ int nvnl_export_cache(void* workspace, int dtype, int64_t n_atoms, int32_t n_sys
     return 0;
 }
 
+int nvnl_import_cache(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+                      const int32_t* batch_idx, int32_t n_systems, double cutoff, const int32_t* cells_per_dimension,
+                      const int32_t* neighbor_search_radius, const int32_t* atom_periodic_shifts,
+                      const int32_t* atom_to_cell_mapping, const int32_t* atoms_per_cell_count,
+                      const int32_t* cell_atom_start_indices, int64_t cache_cells, const int32_t* cell_atom_list,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_atoms <= 0 || n_systems <= 0) return fail(-1, "nvnl_import_cache: n_atoms and n_systems must be positive");
+    if (!(cutoff > 0.0)) return fail(-1, "nvnl_import_cache: cutoff must be positive");
+    if (!positions || !cell || !pbc || !workspace || !cells_per_dimension || !atom_periodic_shifts || !atom_to_cell_mapping ||
+        !atoms_per_cell_count || !cell_atom_start_indices || !cell_atom_list)
+        return fail(-1, "nvnl_import_cache: null pointer");
+    if (n_systems > 1 && !batch_idx) return fail(-1, "nvnl_import_cache: batch_idx is required for n_systems > 1");
+    if (cache_cells < n_systems) return fail(-1, "nvnl_import_cache: the cache holds fewer cells than systems");
+    if (dtype != NVNL_F32 && dtype != NVNL_F64) return fail(-1, "nvnl_import_cache: unsupported dtype");
+    if (workspace_bytes < nvnl_workspace_bytes(n_atoms, n_systems, dtype)) return fail(-1, "nvnl_import_cache: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(-1, "nvnl_import_cache: workspace must be 256-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (dtype == NVNL_F32)
+        return import_t<float>(static_cast<const float*>(positions), n_atoms, static_cast<const float*>(cell), pbc, batch_idx,
+                               n_systems, cutoff, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts,
+                               atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices, cache_cells, cell_atom_list, ws, st);
+    return import_t<double>(static_cast<const double*>(positions), n_atoms, static_cast<const double*>(cell), pbc, batch_idx,
+                            n_systems, cutoff, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts,
+                            atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices, cache_cells, cell_atom_list, ws, st);
+}
+
 int nvnl_refresh_positions(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const void* positions,
                            void* stream) {
     if (!workspace || !positions || n_atoms <= 0) return fail(-1, "nvnl_refresh_positions: bad arguments");
@@ -618,6 +678,30 @@ int nvnl_cells_changed(void* workspace, int dtype, int64_t n_atoms, int32_t n_sy
     else
         return fail(-1, "nvnl_cells_changed: unsupported dtype");
     NVNL_CHECK_LAUNCH("k_cells_changed");
+    return 0;
+}
+
+int nvnl_cells_changed_cache(const void* positions, int dtype, int64_t n_atoms, const void* cell, const uint8_t* pbc,
+                             const int32_t* batch_idx, int32_t n_systems, const int32_t* cells_per_dimension,
+                             const int32_t* atom_to_cell_mapping, int32_t* flag, void* stream) {
+    if (!positions || !cell || !pbc || !cells_per_dimension || !atom_to_cell_mapping || !flag || n_atoms <= 0 || n_systems <= 0)
+        return fail(-1, "nvnl_cells_changed_cache: bad arguments");
+    if (n_systems > 1 && !batch_idx) return fail(-1, "nvnl_cells_changed_cache: batch_idx is required for n_systems > 1");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_cells_changed_cache: memset", e);
+    const unsigned blocks = (unsigned)((n_atoms + 255) / 256);
+    if (dtype == NVNL_F32)
+        k_cells_changed_cache<float><<<blocks, 256, 0, st>>>(n_atoms, n_systems, static_cast<const float*>(positions),
+                                                            static_cast<const float*>(cell), pbc, batch_idx, cells_per_dimension,
+                                                            atom_to_cell_mapping, flag);
+    else if (dtype == NVNL_F64)
+        k_cells_changed_cache<double><<<blocks, 256, 0, st>>>(n_atoms, n_systems, static_cast<const double*>(positions),
+                                                             static_cast<const double*>(cell), pbc, batch_idx, cells_per_dimension,
+                                                             atom_to_cell_mapping, flag);
+    else
+        return fail(-1, "nvnl_cells_changed_cache: unsupported dtype");
+    NVNL_CHECK_LAUNCH("k_cells_changed_cache");
     return 0;
 }
 

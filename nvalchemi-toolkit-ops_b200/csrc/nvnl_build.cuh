@@ -53,13 +53,13 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     // (cell, first target) work items the fast kernel leaves to the general kernel: <= #cells + N/32 entries
     L.deferred = take(sizeof(int2) * (size_t)(L.max_cells + 2 + n / 32 + 1));
     L.ptr_sorted = take(sizeof(int) * (size_t)(n + 4));     // neighbor_ptr gathered into cell-sorted atom order
-    // single-sweep COO path: row_ref[i] = (first entry << 1) | has-shift-keys, or -1; rows = compact rows in sweep
+    // single-sweep COO path: row_ref[i] = (first entry << 2) | header kind, or -1; rows = compact rows in sweep
     // order.  Budget: kRowsPerAtom entries per atom + one reservation block per resident warp; more pairs than that
     // (very large cutoffs) make the query fall back to the two-pass path.
     L.row_ref = take(sizeof(int) * (size_t)n);
     L.rows_cap = rows_per_atom * n + rows_slack;
     if (L.rows_cap < 1) L.rows_cap = 1;
-    if (L.rows_cap > (1LL << 30) - 1) L.rows_cap = (1LL << 30) - 1;
+    if (L.rows_cap > (1LL << 29) - 1) L.rows_cap = (1LL << 29) - 1;   // row_ref = first entry << 2 | header kind
     L.rows = take(sizeof(int) * (size_t)L.rows_cap);
     L.total = o;
     return L;
@@ -249,12 +249,13 @@ __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, 
 //   periodic dim     : cpd = max(1, floor(face / rc_eff)),  R = ceil(rc_eff * cpd / face)
 //   non-periodic dim : the atoms' bounding slab [fmin, fmax] is cut into cells of width >= rc_eff,
 //                      R = 0 if one cell else 1
-//   cap              : halve all dims (like the reference's max_nbins loop) until #cells <= #atoms,
-//                      so the total never exceeds N + S and no host sync is needed to allocate.
+//   cap              : halve all dims (like the reference's max_nbins loop) until #cells <= #atoms (and <= the
+//                      caller's per-system cap, if any), so the total never exceeds N + S and no host sync is
+//                      needed to allocate.
 // rc_eff = rc * (1 + 1e-3): the cell assignment is done in double, the distance test in the input
 // precision; the margin guarantees every pair the fp test accepts lies inside the stencil.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_systems, double cutoff) {
+__global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_systems, double cutoff, long long cell_cap) {
     SysParams* sys = reinterpret_cast<SysParams*>(ws + L.sys);
     const long long* bbox = reinterpret_cast<const long long*>(ws + L.bbox);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
@@ -284,6 +285,10 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
                     const long long kmn = bbox[s * 6 + d], kmx = bbox[s * 6 + 3 + d];
                     double fmin = 0.0, fmax = 0.0;
                     if (kmn <= kmx) { fmin = order_unkey(kmn); fmax = order_unkey(kmx); }
+                    // capped mode (reference-shaped cache): grid the unit cell like the reference does, atoms outside
+                    // are clamped into the edge cells (cell_list.py:227-232) — the binning is then a function of
+                    // (cell, cells_per_dimension) alone and cell_list_needs_rebuild needs no hidden state
+                    if (cell_cap > 0) { fmin = 0.0; fmax = 1.0; }
                     const double ext = (fmax - fmin) * sp.face[d];
                     const double q = ext / rc;
                     cpd = q >= 1.0 ? (q < 1.0e6 ? (int)q : 1000000) : 1;
@@ -295,7 +300,9 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
                 sp.R[d] = R;
                 tot *= cpd;
             }
-            const long long cap = sp.natoms > 1 ? sp.natoms : 1;
+            // caller-imposed cap (the reference-shaped cache holds cell_cap cells per system, cell_list.py:131-150)
+            long long cap = sp.natoms > 1 ? sp.natoms : 1;
+            if (cell_cap > 0 && cell_cap < cap) cap = cell_cap;
             while (tot > cap) {
                 tot = 1;
                 for (int d = 0; d < 3; ++d) {

@@ -30,6 +30,7 @@ enum ErrorBits {
     ERR_IMAGE_RANGE = 1,      // periodic image index / search radius outside the supported range
     ERR_BAD_BATCH_IDX = 2,    // batch_idx outside [0, num_systems)
     ERR_SINGULAR_CELL = 4,    // cell matrix not invertible
+    ERR_BAD_CACHE = 8,        // imported cell-list cache tensors are inconsistent (not produced by a build of this library)
 };
 
 // Per-system grid description, written by k_sys_init / k_grid (device side only).

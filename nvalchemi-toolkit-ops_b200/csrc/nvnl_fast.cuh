@@ -518,7 +518,10 @@ k_fast(const SweepArgs<T> a) {
                 const int ntarget = cell_start[g + 1] - home_start;
                 if (ntarget == 0) continue;
                 int s = 0;
-                if (a.num_systems > 1) s = a.batch_idx[sorted[home_start].j];
+                if (a.num_systems > 1) {
+                    s = a.batch_idx[sorted[home_start].j];
+                    s = s < 0 ? 0 : (s >= a.num_systems ? a.num_systems - 1 : s);   // (k_hash reported the error)
+                }
                 const SysParams& sp = sys[s];
                 const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
                 const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];

@@ -1,47 +1,75 @@
-// nvnl_rows.cuh — single-sweep COO path for fp32 inputs inside the primary periodic image.
+// nvnl_rows.cuh — single-sweep COO path for fp32 inputs inside the primary periodic image (round 2 rewrite).
 //
-// Why: the two-pass COO path (nvnl_fast.cuh: count -> hit masks -> scan -> mask expansion) was issue-bound in BOTH
-// sweeps (330 + 571 warp-instructions per atom, profiles/r1_final_1m_ncu.txt) and its fill pass wrote 360-byte rows
-// at random places of the output (cell-ordered sweep over randomly labelled atoms: 0.72 ms write-pattern floor,
-// profiles/r1_microbench_write_pattern.txt).  This path computes every distance once AND compacts once:
-//
-//   k_rows      (cell order)   stencil sweep; every lane APPENDS the tile index of its own hits to a lane-private
-//                              list in shared memory (predicated 16-bit store + pointer bump: 2 instructions per
-//                              target per 32 candidates, no ballot, no popc); per target one warp scan of the 32
-//                              list lengths, then the lists are gathered (tile index -> original atom index) into a
-//                              compact row of a TEMPORARY buffer handed out in blocks by one global cursor
-//                              (rows of a warp's targets are contiguous -> sequential DRAM writes).
-//                              Emits num_neighbors[i] and row_ref[i] (row location).
+//   k_rows      (cell order)   stencil sweep.  A consumer warp takes FOUR target atoms per trip (two packed f32x2
+//                              pairs) and walks the staged stencil tile in 32-candidate chunks; every lane keeps, per
+//                              target, a TRANSPOSED hit mask in registers (bit v = "my candidate of chunk v hit"):
+//                              per chunk and target the compaction costs one FSETP and one predicated LOP — no
+//                              ballot, no popc, no shared-memory list.  Per trip: ONE packed warp scan pair of the
+//                              four popcounts, ONE reservation in the temporary row buffer, then every lane walks
+//                              the set bits of its masks (tile slot -> original atom index) into four compact rows.
 //   k_scan                     neighbor_ptr (unchanged).
-//   k_rows_out  (index order)  streams the final arrays: rows are read from the temporary buffer (random 360-byte
-//                              reads) and edge_index / shifts are written strictly sequentially.
+//   k_rows_out  (index order)  a warp prefetches the temporary rows of 32 consecutive atoms into shared memory with
+//                              one TMA bulk copy per lane (rows are 16-byte aligned and padded to 4 entries), then
+//                              streams edge_index / shifts strictly sequentially.
 //
-// Cells the lean kernel cannot take (too many images / candidates / targets) go to the general kernel exactly as in
-// the two-pass path; unwrapped inputs and fp64 use the two-pass path.
-// Replaces (different algorithm, same result): cell_list.py:372-556 + neighbor_utils.py:106-147, 362-441.
+// Tile staging (producer warp): variable-size tiles in a byte ring with a descriptor ring (more small tiles in flight
+// for big boxes, whole small systems for 3-cell boxes).  Images of the stencil are ordered by periodic shift; every
+// shift SEGMENT starts on a 32-slot boundary and its tail is padded with far-away sentinel records, so a chunk never
+// straddles two shifts (warp-uniform shift vector, no per-lane selection) and no chunk needs a validity mask.
+//
+// Cells the lean kernel cannot take (> 32 images, > 64 chunks) go to the general kernel; unwrapped inputs and fp64 use
+// the two-pass path.  Replaces (different algorithm, same result): cell_list.py:372-556 + neighbor_utils.py:106-147,
+// 362-441.
 #pragma once
 #include "nvnl_fast.cuh"
 
 namespace nvnl {
 
-constexpr int kRowsCons = 8;                          // consumer warps per CTA
+// CTA shape (tunable at build time for profiling: -DNVNL_ROWS_CONS=.. -DNVNL_ROWS_MINB=.. -DNVNL_ROWS_RING_KB=..)
+#ifndef NVNL_ROWS_CONS
+#define NVNL_ROWS_CONS 5
+#endif
+#ifndef NVNL_ROWS_MINB
+#define NVNL_ROWS_MINB 4
+#endif
+#ifndef NVNL_ROWS_RING_KB
+#define NVNL_ROWS_RING_KB 44
+#endif
+constexpr int kRowsCons = NVNL_ROWS_CONS;             // consumer warps per CTA
 constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
-constexpr int kRowsStages = 3;                        // default TMA ring depth (consumers may run up to two cells apart)
-constexpr int kRowsMaxSeg = 8;                        // image segments per stencil the lean kernel takes (3 bits in a list entry)
+constexpr int kRowsMinBlocks = NVNL_ROWS_MINB;        // CTAs per SM
+constexpr int kRowsDesc = 6;                          // tiles in flight per CTA (descriptor ring)
+constexpr int kRowsRingBytes = NVNL_ROWS_RING_KB * 1024;   // staged records of the tiles in flight
+constexpr int kRowsMaxVC = 64;                        // 32-candidate chunks per tile (two mask words per lane and target)
+constexpr int kRowsMaxSeg = 32;                       // shift segments per tile (one per image at most)
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
+constexpr int kRowsSegShift = 27;                     // boundary rows: entry = atom | segment << 27 (atoms < 2^27)
+constexpr float kRowsFar = 3.0e18f;                   // sentinel coordinate: squares stay finite, never within any cutoff
 
-template <int STAGES>
-struct RowsSmem {
-    FastStage<float> stage[STAGES];
-    int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
-    // lane-private hit lists, two targets per warp: slot s of lane l is byte s * 32 + l; an entry is
-    // chunk | segment << 5 (the candidate's tile index is chunk * 32 + l); a lane cannot have more hits than chunks
-    alignas(16) unsigned char lists[kRowsCons][2][32 * 32];
-    unsigned long long full[STAGES], empty[STAGES];                         // mbarriers of the ring
+// Per-tile descriptor, written by the producer warp, read by the consumers.
+struct RowsDesc {
+    int item;                         // global cell id, -1 = end of work
+    int ntarget, home_slot;           // targets of the cell and the tile slot of the first one
+    int nseg, nvc;                    // shift segments, 32-candidate chunks (interior tiles: even)
+    int data_off;                     // byte offset of the tile in the ring
+    int shifted;                      // some segment has a non-zero shift
+    int next_target;                  // consumer claim counter
+    int footprint;                    // producer-private: ring bytes held by this tile
+    int pad0[3];
+    int seg_vc[kRowsMaxSeg + 1];      // first chunk of every segment (segment s covers slots 32 * seg_vc[s] ...)
+    int seg_key[kRowsMaxSeg];         // packed integer shift of the segment
+    float segS[kRowsMaxSeg][4];       // its lattice vector s·cell
+    unsigned char vc_seg[kRowsMaxVC]; // chunk -> segment
 };
 
-template <int STAGES>
-constexpr size_t rows_smem_bytes() { return (size_t)STAGES * kFastStageBytes + sizeof(RowsSmem<STAGES>); }
+struct RowsSmem {
+    RowsDesc desc[kRowsDesc];
+    int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
+    unsigned long long full[kRowsDesc], empty[kRowsDesc];                   // mbarriers of the descriptor ring
+    int zero_next;                                                          // next piece of the CTA's zero-fill slice
+};
+
+constexpr size_t rows_smem_bytes() { return (size_t)kRowsRingBytes + sizeof(RowsSmem); }
 
 struct RowsArgs {
     unsigned char* ws;
@@ -55,16 +83,8 @@ struct RowsArgs {
     long long prezero_ints;
 };
 
-__device__ __forceinline__ void sts_u8(uint32_t addr, int v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ int lds_u8(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 // the k_rows barriers are polled with a short sleep between tries: a spinning warp would otherwise take issue slots
-// from the sweeping warps of its scheduler (ncu: 13 % of the issued instructions were the bare try_wait loop)
+// from the sweeping warps of its scheduler
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -78,8 +98,39 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         "NVNL_BDONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void sts_rec(uint32_t addr, float x, float y, float z, int j) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "r"(j) : "memory");
+}
+__device__ __forceinline__ int lds_b32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// squared distances of one candidate to the two packed targets
+// m |= bit where d < rc2: one FSETP and one predicated LOP
+__device__ __forceinline__ void rows_acc(unsigned& m, float d, float rc2, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(m) : "f"(d), "f"(rc2), "r"(bit));
+}
+
+// packed target coordinates of a trip: pairs (0,1) and (2,3)
+struct RowsTargets {
+    f32x2_t X01, Y01, Z01, X23, Y23, Z23;
+    int i[4];
+};
+
+// squared distances of one candidate to a packed target pair; op order of the reference: (r_j - r_i) + s·cell, then
+// dx*dx (+) dy*dy (+) dz*dz
 template <bool FMA, bool SHIFTED>
 __device__ __forceinline__ f32x2_t rows_d2(float x, float y, float z, f32x2_t XI, f32x2_t YI, f32x2_t ZI, float Sx, float Sy,
                                            float Sz) {
@@ -101,194 +152,185 @@ __device__ __forceinline__ f32x2_t rows_d2(float x, float y, float z, f32x2_t XI
     return d2;
 }
 
-// lanes that hit append `val` = chunk | segment << 5 to their private lists (predicated 8-bit store + pointer
-// bump).  EXCL: the targets themselves (tile indices selfA / selfB, zero shift, d = 0) are not recorded — (i, i, 0) is
-// not a pair; half fill needs no such test (i < j fails).
-template <bool HALF, bool TAIL, bool EXCL>
-__device__ __forceinline__ void rows_append(f32x2_t d2, int c, int val, int j, int iA, int iB, float rc2, bool lexpos,
-                                            bool valid, int selfA, int selfB, uint32_t& la, uint32_t& lb) {
-    float dA, dB;
-    unpack2(d2, dA, dB);
-    bool hA = dA < rc2, hB = dB < rc2;
-    if (TAIL) { hA = hA && valid; hB = hB && valid; }
-    if (EXCL) { hA = hA && c != selfA; hB = hB && c != selfB; }
-    if (HALF) {
-        hA = hA && (iA < j || (iA == j && lexpos));
-        hB = hB && (iB < j || (iB == j && lexpos));
-    }
-    if (hA) { sts_u8(la, val); la += 32u; }
-    if (hB) { sts_u8(lb, val); lb += 32u; }
-}
-
-// one 32-candidate chunk against two targets (boundary cells: single chunks and chunks with image shifts)
-template <bool HALF, bool FMA, bool SHIFTED, bool TAIL>
-__device__ __forceinline__ void rows_chunk2(uint32_t addr, int c, int sg, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA, int iB,
-                                            float Sx, float Sy, float Sz, float rc2, bool lexpos, bool valid, int selfA,
-                                            int selfB, uint32_t& la, uint32_t& lb) {
+// one 32-candidate chunk against the four targets of the trip; `bit` = this chunk's bit in the mask word
+template <bool HALF, bool FMA, bool SHIFTED>
+__device__ __forceinline__ void rows_chunk4(uint32_t addr, const RowsTargets& t, float Sx, float Sy, float Sz, float rc2,
+                                            unsigned bit, bool lexpos, unsigned (&m)[4]) {
     float x, y, z;
     int j;
     lds_rec(addr, x, y, z, j);
-    const f32x2_t d2 = rows_d2<FMA, SHIFTED>(x, y, z, XI, YI, ZI, Sx, Sy, Sz);
-    rows_append<HALF, TAIL, !HALF>(d2, c, (c >> 5) | (sg << 5), j, iA, iB, rc2, lexpos, valid, selfA, selfB, la, lb);
+    const f32x2_t a = rows_d2<FMA, SHIFTED>(x, y, z, t.X01, t.Y01, t.Z01, Sx, Sy, Sz);
+    const f32x2_t b = rows_d2<FMA, SHIFTED>(x, y, z, t.X23, t.Y23, t.Z23, Sx, Sy, Sz);
+    float d[4];
+    unpack2(a, d[0], d[1]);
+    unpack2(b, d[2], d[3]);
+    if (!HALF) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rows_acc(m[k], d[k], rc2, bit);
+    } else {
+        // half fill keeps (i, j, s) only for i < j, or i == j with a lexicographically positive shift
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool keep = t.i[k] < j || (t.i[k] == j && lexpos);
+            if (d[k] < rc2 && keep) m[k] |= bit;
+        }
+    }
 }
 
-// four zero-shift chunks: all loads first, then the four independent FP chains, then the appends (ILP inside the warp).
-// MASKED: the group may run past the end of the tile — candidates with index >= limit are ignored (whatever the
-// stage buffer holds there is read but never recorded).
-template <bool HALF, bool FMA, bool MASKED, bool EXCL>
-__device__ __forceinline__ void rows_chunk2x4(uint32_t addr, int c, int limit, f32x2_t XI, f32x2_t YI, f32x2_t ZI, int iA,
-                                              int iB, float rc2, int selfA, int selfB, uint32_t& la, uint32_t& lb) {
-    constexpr uint32_t RS = sizeof(Rec<float>);
-    float x[4], y[4], z[4];
-    int j[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) lds_rec(addr + (uint32_t)u * 32u * RS, x[u], y[u], z[u], j[u]);
-    f32x2_t d2[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) d2[u] = rows_d2<FMA, false>(x[u], y[u], z[u], XI, YI, ZI, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-        rows_append<HALF, MASKED, EXCL>(d2[u], c + 32 * u, (c >> 5) + u, j[u], iA, iB, rc2, false, c + 32 * u < limit, selfA,
-                                        selfB, la, lb);
-}
-
-// four chunks that each lie entirely inside ONE image segment (warp-uniform shift vector per chunk): same structure as
-// rows_chunk2x4 plus the three packed adds of the shift.  Experiment (UNI), see k_rows.
+// chunks [v0, v1) of the zero-shift home segment, two per trip (interior tiles pad their chunk count to an even number)
 template <bool HALF, bool FMA>
-__device__ __forceinline__ void rows_chunk2x4_shift(const FastStage<float>& sm, uint32_t addr, int c, int ck, f32x2_t XI,
-                                                    f32x2_t YI, f32x2_t ZI, int iA, int iB, float rc2, int selfA, int selfB,
-                                                    uint32_t& la, uint32_t& lb) {
+__device__ __forceinline__ void rows_run_zero(uint32_t addr, int v0, int v1, const RowsTargets& t, float rc2, unsigned (&m)[4]) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    float x[4], y[4], z[4];
-    int j[4], sgv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) lds_rec(addr + (uint32_t)u * 32u * RS, x[u], y[u], z[u], j[u]);
-    f32x2_t d2[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        sgv[u] = sm.chunk_seg[ck + u];
-        d2[u] = rows_d2<FMA, true>(x[u], y[u], z[u], XI, YI, ZI, sm.segS[3 * sgv[u]], sm.segS[3 * sgv[u] + 1],
-                                   sm.segS[3 * sgv[u] + 2]);
+    unsigned bit = 1u << (v0 & 31);
+    int v = v0;
+#pragma unroll 1
+    for (; v + 2 <= v1; v += 2) {
+        rows_chunk4<HALF, FMA, false>(addr, t, 0.f, 0.f, 0.f, rc2, bit, false, m);
+        rows_chunk4<HALF, FMA, false>(addr + 32u * RS, t, 0.f, 0.f, 0.f, rc2, bit << 1, false, m);
+        addr += 64u * RS;
+        bit <<= 2;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        bool lexpos = false;
-        if (HALF) {
-            int csx, csy, csz;
-            unpack_key(sm.seg_key[sgv[u]], csx, csy, csz);
-            lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
-        }
-        rows_append<HALF, false, !HALF>(d2[u], c + 32 * u, (ck + u) | (sgv[u] << 5), j[u], iA, iB, rc2, lexpos, true, selfA,
-                                        selfB, la, lb);
+    if (v < v1) rows_chunk4<HALF, FMA, false>(addr, t, 0.f, 0.f, 0.f, rc2, bit, false, m);
+}
+
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void rows_run_shift(uint32_t addr, int v0, int v1, const RowsTargets& t, float Sx, float Sy,
+                                               float Sz, float rc2, bool lexpos, unsigned (&m)[4]) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    unsigned bit = 1u << (v0 & 31);
+#pragma unroll 1
+    for (int v = v0; v < v1; ++v) {
+        rows_chunk4<HALF, FMA, true>(addr, t, Sx, Sy, Sz, rc2, bit, lexpos, m);
+        addr += 32u * RS;
+        bit <<= 1;
     }
 }
 
-// Sweep of two targets over the staged tile.  la / lb: per-lane append pointers.
-//   interior cell (one zero-shift segment): groups of four chunks, the last group masked;
-//   cell at a periodic boundary: full zero-shift chunks in groups of four, then every other chunk with its shift vector
-//   picked per lane (a chunk may straddle segments).
-// Only the group(s) holding the targets themselves pay for the self-exclusion test.
-template <bool HALF, bool FMA, bool UNI>
-__device__ __forceinline__ void rows_sweep2(const FastStage<float>& sm, uint32_t cand_addr, f32x2_t XI, f32x2_t YI,
-                                            f32x2_t ZI, int iA, int iB, float rc2, int lane, int selfA, int selfB,
-                                            uint32_t& la, uint32_t& lb) {
+// Sweep of the four targets over chunks [32 w, 32 w + 32) of the staged tile: m = their hit masks (bit = chunk - 32 w).
+// (One call per mask word, so that the masks stay in registers; word 1 only exists for tiles of more than 1024 slots.)
+template <bool HALF, bool FMA>
+__device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile_addr, const RowsTargets& t, float rc2,
+                                                int lane, int w, unsigned (&m)[4]) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    constexpr bool EX = !HALF;
-    const int total = sm.total, nchunks = sm.nchunks, nseg = sm.nseg;
-    const bool zero0 = sm.seg_key[0] == 0;
-    const int gA = selfA >> 7, gB = selfB >> 7;
-    uint32_t addr = cand_addr + (uint32_t)lane * RS;
-    int c = lane;
-    if (nseg == 1 && zero0) {
-        const int ngroups = total >> 7;
-#pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
-            if (EX && (g == gA || g == gB))
-                rows_chunk2x4<HALF, FMA, false, true>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
-            else
-                rows_chunk2x4<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
-            addr += 128 * RS;
-            c += 128;
-        }
-        if (total & 127) rows_chunk2x4<HALF, FMA, true, EX>(addr, c, total, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
+    const int nvc = d.nvc;
+    const uint32_t lane_addr = tile_addr + (uint32_t)lane * RS;
+    const int wb = w << 5, we = nvc < wb + 32 ? nvc : wb + 32;
+    if (!d.shifted) {
+        rows_run_zero<HALF, FMA>(lane_addr + (uint32_t)wb * (32u * RS), wb, we, t, rc2, m);
         return;
     }
-    const int zend = zero0 ? sm.seg_begin[1] : 0;
-    const int nzfull = zend >> 5;
-    int ck = 0;
+    const int nseg = d.nseg;
 #pragma unroll 1
-    for (; ck + 4 <= nzfull; ck += 4) {
-        const int g = ck >> 2;
-        if (EX && (g == gA || g == gB))
-            rows_chunk2x4<HALF, FMA, false, true>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
-        else
-            rows_chunk2x4<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
-        addr += 128 * RS;
-        c += 128;
-    }
-#pragma unroll 1
-    for (; ck < nzfull; ++ck) {
-        rows_chunk2<HALF, FMA, false, false>(addr, c, 0, XI, YI, ZI, iA, iB, 0, 0, 0, rc2, false, true, selfA, selfB, la, lb);
-        addr += 32 * RS;
-        c += 32;
-    }
-    const unsigned um = UNI ? (unsigned)sm.qrow[0] : 0u;  // chunks lying entirely inside one segment (producer)
-#pragma unroll 1
-    for (; ck < nchunks; ++ck) {
-        if (UNI && ck + 4 <= nchunks && ((um >> ck) & 15u) == 15u) {
-            rows_chunk2x4_shift<HALF, FMA>(sm, addr, c, ck, XI, YI, ZI, iA, iB, rc2, selfA, selfB, la, lb);
-            addr += 128 * RS;
-            c += 128;
-            ck += 3;
-            continue;
+    for (int s = 0; s < nseg; ++s) {
+        int v0 = d.seg_vc[s], v1 = d.seg_vc[s + 1];
+        v0 = v0 > wb ? v0 : wb;
+        v1 = v1 < we ? v1 : we;
+        if (v0 >= v1) continue;
+        const uint32_t addr = lane_addr + (uint32_t)v0 * (32u * RS);
+        const int key = d.seg_key[s];
+        if (key == 0) {
+            rows_run_zero<HALF, FMA>(addr, v0, v1, t, rc2, m);
+        } else {
+            bool lexpos = false;
+            if (HALF) {
+                int csx, csy, csz;
+                unpack_key(key, csx, csy, csz);
+                lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
+            }
+            rows_run_shift<HALF, FMA>(addr, v0, v1, t, d.segS[s][0], d.segS[s][1], d.segS[s][2], rc2, lexpos, m);
         }
-        int sg = sm.chunk_seg[ck];
-        while (sg + 1 < nseg && c >= sm.seg_begin[sg + 1]) ++sg;
-        bool lexpos = false;
-        if (HALF) {
-            int csx, csy, csz;
-            unpack_key(sm.seg_key[sg], csx, csy, csz);
-            lexpos = csx > 0 || (csx == 0 && (csy > 0 || (csy == 0 && csz > 0)));
-        }
-        rows_chunk2<HALF, FMA, true, true>(addr, c, sg, XI, YI, ZI, iA, iB, sm.segS[3 * sg], sm.segS[3 * sg + 1],
-                                           sm.segS[3 * sg + 2], rc2, lexpos, c < total, selfA, selfB, la, lb);
-        addr += 32 * RS;
-        c += 32;
     }
+}
+
+// Every lane walks the set bits of its own masks of word w, leading bit first (entry r of the lane goes to slot r of
+// its piece of the row, p[k]).  Branch-free: a lane that has run out of bits keeps executing with its load and store
+// predicated off (the loop runs to the longest list of the warp).  SHIFTED rows carry the entry's shift segment in the
+// top bits.  Advances p[k] past the entries written.
+template <bool SHIFTED>
+__device__ __forceinline__ void rows_gather_word(const RowsDesc& d, uint32_t tile_addr, const unsigned (&mw)[4], int w,
+                                                 int lane, int* __restrict__ (&p)[4]) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    unsigned m[4];
+    int mx = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        m[k] = mw[k];
+        const int c = __popc(m[k]);
+        mx = c > mx ? c : mx;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    // address of .j of this lane's candidate of chunk 0 of the word; chunk b is b * 512 bytes above
+    const uint32_t bot_addr = tile_addr + (uint32_t)lane * RS + 12u + (uint32_t)(w * 32) * (32u * RS);
+    const uint32_t seg_bot = smem_u32(&d.vc_seg[0]) + (uint32_t)(w * 32);
+#pragma unroll 2
+    for (int r = 0; r < mx; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned mk = m[k];
+            int b;                                                  // leading set bit, -1 when the lane has none left
+            asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(mk));
+            unsigned one;
+            asm("shl.b32 %0, %1, %2;" : "=r"(one) : "r"(1u), "r"(b));   // (clamped shift: 0 for b = -1)
+            m[k] = mk ^ one;
+            const int b0 = b < 0 ? 0 : b;                           // a lane without bits reads chunk 0 and stores nothing
+            int j = lds_b32(bot_addr + (uint32_t)b0 * (32u * RS));
+            if (SHIFTED) {
+                int sg;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sg) : "r"(seg_bot + (uint32_t)b0));
+                j |= sg << kRowsSegShift;
+            }
+            if (mk != 0u) p[k][r] = j;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] += __popc(mw[k]);
 }
 
 // Per-warp allocator state of the temporary row buffer.
 struct RowsAlloc {
-    long long pos, end;
+    int pos, end;   // entries (the buffer holds fewer than 2^29)
 };
 
-// Epilogue of a target pair: drop the self entries, ONE packed warp scan of both targets' list lengths, ONE row
-// reservation, then the lists are gathered (tile index -> original atom index) into the two compact rows.
-// PAD: every row starts on a 128-byte boundary and is padded to a multiple of 32 entries (the output kernel then reads
-// whole lines; experiment, see k_rows).
-template <bool HALF, bool PAD>
-__device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<float>& sm, Ctrl* ctrl, uint32_t cand_addr,
-                                           uint32_t lbaseA, uint32_t lbaseB, uint32_t la, uint32_t lb, int selfA, int selfB,
-                                           int iA, int iB, bool two, int lane, bool shifted, RowsAlloc& al,
-                                           int* __restrict__ rows, int* __restrict__ row_ref) {
+// Row format in the temporary buffer (all starts are multiples of 4 entries = 16 bytes; TMA-able):
+//   interior cell:        [entries ... padded to 4]                                   row_ref = start << 2
+//   cell at a boundary:   [8 or 32 packed image keys][entries = atom | segment << 27]  row_ref = start << 2 | 1 or 2
+// Epilogue of a trip: popcounts, ONE packed scan pair, ONE reservation, then every lane walks its own set bits.
+// BIG: the tile has more than 32 chunks (second mask word hi); s0 = tile slot of the trip's first target.
+template <bool BIG>
+__device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d, Ctrl* ctrl, uint32_t tile_addr,
+                                           unsigned (&lo)[4], unsigned (&hi)[4], int s0, int nt, int lane,
+                                           RowsAlloc& al, int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
-    const int nA = (int)((la - lbaseA) >> 5);
-    const int nB = two ? (int)((lb - lbaseB) >> 5) : 0;
-    // list lengths are <= 32 per lane, their sums <= 1024: both scans fit one 32-bit word
-    const int packed = nA | (nB << 16);
-    const int incl = warp_incl_scan(packed, lane);
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    const int cntA = tot & 0xffff, cntB = tot >> 16;
-    const int excl = incl - packed;
-    const int exA = excl & 0xffff, exB = excl >> 16;
-    const int maxn = __reduce_max_sync(0xffffffffu, nA > nB ? nA : nB);
-    // row of a cell at a periodic boundary: [kRowsMaxSeg packed image keys][entries = atom | segment << 28]
-    const int hdr = shifted ? (PAD ? 32 : kRowsMaxSeg) : 0;
-    const int lenA = PAD ? ((cntA + 31) & ~31) : cntA, lenB = PAD ? ((cntB + 31) & ~31) : cntB;
-    const int need = lenA + lenB + 2 * hdr;
+    int n[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= nt) { lo[k] = 0u; if (BIG) hi[k] = 0u; }   // targets past the end of the cell
+        n[k] = __popc(lo[k]) + (BIG ? __popc(hi[k]) : 0);
+    }
+    // a lane holds <= 64 hits per target, a row <= 2048 entries: two 16-bit fields per scan word
+    const int pa = n[0] | (n[1] << 16), pb = n[2] | (n[3] << 16);
+    int ia = pa, ib = pb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ua; ib += ub; }
+    }
+    const int ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
+    const int ea = ia - pa, eb = ib - pb;
+    const int cnt[4] = {ta & 0xffff, ta >> 16, tb & 0xffff, tb >> 16};
+    const int ex[4] = {ea & 0xffff, ea >> 16, eb & 0xffff, eb >> 16};
+    const bool shifted = d.shifted != 0;
+    const int hdr = shifted ? (d.nseg <= 8 ? 8 : 32) : 0;
+    int start[4];
+    int need = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        start[k] = need;
+        if (k < nt) need += hdr + ((cnt[k] + 3) & ~3);
+    }
     bool ok = true;
     if (al.pos + need > al.end) {
-        const long long sz = need > kRowsBlock ? need : kRowsBlock;
+        const int sz = need > kRowsBlock ? need : kRowsBlock;
         unsigned long long b = 0ull;
         if (lane == 0) b = atomicAdd(&ctrl->rows_cursor, (unsigned long long)sz);
         b = __shfl_sync(0xffffffffu, b, 0);
@@ -298,85 +340,106 @@ __device__ __forceinline__ void rows_emit2(const RowsArgs& a, const FastStage<fl
             al.pos = al.end = 0;
             ok = false;
         } else {
-            al.pos = (long long)b;
-            al.end = (long long)b + sz;
+            al.pos = (int)b;
+            al.end = (int)b + sz;
         }
     }
-    int startA = 0, startB = 0;
     if (ok) {
-        startA = (int)al.pos;
-        startB = startA + hdr + lenA;
+        const int base = al.pos;
         al.pos += need;
-        int* __restrict__ rowA = rows + startA + hdr + exA;
-        int* __restrict__ rowB = rows + startB + hdr + exB;
-        // two slots of both lists per trip: four independent index -> atom gathers in flight.  Slots past a list's
-        // length hold stale (valid) entries — the lists are zero-initialised — and are read but not stored.
-        // entry -> record address: tile index = chunk * 32 + lane
-        const uint32_t cand_lane = cand_addr + (uint32_t)lane * RS;
-        if (!shifted) {
-#pragma unroll 1
-            for (int s = 0; s < maxn; s += 2) {
-                const uint32_t o = (uint32_t)s * 32u;
-                // & 31: a stale slot may hold an entry (with segment bits) of an earlier boundary cell
-                const int cA0 = lds_u8(lbaseA + o) & 31, cA1 = lds_u8(lbaseA + o + 32u) & 31;
-                const int cB0 = lds_u8(lbaseB + o) & 31, cB1 = lds_u8(lbaseB + o + 32u) & 31;
-                const int jA0 = lds_rec_j<float>(cand_lane + (uint32_t)cA0 * (32u * RS));
-                const int jA1 = lds_rec_j<float>(cand_lane + (uint32_t)cA1 * (32u * RS));
-                const int jB0 = lds_rec_j<float>(cand_lane + (uint32_t)cB0 * (32u * RS));
-                const int jB1 = lds_rec_j<float>(cand_lane + (uint32_t)cB1 * (32u * RS));
-                if (s < nA) rowA[s] = jA0;
-                if (s + 1 < nA) rowA[s + 1] = jA1;
-                if (s < nB) rowB[s] = jB0;
-                if (s + 1 < nB) rowB[s + 1] = jB1;
-            }
-        } else {
-            // cell at a periodic boundary: the row starts with the stencil's packed image keys, every entry carries
-            // its segment in the top bits (atom indices < 2^28 on this path)
-            if (lane < kRowsMaxSeg) {
-                const int key = lane < sm.nseg ? sm.seg_key[lane] : 0;
-                rows[startA + (PAD ? hdr - kRowsMaxSeg : 0) + lane] = key;   // the keys sit right in front of the entries
-                rows[startB + (PAD ? hdr - kRowsMaxSeg : 0) + lane] = key;
-            }
-#pragma unroll 1
-            for (int s = 0; s < maxn; s += 2) {
-                const uint32_t o = (uint32_t)s * 32u;
-                const int vA0 = lds_u8(lbaseA + o), vA1 = lds_u8(lbaseA + o + 32u);
-                const int vB0 = lds_u8(lbaseB + o), vB1 = lds_u8(lbaseB + o + 32u);
-                const int jA0 = lds_rec_j<float>(cand_lane + (uint32_t)(vA0 & 31) * (32u * RS));
-                const int jA1 = lds_rec_j<float>(cand_lane + (uint32_t)(vA1 & 31) * (32u * RS));
-                const int jB0 = lds_rec_j<float>(cand_lane + (uint32_t)(vB0 & 31) * (32u * RS));
-                const int jB1 = lds_rec_j<float>(cand_lane + (uint32_t)(vB1 & 31) * (32u * RS));
-                if (s < nA) rowA[s] = jA0 | ((vA0 >> 5) << 28);
-                if (s + 1 < nA) rowA[s + 1] = jA1 | ((vA1 >> 5) << 28);
-                if (s < nB) rowB[s] = jB0 | ((vB0 >> 5) << 28);
-                if (s + 1 < nB) rowB[s + 1] = jB1 | ((vB1 >> 5) << 28);
+        int* __restrict__ p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            start[k] += base;
+            p[k] = rows + start[k] + hdr + ex[k];
+        }
+        if (shifted) {
+            // the stencil's packed image keys in front of every row: the shift of an entry is a table lookup later
+            if (lane < hdr) {
+                const int key = lane < d.nseg ? d.seg_key[lane] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < nt) rows[start[k] + lane] = key;
             }
         }
+        if (shifted) {
+            rows_gather_word<true>(d, tile_addr, lo, 0, lane, p);
+            if (BIG) rows_gather_word<true>(d, tile_addr, hi, 1, lane, p);
+        } else {
+            rows_gather_word<false>(d, tile_addr, lo, 0, lane, p);
+            if (BIG) rows_gather_word<false>(d, tile_addr, hi, 1, lane, p);
+        }
+        // padding entries of every row (read by the bulk copies of the output kernel, never used)
+        if (lane < 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nt && cnt[k] + lane < ((cnt[k] + 3) & ~3)) rows[start[k] + hdr + cnt[k] + lane] = -1;
+        }
     }
-    if (lane < 2 && (lane == 0 || two)) {
-        const int i = lane ? iB : iA;
-        if (ok) row_ref[i] = (((lane ? startB : startA) + (PAD && shifted ? hdr - kRowsMaxSeg : 0)) << 1) | (shifted ? 1 : 0);
-        a.num_neighbors[i] = lane ? cntB : cntA;
+    if (lane < nt) {
+        const int i = lds_b32(tile_addr + (uint32_t)(s0 + lane) * RS + 12u);   // original index of target `lane`
+        const int c = lane == 0 ? cnt[0] : (lane == 1 ? cnt[1] : (lane == 2 ? cnt[2] : cnt[3]));
+        const int s = lane == 0 ? start[0] : (lane == 1 ? start[1] : (lane == 2 ? start[2] : start[3]));
+        if (ok) row_ref[i] = (s << 2) | (hdr == 0 ? 0 : (hdr == 8 ? 1 : 2));
+        a.num_neighbors[i] = c;
     }
 }
 
+// One trip of a consumer warp: four targets (tile slots s0 .. s0 + nt - 1) against the staged tile, then their rows.
+// Four targets share every candidate load; two packed pairs share every FP instruction.
+template <bool HALF, bool FMA, bool BIG>
+__device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds, Ctrl* ctrl, uint32_t tile_addr, int s0,
+                                          int nt, float rc2, int lane, RowsAlloc& al, int* __restrict__ rows,
+                                          int* __restrict__ row_ref) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    RowsTargets tg;
+    {
+        // targets past the end of the cell repeat the last one (their results are dropped)
+        float x[4], y[4], z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            lds_rec(tile_addr + (uint32_t)(s0 + (k < nt ? k : nt - 1)) * RS, x[k], y[k], z[k], tg.i[k]);
+        // x + (-0) == x bit for bit: one packed add gives each target pair a home in an aligned register pair
+        const f32x2_t nz = pack2(-0.0f, -0.0f);
+        tg.X01 = add2(pack2(x[0], x[1]), nz); tg.Y01 = add2(pack2(y[0], y[1]), nz); tg.Z01 = add2(pack2(z[0], z[1]), nz);
+        tg.X23 = add2(pack2(x[2], x[3]), nz); tg.Y23 = add2(pack2(y[2], y[3]), nz); tg.Z23 = add2(pack2(z[2], z[3]), nz);
+    }
+    unsigned lo[4] = {0u, 0u, 0u, 0u}, hi[4] = {0u, 0u, 0u, 0u};
+    rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, 0, lo);
+    if (BIG) rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, 1, hi);
+    if (!HALF) {
+        // (i, i, 0) is not a pair: the targets sit in the zero-shift home segment (chunk = slot / 32)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sl = s0 + (k < nt ? k : nt - 1);
+            if (lane == (sl & 31)) {
+                const unsigned bit = 1u << ((sl >> 5) & 31);
+                if (!BIG || sl < 1024) lo[k] &= ~bit; else hi[k] &= ~bit;
+            }
+        }
+    }
+    rows_emit4<BIG>(a, ds, ctrl, tile_addr, lo, hi, s0, nt, lane, al, rows, row_ref);
+}
+
 // ------------------------------------------------------------------------------------------------
-// k_rows: warp-specialised persistent kernel (producer identical in role to k_fast's: queue -> stencil images ->
-// shift sort -> segment/chunk tables -> TMA bulk copies into a 2-stage ring).
+// k_rows: warp-specialised persistent kernel.  The LAST warp is the producer (the warp scheduler favours the highest
+// warp id among eligible warps, and the producer's serial per-tile latency bounds the whole CTA): queue -> stencil
+// images -> shift sort -> aligned segment layout -> descriptor + sentinels -> TMA bulk copies (x-adjacent cells are one
+// copy) into the byte ring.  Warps 0..kRowsCons-1 (consumers): claim four targets of the current tile at a time,
+// sweep, emit rows.  No CTA-wide barrier in the steady state.
 // ------------------------------------------------------------------------------------------------
-// STAGES / MINB: ring depth and CTAs per SM.  <3, 3> (72 KB, <= 72 registers) is the measured default; <2, 4> (54 KB,
-// 56 registers, no spills) trades ring depth for 36 instead of 27 resident warps — compiled, selectable with
-// NVNL_ROWS_CONFIG bit 0, not yet measured.  PAD (bit 1): 128-byte aligned, padded temporary rows.  UNI (bit 2): chunks
-// of boundary cells that lie inside one image segment are swept in groups of four with a warp-uniform shift vector.
-template <bool HALF, bool FMA, int STAGES, int MINB, bool PAD, bool UNI>
-__global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
+struct RowsZero {
+    int4* base;                 // the caller's (speculatively sized) shifts buffer, viewed as int4
+    long long pos, end;         // this CTA's slice [pos, end), handed out in 2048-int4 pieces through smem counter
+};
+
+template <bool HALF, bool FMA>
+__global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const RowsArgs a) {
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int kStageBytes = kFastStageBytes;
-    RowsSmem<STAGES>& sm = *reinterpret_cast<RowsSmem<STAGES>*>(smem_raw + (size_t)STAGES * kStageBytes);
-    const uint32_t smem_base = smem_u32(smem_raw);
+    RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kRowsRingBytes);
+    const uint32_t ring_addr = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
-    constexpr int cap = kCandBytes / (int)RS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(a.ws + a.L.ctrl);
@@ -393,97 +456,124 @@ __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
             ctrl->max_count = 0;
         }
     }
-    // stale list slots are read (never stored) by the epilogue: they must hold valid tile indices from the start
-    for (int k = tid; k < (int)(sizeof(sm.lists) / sizeof(unsigned)); k += kRowsThreads)
-        reinterpret_cast<unsigned*>(&sm.lists[0][0][0])[k] = 0u;
     // unwrapped inputs are served by the two-pass kernels launched next to this one
     const bool active = ctrl->unwrapped == 0;
+    // Zero-fill of the caller's shifts buffer, fused into the sweep: the sweep is issue-bound and leaves HBM idle, the
+    // zero-fill is pure HBM writes.  Every CTA owns one slice, handed out in pieces through a shared counter: the
+    // producer warp takes pieces while it waits for ring space, every warp takes the remaining ones before it exits.
+    // (A separate memset kernel does not do: next to this kernel's large CTAs it only runs if the SM already has the
+    // large shared-memory carve-out, otherwise the two serialise — profiles/r2_zero_overlap.txt.)
+    constexpr long long kZeroPiece = 2048;   // int4 per piece (32 KB)
+    int4* const zbase = reinterpret_cast<int4*>(a.prezero);
+    long long zlo = 0, zhi = 0;
+    if (a.prezero) {
+        const long long n16 = a.prezero_ints >> 2;
+        const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
+        zlo = (long long)blockIdx.x * slice;
+        zhi = zlo + slice < n16 ? zlo + slice : n16;
+        if (zlo > zhi) zlo = zhi;
+        if (blockIdx.x == 0 && tid < (int)(a.prezero_ints & 3)) a.prezero[(n16 << 2) + tid] = 0;
+    }
+    const int zpieces = (int)((zhi - zlo + kZeroPiece - 1) / kZeroPiece);
+    auto zero_piece = [&]() -> bool {   // one piece by this warp; false when the slice is done
+        int pc = 0;
+        if (lane == 0) pc = atomicAdd(&sm.zero_next, 1);
+        pc = __shfl_sync(0xffffffffu, pc, 0);
+        if (pc >= zpieces) return false;
+        const long long b = zlo + (long long)pc * kZeroPiece;
+        const long long e = b + kZeroPiece < zhi ? b + kZeroPiece : zhi;
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        long long k = b + lane;
+        for (; k + 224 < e; k += 256) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) zbase[k + 32 * u] = z4;
+        }
+        for (; k < e; k += 32) zbase[k] = z4;
+        return true;
+    };
     if (tid == 0) {
-        for (int st = 0; st < STAGES; ++st) {
+        for (int st = 0; st < kRowsDesc; ++st) {
             mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kRowsCons);
         }
+        sm.zero_next = 0;
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == 0) {
+    if (warp == kRowsCons) {
         // =========================== producer ===========================
         const SysParams* sys = reinterpret_cast<const SysParams*>(a.ws + a.L.sys);
         const int* cell_start = reinterpret_cast<const int*>(a.ws + a.L.cell_start);
         const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(a.ws + a.L.sorted);
         int2* deferred = reinterpret_cast<int2*>(a.ws + a.L.deferred);
+        int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
         const int total_cells = active ? ctrl->total_cells : 0;
-        int stage = 0;
-        uint32_t ephase = 1;  // a fresh mbarrier passes a wait on the opposite parity: the ring starts empty
+        // descriptor ring + byte ring (FIFO): tiles [oldest, nprod) are live
+        int nprod = 0, oldest = 0;
+        int head = 0, used = 0;
         int g_next = 0;
         if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
-        // Zero-fill of the caller's shifts buffer, fused into the sweep: the sweep is issue-bound and leaves HBM idle, the
-        // zero-fill is pure HBM writes.  Every CTA owns one slice; its producer warp writes a quota of it per published
-        // cell (paced over the kernel's lifetime) and the rest when the queue is drained.  A separate memset kernel does
-        // not do: next to this kernel's 72 KB CTAs it only runs if the SM already has the large shared-memory carve-out,
-        // otherwise the two serialise (profiles/r2_zero_overlap.txt).
-        int4* const zbase = reinterpret_cast<int4*>(a.prezero);
-        long long zpos = 0, zend = 0, zquota = 0;
-        if (a.prezero) {
-            const long long n16 = a.prezero_ints >> 2;
-            const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
-            zpos = (long long)blockIdx.x * slice;
-            zend = zpos + slice < n16 ? zpos + slice : n16;
-            if (zpos > zend) zpos = zend;
-            const long long cells_here = total_cells / (int)gridDim.x > 0 ? total_cells / (int)gridDim.x : 1;
-            zquota = (zend - zpos) / cells_here + 32;
-            if (blockIdx.x == 0 && lane < (int)(a.prezero_ints & 3)) a.prezero[(n16 << 2) + lane] = 0;
-        }
-        auto zero_some = [&](long long quota) {
-            long long e = zpos + quota;
-            e = e < zend ? e : zend;
-            const int4 z4 = make_int4(0, 0, 0, 0);
-            long long k = zpos + lane;
-            for (; k + 96 < e; k += 128) {
-                zbase[k] = z4; zbase[k + 32] = z4; zbase[k + 64] = z4; zbase[k + 96] = z4;
-            }
-            for (; k < e; k += 32) zbase[k] = z4;
-            zpos = e;
-        };
+        // grid of the current system (reloaded only when the system changes)
+        int s_cur = -1, cpd0 = 1, cpd1 = 1, cpd2 = 1, R0 = 0, R1 = 0, R2 = 0, pb0 = 0, pb1 = 0, pb2 = 0, coff = 0;
+        bool zeroing = zpieces > 0;
         for (;;) {
             // ---- 1. prepare the next cell entirely in registers (dependent global loads, image enumeration, shift
-            //         sort) BEFORE waiting for a ring stage: after the consumers release a stage only the table
-            //         writes and the TMA issue remain on the critical path ----
+            //         sort, aligned layout) BEFORE waiting for ring space ----
             bool have = false;
-            int g = 0, home_start = 0, ntarget = 0, st = 0, cn = 0, key = kKeyEmpty, off = 0, total = 0, nseg = 1;
-            int home_off = 0, si = 0;
-            unsigned shiftmask = 0u;
-            bool head = false;
+            int g = 0, ntarget = 0, st = 0, cn = 0, key = kKeyEmpty, aoff = 0, total = 0, nseg = 1, nvc = 0;
+            int home_slot = 0, si = 0, seg_len = 0, seg_vcb = 0, seg_nch = 0, grp_cn = 0;
+            unsigned shiftmask = 0u, hm = 1u;
+            bool head_lane = false;
             T Sx = (T)0, Sy = (T)0, Sz = (T)0;
             for (;;) {
                 g = __shfl_sync(0xffffffffu, g_next, 0);
                 if (g >= total_cells) break;
                 if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
-                home_start = cell_start[g];
+                const int home_start = cell_start[g];
                 ntarget = cell_start[g + 1] - home_start;
                 if (ntarget == 0) continue;
                 int s = 0;
-                if (a.num_systems > 1) s = a.batch_idx[sorted[home_start].j];
+                if (a.num_systems > 1) {
+                    s = a.batch_idx[sorted[home_start].j];
+                    s = s < 0 ? 0 : (s >= a.num_systems ? a.num_systems - 1 : s);   // (k_hash reported the error)
+                }
                 const SysParams& sp = sys[s];
-                const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
-                const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];
+                if (s != s_cur) {
+                    s_cur = s;
+                    cpd0 = sp.cpd[0]; cpd1 = sp.cpd[1]; cpd2 = sp.cpd[2];
+                    R0 = sp.R[0]; R1 = sp.R[1]; R2 = sp.R[2];
+                    pb0 = sp.pbc[0]; pb1 = sp.pbc[1]; pb2 = sp.pbc[2];
+                    coff = sp.cell_offset;
+                }
                 const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
                 const int nimg = nx * ny * nzz;
-                bool ok = nimg <= 32 && ntarget <= kFastMaxTargets;
+                bool ok = nimg <= 32;
                 int tag = 0;
                 st = 0; cn = 0; key = kKeyEmpty;
-                const int coff = sp.cell_offset;
                 if (ok && lane < nimg) {
                     const int local = g - coff;
                     const int cx = local % cpd0, cy = (local / cpd0) % cpd1, cz = local / (cpd0 * cpd1);
-                    const int dx = lane % nx - R0, dy = (lane / nx) % ny - R1, dz = lane / (nx * ny) - R2;
+                    int dx, dy, dz;
+                    const bool r111 = R0 == 1 && R1 == 1 && R2 == 1;   // the common 3 x 3 x 3 stencil
+                    if (r111) { dx = lane % 3 - 1; dy = (lane / 3) % 3 - 1; dz = lane / 9 - 1; }
+                    else { dx = lane % nx - R0; dy = (lane / nx) % ny - R1; dz = lane / (nx * ny) - R2; }
                     int tx = cx + dx, ty = cy + dy, tz = cz + dz;
                     bool in = true;
                     int csx = 0, csy = 0, csz = 0;
-                    if (sp.pbc[0]) divmod_floor(tx, cpd0, csx, tx); else in = in && tx >= 0 && tx < cpd0;
-                    if (sp.pbc[1]) divmod_floor(ty, cpd1, csy, ty); else in = in && ty >= 0 && ty < cpd1;
-                    if (sp.pbc[2]) divmod_floor(tz, cpd2, csz, tz); else in = in && tz >= 0 && tz < cpd2;
+                    if (r111) {
+                        // |d| <= 1 in every dimension: one conditional wrap instead of a division
+                        if (pb0) { if (tx < 0) { tx += cpd0; csx = -1; } else if (tx >= cpd0) { tx -= cpd0; csx = 1; } }
+                        else in = in && tx >= 0 && tx < cpd0;
+                        if (pb1) { if (ty < 0) { ty += cpd1; csy = -1; } else if (ty >= cpd1) { ty -= cpd1; csy = 1; } }
+                        else in = in && ty >= 0 && ty < cpd1;
+                        if (pb2) { if (tz < 0) { tz += cpd2; csz = -1; } else if (tz >= cpd2) { tz -= cpd2; csz = 1; } }
+                        else in = in && tz >= 0 && tz < cpd2;
+                    } else {
+                        if (pb0) divmod_floor(tx, cpd0, csx, tx); else in = in && tx >= 0 && tx < cpd0;
+                        if (pb1) divmod_floor(ty, cpd1, csy, ty); else in = in && ty >= 0 && ty < cpd1;
+                        if (pb2) divmod_floor(tz, cpd2, csz, tz); else in = in && tz >= 0 && tz < cpd2;
+                    }
                     if (in) {
                         const int gc = coff + tx + cpd0 * (ty + cpd1 * tz);
                         st = cell_start[gc];
@@ -506,35 +596,38 @@ __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
                     __syncwarp();
                 }
                 const int incl = warp_incl_scan(cn, lane);
-                off = incl - cn;
+                const int off = incl - cn;            // dense offset of this image
                 total = __shfl_sync(0xffffffffu, incl, 31);
-                ok = ok && total <= cap;
-                // segments = runs of equal shift among the non-empty images (sorted by shift above)
                 nseg = 1;
-                head = false;
-                unsigned hm = 0u;
-                if (shiftmask) {
+                hm = 1u;
+                head_lane = lane == 0;
+                if (!shiftmask) {
+                    // interior cell: one zero-shift segment, chunk count padded to an even number (two chunks per trip)
+                    aoff = off;
+                    nvc = ((total + 63) >> 6) << 1;
+                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0;
+                } else {
+                    // segments = runs of equal shift among the non-empty images; each starts on a 32-slot boundary
                     const int pk = __shfl_up_sync(0xffffffffu, key, 1);
-                    head = cn > 0 && (lane == 0 || pk != key);
-                    hm = __ballot_sync(0xffffffffu, head);
+                    head_lane = cn > 0 && (lane == 0 || pk != key);
+                    hm = __ballot_sync(0xffffffffu, head_lane);
                     nseg = __popc(hm);
-                    ok = ok && nseg <= kRowsMaxSeg;  // a list entry has 3 bits for the segment (boxes < 3 cells wide: general kernel)
-                }
-                if (!ok) {
-                    // leave the cell to the general kernel as work items of kDeferTargets target atoms
-                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
-                    int base = 0;
-                    if (lane == 0) {
-                        base = atomicAdd(&ctrl->n_deferred, nitems);
-                        ctrl->had_deferred = 1;
-                    }
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
-                    continue;
-                }
-                if (shiftmask) {
-                    if (head) {
-                        si = __popc(hm & ((1u << lane) - 1u));
+                    const unsigned le = 0xffffffffu >> (31 - lane);                 // lanes <= me
+                    const int hl = 31 - __clz((int)(hm & le) | 1);                  // head lane of my segment
+                    const unsigned gt = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+                    const unsigned nh = hm & gt;                                    // heads after me
+                    const int nhl = nh ? __ffs((int)nh) - 1 : 31;
+                    const int off_next = __shfl_sync(0xffffffffu, off, nhl);
+                    seg_len = head_lane ? ((nh ? off_next : total) - off) : 0;
+                    seg_nch = (seg_len + 31) >> 5;
+                    const int vincl = warp_incl_scan(seg_nch, lane);
+                    seg_vcb = vincl - seg_nch;
+                    nvc = __shfl_sync(0xffffffffu, vincl, 31);
+                    si = __popc(hm & le) - 1;
+                    const int seg_off = __shfl_sync(0xffffffffu, off, hl);
+                    const int seg_slot = __shfl_sync(0xffffffffu, seg_vcb, hl) << 5;
+                    aoff = seg_slot + (off - seg_off);
+                    if (head_lane) {
                         int csx, csy, csz;
                         unpack_key(key, csx, csy, csz);
                         T cm[9];
@@ -543,125 +636,163 @@ __global__ void __launch_bounds__(kRowsThreads, MINB) k_rows(const RowsArgs a) {
                         shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
                     }
                 }
+                ok = ok && nvc <= kRowsMaxVC && nseg <= kRowsMaxSeg;
+                if (!ok) {
+                    // leave the cell to the general kernel as work items of kDeferTargets target atoms; its atoms have
+                    // no temporary row
+                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
+                    int base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(&ctrl->n_deferred, nitems);
+                        ctrl->had_deferred = 1;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
+                    for (int k = lane; k < ntarget; k += 32) row_ref[sorted[home_start + k].j] = -1;
+                    continue;
+                }
                 const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
                 const int home_lane = __ffs(tagm) - 1;
-                home_off = __shfl_sync(0xffffffffu, off, home_lane);
+                home_slot = __shfl_sync(0xffffffffu, aoff, home_lane);
+                // copy groups: images whose source runs AND destinations are contiguous (x-adjacent cells of one
+                // stencil row) go as ONE bulk copy, issued by the first lane of the group
+                {
+                    const int pe_src = __shfl_up_sync(0xffffffffu, st + cn, 1);
+                    const int pe_dst = __shfl_up_sync(0xffffffffu, aoff + cn, 1);
+                    const bool cont = lane > 0 && st == pe_src && aoff == pe_dst;
+                    const unsigned gh = __ballot_sync(0xffffffffu, !cont);                 // group heads
+                    const unsigned gt2 = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+                    const unsigned ngh = gh & gt2;
+                    const int last = ngh ? __ffs((int)ngh) - 2 : 31;                        // last lane of my group
+                    const int incl_last = __shfl_sync(0xffffffffu, incl, last);
+                    grp_cn = cont ? 0 : incl_last - off;
+                }
                 have = true;
                 break;
             }
-            if (zpos < zend) zero_some(have ? zquota : zend - zpos);
-            // ---- 2. wait until the consumers have released this ring stage, then publish the tables and issue the copies ----
-            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.empty[stage]), ephase);
-            FastStage<T>& sg = sm.stage[stage];
+            // ---- 2. descriptor slot + ring space (FIFO release; the wait is spent zero-filling), then publish the tables
+            //         and issue the copies ----
+            const int dslot = nprod % kRowsDesc;
+            const int bytes = have ? nvc * 32 * (int)RS : 0;
+            int foot, data_off;
+            for (;;) {
+                foot = bytes; data_off = head;
+                if (head + bytes > kRowsRingBytes) { foot += kRowsRingBytes - head; data_off = 0; }   // wrap: the tail fragment is charged to this tile
+                if (nprod - oldest < kRowsDesc && used + foot <= kRowsRingBytes) break;
+                const int os = oldest % kRowsDesc;
+                uint64_t* eb = reinterpret_cast<uint64_t*>(&sm.empty[os]);
+                const uint32_t ep = (uint32_t)((oldest / kRowsDesc) & 1);
+                while (zeroing && !mbar_test(eb, ep)) zeroing = zero_piece();
+                mbar_wait_backoff(eb, ep);
+                used -= sm.desc[os].footprint;
+                ++oldest;
+                if (oldest == nprod) { head = 0; used = 0; }   // ring drained: start over at its beginning
+            }
+            RowsDesc& ds = sm.desc[dslot];
             if (!have) {
                 if (lane == 0) {
-                    sg.item = -1;
-                    mbar_arrive(reinterpret_cast<uint64_t*>(&sm.full[stage]));
+                    ds.item = -1;
+                    ds.footprint = 0;
+                    mbar_arrive(reinterpret_cast<uint64_t*>(&sm.full[dslot]));
                 }
                 break;
             }
-            Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw + (size_t)stage * kStageBytes);
-            if (shiftmask) {
-                if (head) {
-                    sg.seg_begin[si] = off;
-                    sg.seg_key[si] = key;
-                    sg.segS[3 * si] = Sx; sg.segS[3 * si + 1] = Sy; sg.segS[3 * si + 2] = Sz;
-                }
-                if (lane == 0) sg.seg_begin[nseg] = total;
-            } else {
-                if (lane == 0) { sg.seg_begin[0] = 0; sg.seg_begin[1] = total; sg.seg_key[0] = 0; }
-                if (lane < 3) sg.segS[lane] = (T)0;
-            }
-            __syncwarp();
-            const int nchunks = (total + 31) >> 5;
-            bool uni_chunk = false;
-            if (lane < nchunks) {
-                int sgi = 0;
-                while (sgi + 1 < nseg && (lane << 5) >= sg.seg_begin[sgi + 1]) ++sgi;
-                sg.chunk_seg[lane] = sgi;
-                if (UNI) {
-                    const int last = (lane << 5) + 31;
-                    uni_chunk = last < total && (sgi + 1 >= nseg || last < sg.seg_begin[sgi + 1]);
-                }
-            }
-            if (UNI) {
-                const unsigned umask = __ballot_sync(0xffffffffu, uni_chunk);
-                if (lane == 0) sg.qrow[0] = (int)umask;  // (qrow is unused on this path)
+            used += foot;
+            head = data_off + bytes;
+            const uint32_t tile_addr = ring_addr + (uint32_t)data_off;
+            if (head_lane) {
+                ds.seg_vc[si] = seg_vcb;
+                ds.seg_key[si] = shiftmask ? key : 0;
+                ds.segS[si][0] = Sx; ds.segS[si][1] = Sy; ds.segS[si][2] = Sz; ds.segS[si][3] = (T)0;
             }
             if (lane == 0) {
-                sg.nchunks = nchunks;
-                sg.item = g; sg.ntarget = ntarget; sg.home_start = home_start; sg.home_off = home_off;
-                sg.nseg = nseg; sg.total = total; sg.next_target = 0;
+                ds.seg_vc[nseg] = nvc;
+                ds.item = g; ds.ntarget = ntarget; ds.home_slot = home_slot; ds.nseg = nseg; ds.nvc = nvc;
+                ds.data_off = data_off; ds.shifted = shiftmask ? 1 : 0; ds.next_target = 0; ds.footprint = foot;
+            }
+            // sentinel records behind every segment (up to its padded end) and the chunk -> segment table
+            {
+                int myseg0 = 0, myseg1 = 0;
+                unsigned rest = hm;
+                while (rest) {
+                    const int h = __ffs((int)rest) - 1;
+                    rest &= rest - 1u;
+                    const int vb = __shfl_sync(0xffffffffu, seg_vcb, h), nch = __shfl_sync(0xffffffffu, seg_nch, h);
+                    const int len = __shfl_sync(0xffffffffu, seg_len, h), sidx = __shfl_sync(0xffffffffu, si, h);
+                    if (lane >= vb && lane < vb + nch) myseg0 = sidx;
+                    if (lane + 32 >= vb && lane + 32 < vb + nch) myseg1 = sidx;
+                    const int gb = (vb << 5) + len, ge = (vb + nch) << 5;     // < 64 slots
+                    for (int q = gb + lane; q < ge; q += 32)
+                        sts_rec(tile_addr + (uint32_t)q * RS, kRowsFar, kRowsFar, kRowsFar, -1);
+                }
+                if (shiftmask) {
+                    ds.vc_seg[lane] = (unsigned char)myseg0;
+                    ds.vc_seg[lane + 32] = (unsigned char)myseg1;
+                }
             }
             const uint32_t tx = (uint32_t)total * RS;
-            __syncwarp();  // every lane's table writes precede lane 0's release-arrive below
-            if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[stage]), tx);
+            __syncwarp();  // every lane's table / sentinel writes precede lane 0's release-arrive below
+            if (lane == 0) mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.full[dslot]), tx);
             __syncwarp();
-            if (cn > 0)
-                tma_load_1d(cand + off, sorted + st, (uint32_t)cn * RS, reinterpret_cast<uint64_t*>(&sm.full[stage]));
-            if (++stage == STAGES) { stage = 0; ephase ^= 1u; }
+            if (grp_cn > 0)
+                tma_load_1d(smem_raw + data_off + (size_t)aoff * RS, sorted + st, (uint32_t)grp_cn * RS,
+                            reinterpret_cast<uint64_t*>(&sm.full[dslot]));
+            ++nprod;
         }
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
         if (lane == 0) {
             __threadfence();
-            const int d = atomicAdd(&ctrl->done[0], 1);
-            if (d == (int)gridDim.x - 1) {
+            const int dn = atomicAdd(&ctrl->done[0], 1);
+            if (dn == (int)gridDim.x - 1) {
                 ctrl->work_counter[0] = 0;
                 ctrl->done[0] = 0;
             }
         }
     } else {
         // =========================== consumers ===========================
-        const int cw = warp - 1;
         int* rows = reinterpret_cast<int*>(a.ws + a.L.rows);
         int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
-        const uint32_t lbaseA = smem_u32(&sm.lists[cw][0][0]) + (uint32_t)lane;
-        const uint32_t lbaseB = smem_u32(&sm.lists[cw][1][0]) + (uint32_t)lane;
         RowsAlloc al;
         al.pos = al.end = 0;
         const float rc2 = a.cutoff_sq;
-        int stage = 0;
-        uint32_t fphase = 0;
-        for (;;) {
-            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.full[stage]), fphase);
-            FastStage<T>& sg = sm.stage[stage];
-            if (sg.item < 0) break;
-            const uint32_t cand_addr = smem_base + (uint32_t)stage * kStageBytes;
-            const int ntarget = sg.ntarget, home_off = sg.home_off;
-            const bool shifted = sg.nseg > 1 || sg.seg_key[0] != 0;
+        for (int ncons = 0;; ++ncons) {
+            const int dslot = ncons % kRowsDesc;
+            mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.full[dslot]), (uint32_t)((ncons / kRowsDesc) & 1));
+            RowsDesc& ds = sm.desc[dslot];
+            if (ds.item < 0) break;
+            const uint32_t tile_addr = ring_addr + (uint32_t)ds.data_off;
+            const int ntarget = ds.ntarget, home_slot = ds.home_slot;
+            const bool big = ds.nvc > 32;   // (rare: tiles of more than 1024 slots need a second mask word)
             for (;;) {
-                // two targets per trip: they share every candidate load and every FP instruction (f32x2)
-                int t = 0;
-                if (lane == 0) t = atomicAdd(&sg.next_target, 2);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (t >= ntarget) break;
-                const bool two = t + 1 < ntarget;
-                const int selfA = home_off + t, selfB = two ? selfA + 1 : selfA;
-                float xa, ya, za, xb, yb, zb;
-                int iA, iB;
-                lds_rec(cand_addr + (uint32_t)selfA * RS, xa, ya, za, iA);
-                lds_rec(cand_addr + (uint32_t)selfB * RS, xb, yb, zb, iB);
-                // x + (-0) == x bit for bit: one packed add gives each target pair a home in an aligned register pair
-                const f32x2_t nz = pack2(-0.0f, -0.0f);
-                const f32x2_t XI = add2(pack2(xa, xb), nz), YI = add2(pack2(ya, yb), nz), ZI = add2(pack2(za, zb), nz);
-                uint32_t la = lbaseA, lb = lbaseB;
-                rows_sweep2<HALF, FMA, UNI>(sg, cand_addr, XI, YI, ZI, iA, iB, rc2, lane, selfA, selfB, la, lb);
-                rows_emit2<HALF, PAD>(a, sg, ctrl, cand_addr, lbaseA, lbaseB, la, lb, selfA, selfB, iA, iB, two, lane, shifted, al,
-                                 rows, row_ref);
+                int t0 = 0;
+                if (lane == 0) t0 = atomicAdd(&ds.next_target, 4);
+                t0 = __shfl_sync(0xffffffffu, t0, 0);
+                if (t0 >= ntarget) break;
+                const int nt = ntarget - t0 < 4 ? ntarget - t0 : 4;
+                if (big)
+                    rows_trip<HALF, FMA, true>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
+                else
+                    rows_trip<HALF, FMA, false>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[stage]));
-            if (++stage == STAGES) { stage = 0; fphase ^= 1u; }
+            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[dslot]));
         }
     }
+    // whatever is left of this CTA's zero-fill slice
+    if (zpieces > 0)
+        while (zero_piece()) {}
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_rows_out: the final arrays in atom-index order.  One warp per 32 consecutive atoms; rows come from the temporary
-// buffer (row_ref), everything written is sequential in the large: out_i (= i), out_j, shifts (zeros unless the row's
-// cell touched a periodic boundary, then the packed image keys stored behind the row are unpacked).
+// k_rows_out: the final arrays in atom-index order.  One warp per 32 consecutive atoms: every lane issues ONE TMA bulk
+// copy that brings its atom's temporary row into the warp's shared-memory staging buffer (as many rows per batch as
+// fit), then the warp writes out_i (= i), out_j and, for rows of cells at a periodic boundary, the shifts unpacked from
+// the image keys in front of the row — all strictly sequential in the large.
 // Atoms with row_ref < 0 were handled by the general kernel, which writes their rows itself.
 // ------------------------------------------------------------------------------------------------
+constexpr int kOutWarps = 8;
+constexpr int kOutCap = 2048;   // staging entries per warp (8 KB)
+
 __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int value, int lane) {
     int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
     head = head < n ? head : n;
@@ -674,14 +805,55 @@ __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int valu
     if (lane < tail) dst[head + 4 * nv + lane] = value;
 }
 
-// SPEC (experiment): launched BEFORE the host knows the pair count, into buffers sized from a guess — the kernel reads
-// the count itself, places row 1 of edge_index behind it, and does nothing if the guess was too small or the query was
-// served by the two-pass kernels (the host then repeats the fill the regular way).
+struct RowsOutSmem {
+    alignas(128) int buf[kOutWarps][kOutCap];
+    unsigned long long bar[kOutWarps];
+};
+
+// writes one row (already in shared or global memory at `row`, header of `hdr` keys in front of it)
+__device__ __forceinline__ void rows_out_row(const int* row, int hdr, int cnt, int iv, int index_offset, int shifts_zeroed,
+                                             int* __restrict__ oi, int* __restrict__ oj, int* __restrict__ sh, int lane) {
+    if (hdr == 0) {
+        for (int k = lane; k < cnt; k += 32) {
+            oj[k] = row[k] + index_offset;
+            oi[k] = iv;
+        }
+        if (!shifts_zeroed) warp_fill(sh, 3 * cnt, 0, lane);
+    } else {
+        const int keyl = lane < hdr ? row[lane - hdr] : 0;
+        if (!shifts_zeroed) {
+            warp_fill(sh, 3 * cnt, 0, lane);
+            __syncwarp();  // the zeros of other lanes precede the image shifts written below
+        }
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
+            const int e = k < cnt ? row[k] : 0;
+            const int key = __shfl_sync(0xffffffffu, keyl, ((unsigned)e >> kRowsSegShift) & 31);
+            if (k < cnt) {
+                oj[k] = (e & ((1 << kRowsSegShift) - 1)) + index_offset;
+                oi[k] = iv;
+                if (key != 0) {
+                    int csx, csy, csz;
+                    unpack_key(key, csx, csy, csz);
+                    sh[3 * k] = csx;
+                    sh[3 * k + 1] = csy;
+                    sh[3 * k + 2] = csz;
+                }
+            }
+        }
+    }
+}
+
+// SPEC: launched BEFORE the host knows the pair count, into buffers sized from a guess — the kernel reads the count
+// itself, places row 1 of edge_index behind it, and does nothing if the guess was too small or the query was served by
+// the two-pass kernels (the host then repeats the fill the regular way).
 template <bool SPEC>
-__global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
-                                                     const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
-                                                     int* __restrict__ out_j_arg, int* __restrict__ out_shifts,
-                                                     int index_offset, int shifts_zeroed, long long spec_cap) {
+__global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
+                                                             const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
+                                                             int* __restrict__ out_j_arg, int* __restrict__ out_shifts,
+                                                             int index_offset, int shifts_zeroed, long long spec_cap) {
+    extern __shared__ __align__(128) unsigned char out_smem_raw[];
+    RowsOutSmem& sm = *reinterpret_cast<RowsOutSmem*>(out_smem_raw);
     int* __restrict__ out_j = out_j_arg;
     if (SPEC) {
         const Ctrl* ctrl = reinterpret_cast<const Ctrl*>(ws + L.ctrl);
@@ -691,94 +863,67 @@ __global__ void __launch_bounds__(256, 5) k_rows_out(const unsigned char* __rest
     }
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
     const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
-    const int lane = threadIdx.x & 31;
-    const long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-    if (base >= n) return;
-    const long long il = base + lane;
-    const int ref_l = il < n ? row_ref[il] : -1;
-    const int p_l = neighbor_ptr[il < n ? il : n];
-    const int pe_l = neighbor_ptr[il + 1 < n ? il + 1 : n];
-    const int na = n - base < 32 ? (int)(n - base) : 32;
-    // software pipeline: the row of atom t + 1 is in flight while atom t is written.  entries of a row start behind
-    // its header (boundary rows: kRowsMaxSeg image keys)
-    int ref = __shfl_sync(0xffffffffu, ref_l, 0);
-    int p = __shfl_sync(0xffffffffu, p_l, 0);
-    int cnt = __shfl_sync(0xffffffffu, pe_l, 0) - p;
-    int v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int k = lane + 32 * u;
-        v[u] = (ref >= 0 && k < cnt) ? rows[(ref >> 1) + ((ref & 1) ? kRowsMaxSeg : 0) + k] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar[warp]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
     }
-    for (int t = 0; t < na; ++t) {
-        int nref = -1, np = 0, ncnt = 0;
-        int nv[4] = {0, 0, 0, 0};
-        if (t + 1 < na) {
-            nref = __shfl_sync(0xffffffffu, ref_l, t + 1);
-            np = __shfl_sync(0xffffffffu, p_l, t + 1);
-            ncnt = __shfl_sync(0xffffffffu, pe_l, t + 1) - np;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = lane + 32 * u;
-                nv[u] = (nref >= 0 && k < ncnt) ? rows[(nref >> 1) + ((nref & 1) ? kRowsMaxSeg : 0) + k] : 0;
+    __syncwarp();
+    int* buf = sm.buf[warp];
+    uint32_t parity = 0;
+    const long long nwarps = (long long)gridDim.x * kOutWarps;
+    for (long long base = ((long long)blockIdx.x * kOutWarps + warp) * 32; base < n; base += nwarps * 32) {
+        const long long il = base + lane;
+        const int ref = il < n ? row_ref[il] : -1;
+        const int p = neighbor_ptr[il < n ? il : n];
+        const int cnt = neighbor_ptr[il + 1 < n ? il + 1 : n] - p;
+        const int na = n - base < 32 ? (int)(n - base) : 32;
+        const int flag = ref & 3;
+        const int hdr = ref < 0 ? 0 : (flag == 0 ? 0 : (flag == 1 ? 8 : 32));
+        const int clen = (ref < 0 || cnt == 0) ? 0 : hdr + ((cnt + 3) & ~3);      // entries to copy
+        const int* src = rows + (ref >> 2);
+        int s = 0;
+        while (s < na) {
+            const int v = lane >= s ? clen : 0;
+            const int incl = warp_incl_scan(v, lane);
+            const unsigned fit = __ballot_sync(0xffffffffu, lane >= s && lane < na && incl <= kOutCap);
+            // lanes [s, e) fit one batch (incl is monotone: the fitting lanes are a prefix)
+            const int e = s + __popc(fit);
+            if (e == s) {
+                // a single row longer than the staging buffer: straight from global memory
+                const int ref_t = __shfl_sync(0xffffffffu, ref, s), p_t = __shfl_sync(0xffffffffu, p, s);
+                const int cnt_t = __shfl_sync(0xffffffffu, cnt, s), hdr_t = __shfl_sync(0xffffffffu, hdr, s);
+                if (ref_t >= 0 && cnt_t > 0)
+                    rows_out_row(rows + (ref_t >> 2) + hdr_t, hdr_t, cnt_t, (int)(base + s) + index_offset, index_offset,
+                                 shifts_zeroed, out_i + (size_t)p_t, out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
+                ++s;
+                continue;
             }
-        }
-        if (ref >= 0 && cnt > 0) {
-            const int iv = (int)(base + t) + index_offset;
-            int* __restrict__ oj = out_j + (size_t)p;
-            int* sh = out_shifts + 3 * (size_t)p;
-            int* __restrict__ oi = out_i + (size_t)p;
-            if (!(ref & 1)) {
-                const int* __restrict__ row = rows + (ref >> 1);
-                int* __restrict__ ojl = oj + lane;   // per-lane bases: the four stores below differ by immediates only
-                int* __restrict__ oil = oi + lane;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (lane + 32 * u < cnt) {
-                        ojl[32 * u] = v[u] + index_offset;
-                        oil[32 * u] = iv;
-                    }
+            const int tot = __shfl_sync(0xffffffffu, incl, e - 1);
+            if (tot > 0) {
+                fence_proxy_async_smem();
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)tot * 4u);
+                __syncwarp();
+                if (lane >= s && lane < e && v > 0) tma_load_1d(buf + (incl - v), src, (uint32_t)v * 4u, bar);
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                for (int t = s; t < e; ++t) {
+                    const int cnt_t = __shfl_sync(0xffffffffu, cnt, t), v_t = __shfl_sync(0xffffffffu, v, t);
+                    if (v_t == 0) continue;
+                    const int off_t = __shfl_sync(0xffffffffu, incl, t) - v_t;
+                    const int p_t = __shfl_sync(0xffffffffu, p, t), hdr_t = __shfl_sync(0xffffffffu, hdr, t);
+                    rows_out_row(buf + off_t + hdr_t, hdr_t, cnt_t, (int)(base + t) + index_offset, index_offset, shifts_zeroed,
+                                 out_i + (size_t)p_t, out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
                 }
-                for (int k = 128 + lane; k < cnt; k += 32) {  // rows longer than 128 (rare)
-                    oj[k] = row[k] + index_offset;
-                    oi[k] = iv;
-                }
-                if (!shifts_zeroed) warp_fill(sh, 3 * cnt, 0, lane);
-            } else {
-                const int* __restrict__ hdr = rows + (ref >> 1);
-                const int* __restrict__ row = hdr + kRowsMaxSeg;
-                const int keyl = lane < kRowsMaxSeg ? hdr[lane] : 0;
-                if (!shifts_zeroed) {
-                    warp_fill(sh, 3 * cnt, 0, lane);
-                    __syncwarp();  // the zeros of other lanes precede the image shifts written below
-                }
-                auto emit = [&](int e, int k) {
-                    const int key = __shfl_sync(0xffffffffu, keyl, ((unsigned)e >> 28) & (kRowsMaxSeg - 1));
-                    if (k < cnt) {
-                        oj[k] = (e & 0x0fffffff) + index_offset;
-                        oi[k] = iv;
-                        if (key != 0) {
-                            int csx, csy, csz;
-                            unpack_key(key, csx, csy, csz);
-                            sh[3 * k] = csx;
-                            sh[3 * k + 1] = csy;
-                            sh[3 * k + 2] = csz;
-                        }
-                    }
-                };
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (32 * u < cnt) emit(v[u], 32 * u + lane);
-                for (int k0 = 128; k0 < cnt; k0 += 32) emit(k0 + lane < cnt ? row[k0 + lane] : 0, k0 + lane);
+                __syncwarp();   // every lane is done with the buffer before the next batch lands in it
             }
+            s = e;
         }
-        ref = nref; p = np; cnt = ncnt;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = nv[u];
     }
 }
 
-// resets the per-query state of the control block and marks every atom "no temporary row"
+// resets the per-query state of the control block
 __global__ void k_query_reset(unsigned char* __restrict__ ws, WsLayout L, long long n, int with_rows) {
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -787,10 +932,7 @@ __global__ void k_query_reset(unsigned char* __restrict__ ws, WsLayout L, long l
         ctrl->rows_cursor = 0ull;
         ctrl->rows_overflow = 0;
     }
-    if (with_rows) {
-        int* row_ref = reinterpret_cast<int*>(ws + L.row_ref);
-        for (long long i = gid; i < n; i += (long long)gridDim.x * blockDim.x) row_ref[i] = -1;
-    }
+    (void)n; (void)with_rows;
 }
 
 }  // namespace nvnl

@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a
         }
         // ---- system of this cell and its grid ----
         const int j0 = sorted[home_start].j;
-        const int s = a.batch_idx ? a.batch_idx[j0] : 0;
+        int s = a.batch_idx ? a.batch_idx[j0] : 0;
+        s = s < 0 ? 0 : (s >= a.num_systems ? a.num_systems - 1 : s);   // (k_hash reported the error)
         const SysParams& sp = sys[s];
         const int cpd0 = sp.cpd[0], cpd1 = sp.cpd[1], cpd2 = sp.cpd[2];
         const int R0 = sp.R[0], R1 = sp.R[1], R2 = sp.R[2];

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libnvalchemi_nl_b200.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 c_void_p, c_int, c_int32, c_int64, c_double, c_size_t = (
@@ -23,8 +23,11 @@ _SIGNATURES = {
     "nvnl_launch_count": (c_int64, []),
     "nvnl_set_rows_budget": (None, [c_int64, c_int64]),
     "nvnl_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
-    "nvnl_build": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double,
+    "nvnl_build": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int64,
                            c_void_p, c_size_t, c_void_p]),
+    "nvnl_import_cache": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "nvnl_count": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
                            c_void_p]),
     "nvnl_status": (c_int, [c_void_p, c_int, c_int64, c_int32, ctypes.POINTER(c_int64), ctypes.POINTER(c_int32),
@@ -44,6 +47,8 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "nvnl_refresh_positions": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p]),
     "nvnl_cells_changed": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nvnl_cells_changed_cache": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "nvnl_moved_beyond": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_double, c_void_p, c_void_p]),
     "nvnl_get_grid": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "nvnl_unpack_gathered": (c_int, [c_void_p, c_int32, c_int64, c_int64, ctypes.POINTER(c_int64), c_void_p, c_int64,

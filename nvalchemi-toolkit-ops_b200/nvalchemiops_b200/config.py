@@ -24,3 +24,9 @@ prezero_min_pairs: int = 1_000_000   # below this the extra launch + event cost 
 # edge_index buffer of the guessed size (nvnl_fill_rows_speculative); the host then only creates the views.  Removes the
 # ~25 us the GPU idles at the sync.  Compiled and covered by host-logic tests, not yet measured on hardware.
 speculative_fill: bool = False
+
+# Debug: validate inputs on the padded-matrix path too.  That path is sync-free (CUDA-graph capturable) and therefore
+# does not read the device error word: an out-of-range batch_idx is clamped to a valid system, a search radius of 64+
+# cells is truncated, a singular cell yields an empty list — the COO path raises ValueError for all three.  True = one
+# host sync per matrix query to raise the same errors.
+check_inputs: bool = False

@@ -9,6 +9,7 @@ from .neighbor_utils import (
     estimate_max_neighbors,
     get_neighbor_list_from_neighbor_matrix,
 )
+from . import ops  # noqa: F401  (registers the torch custom ops)
 from .neighborlist import neighbor_list
 from .rebuild_detection import (cell_list_needs_rebuild, check_cell_list_rebuild_needed,
                                 check_neighbor_list_rebuild_needed, neighbor_list_needs_rebuild)

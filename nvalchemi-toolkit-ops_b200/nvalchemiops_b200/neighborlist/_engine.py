@@ -19,6 +19,7 @@ ERR_MESSAGES = {
     1: "an atom lies more than 1e6 periodic images from the cell, or the search radius exceeds 63 cells",
     2: "batch_idx contains a system index outside [0, num_systems)",
     4: "a cell matrix is singular",
+    8: "the cell-list cache tensors are inconsistent (they were not produced by build_cell_list of this package)",
 }
 
 
@@ -67,8 +68,9 @@ def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def build(positions, cutoff, cell, pbc, batch_idx=None, batch_ptr=None, workspace=None) -> CellListHandle:
-    """Grid + hash + counting sort (nvnl_build).  ``cell`` [S,3,3], ``pbc`` [S,3] bool."""
+def build(positions, cutoff, cell, pbc, batch_idx=None, batch_ptr=None, workspace=None, max_cells=0) -> CellListHandle:
+    """Grid + hash + counting sort (nvnl_build).  ``cell`` [S,3,3], ``pbc`` [S,3] bool.  ``max_cells`` > 0 caps the
+    grid at the capacity of a caller-provided reference-shaped cache (see include/nvalchemi_nl_b200.h)."""
     _require_cuda(positions, "positions")
     code = _dtype_code(positions.dtype)
     if positions.ndim != 2 or positions.shape[1] != 3:
@@ -98,12 +100,81 @@ def build(positions, cutoff, cell, pbc, batch_idx=None, batch_ptr=None, workspac
     with torch.cuda.device(dev):
         _lib.check(
             L.nvnl_build(_ptr(positions), code, n, _ptr(cell), _ptr(pbc_u8), _ptr(batch_idx), _ptr(batch_ptr), ns,
-                         float(cutoff), _ptr(workspace), workspace.numel(), _stream(dev)),
+                         float(cutoff), int(max_cells), _ptr(workspace), workspace.numel(), _stream(dev)),
             "nvnl_build",
         )
     # keep the inputs alive until the stream has consumed them
     workspace._nvnl_keepalive = (positions, cell, pbc_u8, batch_idx, batch_ptr)
     return CellListHandle(workspace, code, n, ns, batch_idx, positions.dtype, dev, float(cutoff))
+
+
+def import_cache(positions, cutoff, cell, pbc, batch_idx, cells_per_dimension, neighbor_search_radius,
+                 atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                 cell_atom_list) -> CellListHandle:
+    """Rebuild a workspace from the VALUES of the seven reference-shaped cache tensors and the current positions
+    (nvnl_import_cache) — the query side of the split build/query workflow, no hidden state."""
+    _require_cuda(positions, "positions")
+    code = _dtype_code(positions.dtype)
+    n, dev = positions.shape[0], positions.device
+    positions = positions.contiguous()
+    cell = cell.to(device=dev, dtype=positions.dtype).reshape(-1, 3, 3).contiguous()
+    ns = cell.shape[0]
+    pbc_u8 = pbc.to(device=dev).reshape(-1, 3).to(torch.uint8).contiguous()
+    if pbc_u8.shape[0] != ns:
+        raise ValueError(f"pbc has {pbc_u8.shape[0]} systems but cell has {ns}")
+    if batch_idx is not None:
+        batch_idx = batch_idx.to(device=dev, dtype=torch.int32).contiguous()
+    elif ns > 1:
+        raise ValueError("batch_idx is required when more than one cell is given")
+    cache = [cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+             atoms_per_cell_count, cell_atom_start_indices, cell_atom_list]
+    for k, t in enumerate(cache):
+        if t.dtype != torch.int32 or t.device != dev:
+            raise ValueError("cell-list cache tensors must be int32 tensors on the positions' device")
+        cache[k] = t.contiguous()
+    if cache[0].numel() != 3 * ns or cache[2].numel() != 3 * n or cache[3].numel() != 3 * n or cache[6].numel() != n:
+        raise ValueError("cell-list cache tensors do not match (total_atoms, num_systems)")
+    rad = cache[1] if cache[1].numel() == 3 * ns else None
+    ncache = min(cache[4].numel(), cache[5].numel())
+    L = _lib.lib()
+    nbytes = int(L.nvnl_workspace_bytes(n, ns, code))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            L.nvnl_import_cache(_ptr(positions), code, n, _ptr(cell), _ptr(pbc_u8), _ptr(batch_idx), ns, float(cutoff),
+                                _ptr(cache[0]), _ptr(rad), _ptr(cache[2]), _ptr(cache[3]), _ptr(cache[4]), _ptr(cache[5]),
+                                ncache, _ptr(cache[6]), _ptr(ws), ws.numel(), _stream(dev)),
+            "nvnl_import_cache",
+        )
+    ws._nvnl_keepalive = (positions, cell, pbc_u8, batch_idx, cache)
+    return CellListHandle(ws, code, n, ns, batch_idx, positions.dtype, dev, float(cutoff))
+
+
+def cells_changed_cache(positions, cell, pbc, batch_idx, cells_per_dimension, atom_to_cell_mapping) -> torch.Tensor:
+    """int32 device flag [1]: 1 if any atom's cell on the cached grid differs from ``atom_to_cell_mapping``
+    (nvnl_cells_changed_cache; stateless)."""
+    _require_cuda(positions, "current_positions")
+    code = _dtype_code(positions.dtype)
+    n, dev = positions.shape[0], positions.device
+    positions = positions.contiguous()
+    cell = cell.to(device=dev, dtype=positions.dtype).reshape(-1, 3, 3).contiguous()
+    ns = cell.shape[0]
+    pbc_u8 = pbc.to(device=dev).reshape(-1, 3).to(torch.uint8).contiguous()
+    cpd = cells_per_dimension.to(device=dev, dtype=torch.int32).reshape(-1, 3).contiguous()
+    amap = atom_to_cell_mapping.to(device=dev, dtype=torch.int32).contiguous()
+    if cpd.shape[0] != ns or pbc_u8.shape[0] != ns or amap.numel() != 3 * n:
+        raise ValueError("cells_per_dimension / pbc / atom_to_cell_mapping do not match (total_atoms, num_systems)")
+    if batch_idx is not None:
+        batch_idx = batch_idx.to(device=dev, dtype=torch.int32).contiguous()
+    elif ns > 1:
+        raise ValueError("batch_idx is required when more than one cell is given")
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.nvnl_cells_changed_cache(_ptr(positions), code, n, _ptr(cell), _ptr(pbc_u8), _ptr(batch_idx), ns,
+                                              _ptr(cpd), _ptr(amap), _ptr(flag), _stream(dev)),
+                   "nvnl_cells_changed_cache")
+    return flag
 
 
 def _raise_on_error_bits(bits: int):
@@ -142,6 +213,10 @@ def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_
     if neighbor_matrix.shape[0] != h.n or neighbor_matrix_shifts.shape[:2] != (h.n, M) or num_neighbors.shape[0] != h.n:
         raise ValueError("output tensors do not match (total_atoms, max_neighbors)")
     L = _lib.lib()
+    if config.check_inputs:
+        # debug switch: the padded-matrix path is sync-free and does not read the device error word by default
+        # (an out-of-range batch_idx is clamped, an over-long search radius truncated); this costs one host sync
+        _raise_on_error_bits(status(h)[3])
     with torch.cuda.device(h.device):
         _lib.check(
             L.nvnl_fill_matrix(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
@@ -156,7 +231,7 @@ def use_rows(h: CellListHandle) -> bool:
     """fp32 inputs take the single-sweep COO path unless config.coo_path says otherwise."""
     if config.coo_path not in ("rows", "masks"):
         raise ValueError(f"config.coo_path must be 'rows' or 'masks', not {config.coo_path!r}")
-    return config.coo_path == "rows" and h.dtype == torch.float32 and h.n < (1 << 28)
+    return config.coo_path == "rows" and h.dtype == torch.float32 and h.n < (1 << 27)
 
 
 # Pair count of the last COO query per (device, atoms, systems, cutoff^2, half_fill): lets the next query with the same

@@ -7,22 +7,19 @@ from __future__ import annotations
 import torch
 
 from . import _engine
-from .cell_list import _attach, _find_handle, _run
+from .cell_list import _CACHE_KEYS, _estimate_grid, _run
 
 
 def estimate_batch_cell_list_sizes(cell: torch.Tensor, pbc: torch.Tensor, cutoff: float, max_nbins: int = 1000):
-    """Signature of batch_cell_list.py:659-736; see ``estimate_cell_list_sizes`` for what it means here."""
-    from .cell_list import estimate_cell_list_sizes
-
+    """``(max_total_cells, neighbor_search_radius [S,3] int32)`` — batch_cell_list.py:659-736: every system's grid is
+    halved until it has at most ``max_nbins`` cells, the counts are summed.  One ``.item()`` sync for the whole batch
+    (no per-system sync).  See ``estimate_cell_list_sizes`` for how the result is used."""
     ns = cell.shape[0]
     if ns == 0 or cutoff <= 0:
         return 1, torch.zeros((ns, 3), device=cell.device, dtype=torch.int32)
-    total, radii = 0, []
-    for s in range(ns):
-        n, r = estimate_cell_list_sizes(cell[s], pbc[s], cutoff, max_nbins)
-        total += min(n, max_nbins)
-        radii.append(r)
-    return total, torch.stack(radii).to(cell.device)
+    _engine._dtype_code(cell.dtype)
+    cells, radius = _estimate_grid(cell, pbc, cutoff, max_nbins)
+    return int(cells.sum().item()), radius
 
 
 def batch_cell_list(
@@ -57,7 +54,8 @@ def batch_cell_list(
     empty_fill = -1  # batch_cell_list.py:1369
     if fill_value is None:
         fill_value = total_atoms
-    cache = {"cells_per_dimension": cells_per_dimension, "neighbor_search_radius": neighbor_search_radius}
+    cache = dict(zip(_CACHE_KEYS, (cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                                   atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)))
     return _run(positions, cutoff, cell.reshape(-1, 3, 3), pbc.reshape(-1, 3), batch_idx, batch_ptr, max_neighbors,
                 half_fill, fill_value, return_neighbor_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors,
                 cache, empty_fill=empty_fill)
@@ -66,14 +64,14 @@ def batch_cell_list(
 def batch_build_cell_list(positions, cutoff, cell, pbc, batch_idx, cells_per_dimension, neighbor_search_radius,
                           atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
                           cell_atom_list) -> None:
-    """Batched ``build_cell_list`` (reference batch_cell_list.py:1070-1135); see ``cell_list.build_cell_list``."""
-    if positions.shape[0] == 0 or cutoff <= 0:
-        return
-    h = _engine.build(positions, cutoff, cell.reshape(-1, 3, 3), pbc.reshape(-1, 3), batch_idx=batch_idx)
-    _engine.export_cache(h, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
-                         atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)
-    _attach(h, cells_per_dimension, atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count,
-            cell_atom_start_indices, cell_atom_list)
+    """Batched ``build_cell_list`` (reference batch_cell_list.py:1070-1135): every system's grid has at most
+    ``atoms_per_cell_count.numel() // num_systems`` cells (batch_cell_list.py:162-176)."""
+    from .ops import batch_build_cell_list_op
+
+    _engine._require_cuda(positions, "positions")
+    batch_build_cell_list_op(positions, float(cutoff), cell, pbc, batch_idx, cells_per_dimension, neighbor_search_radius,
+                             atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                             cell_atom_list)
 
 
 def batch_query_cell_list(positions, cell, pbc, cutoff, batch_idx, cells_per_dimension, neighbor_search_radius,
@@ -81,12 +79,9 @@ def batch_query_cell_list(positions, cell, pbc, cutoff, batch_idx, cells_per_dim
                           cell_atom_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, half_fill=False) -> None:
     """Batched ``query_cell_list`` — note the reference's argument order ``(positions, cell, pbc, cutoff, batch_idx, ...)``
     (batch_cell_list.py:1139-1144)."""
-    if positions.shape[0] == 0 or cutoff <= 0:
-        return
-    h = _find_handle(cell_atom_list, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
-                     atom_periodic_shifts, cells_per_dimension)
-    if cutoff > h.cutoff * (1.0 + 1e-12):
-        raise ValueError(f"query cutoff {cutoff} exceeds the cutoff {h.cutoff} the cell list was built for")
-    _engine.refresh_positions(h, positions)
-    _engine.query_matrix(h, _engine.cutoff_sq_in_dtype(cutoff, positions.dtype), neighbor_matrix, neighbor_matrix_shifts,
-                         num_neighbors, 0, half_fill, pad_rows=False)
+    from .ops import batch_query_cell_list_op
+
+    _engine._require_cuda(positions, "positions")
+    batch_query_cell_list_op(positions, cell, pbc, float(cutoff), batch_idx, cells_per_dimension, neighbor_search_radius,
+                             atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                             cell_atom_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, bool(half_fill))

@@ -39,9 +39,12 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
 
     if cutoff_sq is None:
         cutoff_sq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
-    want_cache = cache is not None and any(v is not None for v in cache.values())
+    # The reference uses caller-provided cache tensors only when ALL seven are given (cell_list.py:1376-1410): it
+    # zeroes them, builds into them and returns the same objects' contents.  Same here: the grid is then capped at
+    # their capacity and all seven are filled.  Otherwise the library sizes its own workspace.
+    full_cache = cache is not None and all(cache.get(k) is not None for k in _CACHE_KEYS)
     matrix_only = not (return_neighbor_list and neighbor_matrix is None)
-    if matrix_only and not want_cache:
+    if matrix_only and not full_cache:
         # padded-matrix outputs: one mutation-only custom op (torch.compile keeps it in the graph, no host sync)
         user_buffers = neighbor_matrix is not None and neighbor_matrix_shifts is not None and num_neighbors is not None
         if max_neighbors is None and not user_buffers:
@@ -63,13 +66,13 @@ def _run(positions, cutoff, cell, pbc, batch_idx, batch_ptr, max_neighbors, half
                 fill_value=fill_value,
             )
         return neighbor_matrix, num_neighbors, neighbor_matrix_shifts
-    h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
-    if want_cache:
-        cpd, rad = _engine.get_grid(h)
-        if cache.get("cells_per_dimension") is not None:
-            cache["cells_per_dimension"].copy_(cpd.reshape(cache["cells_per_dimension"].shape))
-        if cache.get("neighbor_search_radius") is not None:
-            cache["neighbor_search_radius"].copy_(rad.reshape(cache["neighbor_search_radius"].shape))
+    if full_cache:
+        tensors = [cache[k] for k in _CACHE_KEYS]
+        capacity = min(cache["atoms_per_cell_count"].numel(), cache["cell_atom_start_indices"].numel())
+        h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr, max_cells=capacity)
+        _engine.export_cache(h, *tensors)
+    else:
+        h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
     return _query(h, cutoff, cutoff_sq, max_neighbors, half_fill, fill_value, return_neighbor_list, neighbor_matrix,
                   neighbor_matrix_shifts, num_neighbors)
 
@@ -104,20 +107,46 @@ def _query(h, cutoff, cutoff_sq, max_neighbors, half_fill, fill_value, return_ne
     return neighbor_matrix, num_neighbors, neighbor_matrix_shifts
 
 
+def _estimate_grid(cell: torch.Tensor, pbc: torch.Tensor, cutoff: float, max_nbins: int):
+    """Per-system allocated cell count [S] (int64) and search radius [S,3] (int32) with the reference's arithmetic
+    (_estimate_cell_list_sizes, cell_list.py:35-99 / batch_cell_list.py:35-99): face distances from the adjugate
+    inverse in the input precision, cells per dimension = max(trunc(face / cutoff), 1), radius from the UN-halved grid,
+    then all dimensions halved until the product fits ``max_nbins``.  Tensor ops on the input device, no host sync."""
+    c = cell.reshape(-1, 3, 3)
+    a, b, cc = c[:, 0, 0], c[:, 0, 1], c[:, 0, 2]
+    d, e, f = c[:, 1, 0], c[:, 1, 1], c[:, 1, 2]
+    g, h, i = c[:, 2, 0], c[:, 2, 1], c[:, 2, 2]
+    det = a * (e * i - f * h) - b * (d * i - f * g) + cc * (d * h - e * g)
+    # columns of the inverse = rows of its transpose; face distance d = 1 / |row d of inverse^T|
+    col0 = torch.stack([e * i - f * h, f * g - d * i, d * h - e * g], dim=1)
+    col1 = torch.stack([cc * h - b * i, a * i - cc * g, b * g - a * h], dim=1)
+    col2 = torch.stack([b * f - cc * e, cc * d - a * f, a * e - b * d], dim=1)
+    inv_t = torch.stack([col0, col1, col2], dim=1) / det[:, None, None]
+    face = 1.0 / torch.linalg.vector_norm(inv_t, dim=2)
+    rc = torch.tensor(cutoff, dtype=cell.dtype, device=cell.device)
+    cpd = torch.clamp((face / rc).to(torch.int64), min=1)
+    open_single = (cpd == 1) & ~pbc.reshape(-1, 3).to(device=cell.device, dtype=torch.bool)
+    radius = torch.where(open_single, torch.zeros_like(cpd), torch.ceil(rc * cpd.to(cell.dtype) / face).to(torch.int64))
+    # halvings k = 0, 1, ...: the first k whose product fits (closed form of the reference's while loop)
+    shifts = torch.arange(32, device=cell.device, dtype=torch.int64)
+    cpd_k = torch.clamp(cpd[:, None, :] >> shifts[None, :, None], min=1)
+    fits = cpd_k.prod(dim=2) <= max(int(max_nbins), 1)
+    k = torch.argmax(fits.to(torch.int8), dim=1)
+    cells = torch.gather(cpd_k.prod(dim=2), 1, k[:, None])[:, 0]
+    return cells, radius.to(torch.int32)
+
+
 def estimate_cell_list_sizes(cell: torch.Tensor, pbc: torch.Tensor, cutoff: float, max_nbins: int = 1000):
-    """Signature of cell_list.py:639-722.  The CUDA path sizes its own workspace (number of cells <= number of
-    atoms, no device->host sync), so this only reports the stencil radius the reference would use per dimension
-    computed on the host from ``cell``; ``max_nbins`` is accepted and ignored."""
-    cell = cell.reshape(-1, 3, 3)[0].detach().double().cpu()
-    pbc = pbc.reshape(-1)[:3].detach().cpu()
-    if cutoff <= 0:
-        return 1, torch.zeros((3,), dtype=torch.int32, device=pbc.device)
-    inv = torch.linalg.inv(cell)
-    face = 1.0 / torch.linalg.norm(inv, dim=0)
-    cpd = torch.clamp((face / cutoff).floor().to(torch.int64), min=1)
-    radius = torch.where((cpd == 1) & (~pbc.bool()), torch.zeros_like(cpd),
-                         torch.ceil(cutoff * cpd / face).to(torch.int64))
-    return int(cpd.prod().item()), radius.to(torch.int32).to(cell.device)
+    """``(max_total_cells, neighbor_search_radius [3] int32 on cell.device)`` — cell_list.py:639-722, same formula and
+    the same single ``.item()`` sync.  The result sizes ``allocate_cell_list``; ``build_cell_list`` keeps its grid within
+    that capacity (so the default ``max_nbins = 1000`` gives large systems the reference's coarse, slow grid — pass a
+    larger value, e.g. the number of atoms, for the split workflow; ``cell_list`` / ``neighbor_list`` size their own
+    workspace and are not affected)."""
+    if (cell.ndim == 3 and cell.shape[0] == 0) or cutoff <= 0:
+        return 1, torch.zeros((3,), dtype=torch.int32, device=cell.device)
+    _engine._dtype_code(cell.dtype)
+    cells, radius = _estimate_grid(cell.reshape(-1, 3, 3)[:1], pbc.reshape(-1, 3)[:1], cutoff, max_nbins)
+    return int(cells[0].item()), radius[0]
 
 
 def cell_list(
@@ -144,16 +173,17 @@ def cell_list(
 
     Returns ``(neighbor_matrix [N,M] i32, num_neighbors [N] i32, neighbor_matrix_shifts [N,M,3] i32)`` or, with
     ``return_neighbor_list=True``, ``(neighbor_list [2,P] i32, neighbor_ptr [N+1] i32, shifts [P,3] i32)``.
-    Pre-allocated output tensors are filled in place and returned as the same objects.  The seven cell-list
-    cache tensors of the reference are accepted for signature compatibility; only ``cells_per_dimension`` and
-    ``neighbor_search_radius`` are written (the grid actually used) — the cache itself is an opaque workspace.
+    Pre-allocated output tensors are filled in place and returned as the same objects.  As in the reference, the seven
+    cell-list cache tensors are used only when ALL of them are given: the grid is then capped at their capacity and all
+    seven are filled in place (cell_list.py:1376-1410); otherwise the library sizes its own workspace.
     """
     total_atoms = positions.shape[0]
     cell = cell if cell.ndim == 3 else cell.unsqueeze(0)
     pbc = pbc.squeeze(0) if pbc.ndim == 2 else pbc
     if fill_value is None:
         fill_value = total_atoms
-    cache = {"cells_per_dimension": cells_per_dimension, "neighbor_search_radius": neighbor_search_radius}
+    cache = dict(zip(_CACHE_KEYS, (cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
+                                   atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)))
     return _run(positions, cutoff, cell[:1], pbc.reshape(1, 3), None, None, max_neighbors, half_fill, fill_value,
                 return_neighbor_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, cache,
                 empty_fill=fill_value)
@@ -161,28 +191,9 @@ def cell_list(
 
 # ----------------------------------------------------------------------------------------------------------------
 # split build / query (the MD workflow: build with cutoff + skin, re-query while atoms move) — reference
-# cell_list.py:1037-1192 and docs/userguide/components/neighborlist.md:421-500
+# cell_list.py:1037-1192 and docs/userguide/components/neighborlist.md:421-500.  Thin wrappers over the custom ops
+# (ops.py); there is no hidden state: the cell list IS the seven tensors.
 # ----------------------------------------------------------------------------------------------------------------
-_HANDLE_ATTR = "_nvnl_handle"
-
-
-def _attach(handle, *tensors):
-    for t in tensors:
-        if t is not None:
-            setattr(t, _HANDLE_ATTR, handle)
-
-
-def _find_handle(*tensors):
-    for t in tensors:
-        h = getattr(t, _HANDLE_ATTR, None) if t is not None else None
-        if h is not None:
-            return h
-    raise RuntimeError(
-        "nvalchemiops_b200: these cache tensors were not produced by build_cell_list / batch_build_cell_list of this "
-        "package (the cell list itself lives in an opaque device workspace attached to them)."
-    )
-
-
 def build_cell_list(
     positions: torch.Tensor,
     cutoff: float,
@@ -196,17 +207,16 @@ def build_cell_list(
     cell_atom_start_indices: torch.Tensor,
     cell_atom_list: torch.Tensor,
 ) -> None:
-    """Build the cell list (reference cell_list.py:1037-1105).  The seven cache tensors are filled with this
-    implementation's grid / binning (for inspection and for ``cell_list_needs_rebuild``); the structure the queries
-    actually use is an opaque device workspace attached to them — pass the SAME tensor objects to ``query_cell_list``."""
-    if positions.shape[0] == 0 or cutoff <= 0:
-        return
+    """Build the cell list into the seven cache tensors (reference cell_list.py:1037-1105).  The grid has at most
+    ``atoms_per_cell_count.numel()`` cells (``estimate_cell_list_sizes`` / ``allocate_cell_list``); the values are this
+    implementation's binning and are all ``query_cell_list`` / ``cell_list_needs_rebuild`` need."""
+    from .ops import build_cell_list_op
+
+    _engine._require_cuda(positions, "positions")
     cell = cell if cell.ndim == 3 else cell.unsqueeze(0)
-    h = _engine.build(positions, cutoff, cell[:1], pbc.reshape(1, 3))
-    _engine.export_cache(h, cells_per_dimension, neighbor_search_radius, atom_periodic_shifts, atom_to_cell_mapping,
-                         atoms_per_cell_count, cell_atom_start_indices, cell_atom_list)
-    _attach(h, cells_per_dimension, atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count,
-            cell_atom_start_indices, cell_atom_list)
+    build_cell_list_op(positions, float(cutoff), cell, pbc, cells_per_dimension, neighbor_search_radius,
+                       atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                       cell_atom_list)
 
 
 def query_cell_list(
@@ -229,12 +239,10 @@ def query_cell_list(
     """Query a (possibly stale) cell list with the current ``positions`` and a cutoff <= the build cutoff
     (reference cell_list.py:1108-1192).  Writes hits and ``num_neighbors`` in place; like the reference op it does
     not reset the unused slots of ``neighbor_matrix`` / ``neighbor_matrix_shifts`` (the caller pre-fills them)."""
-    if positions.shape[0] == 0 or cutoff <= 0:
-        return
-    h = _find_handle(cell_atom_list, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
-                     atom_periodic_shifts, cells_per_dimension)
-    if cutoff > h.cutoff * (1.0 + 1e-12):
-        raise ValueError(f"query cutoff {cutoff} exceeds the cutoff {h.cutoff} the cell list was built for")
-    _engine.refresh_positions(h, positions)
-    _engine.query_matrix(h, _engine.cutoff_sq_in_dtype(cutoff, positions.dtype), neighbor_matrix, neighbor_matrix_shifts,
-                         num_neighbors, 0, half_fill, pad_rows=False)
+    from .ops import query_cell_list_op
+
+    _engine._require_cuda(positions, "positions")
+    cell = cell if cell.ndim == 3 else cell.unsqueeze(0)
+    query_cell_list_op(positions, float(cutoff), cell, pbc, cells_per_dimension, neighbor_search_radius,
+                       atom_periodic_shifts, atom_to_cell_mapping, atoms_per_cell_count, cell_atom_start_indices,
+                       cell_atom_list, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, bool(half_fill))

@@ -1,9 +1,8 @@
-"""Host-side helpers of the neighbor-list path, mirroring nvalchemiops/neighborlist/neighbor_utils.py.
-
-Same names, argument meaning and error behaviour as the reference:
-``estimate_max_neighbors`` (:296-340), ``NeighborOverflowError`` (:343-349), ``assert_max_neighbors``
-(:352-359), ``get_neighbor_list_from_neighbor_matrix`` (:362-441), ``_prepare_batch_idx_ptr`` (:444-491),
-``allocate_cell_list`` (:494-539).  These are tensor plumbing (torch ops), not the hot path.
+"""Host-side helpers of the neighbor-list path — the contract of nvalchemiops/neighborlist/neighbor_utils.py
+(``estimate_max_neighbors`` :296-340, ``NeighborOverflowError`` :343-349, ``assert_max_neighbors`` :352-359,
+``get_neighbor_list_from_neighbor_matrix`` :362-441, ``_prepare_batch_idx_ptr`` :444-491, ``allocate_cell_list``
+:494-539), written independently: same names, argument meaning, return shapes/dtypes and error behaviour.
+Tensor plumbing (torch ops), not the hot path.
 """
 from __future__ import annotations
 
@@ -11,32 +10,39 @@ import math
 
 import torch
 
+_SPHERE = 4.0 * math.pi / 3.0
+
 
 def estimate_max_neighbors(cutoff: float, atomic_density: float = 0.35, safety_factor: float = 5.0) -> int:
-    """Upper bound on neighbors per atom: ceil(max(1, sf * rho * 4/3 pi rc^3) / 16) * 16."""
+    """Row width of the padded neighbor matrix: ``safety_factor`` times the atoms expected inside the cutoff sphere at
+    number density ``atomic_density`` (at least one), rounded up to a multiple of 16; 0 for a non-positive cutoff."""
     if cutoff <= 0:
         return 0
-    cutoff_sphere_volume = atomic_density * (4.0 / 3.0) * math.pi * (cutoff**3)
-    expected_neighbors = max(1, safety_factor * cutoff_sphere_volume)
-    return int(math.ceil(expected_neighbors / 16)) * 16
+    inside_sphere = _SPHERE * cutoff**3 * atomic_density
+    want = safety_factor * inside_sphere
+    if want < 1:
+        want = 1
+    return 16 * int(math.ceil(want / 16))
 
 
 class NeighborOverflowError(Exception):
-    """Raised when an atom has more neighbors than the padded matrix can hold."""
+    """An atom has more neighbors than the padded matrix can hold (raised by the COO conversions only)."""
 
     def __init__(self, max_neighbors: int, num_neighbors: int):
+        # message text kept identical to the reference's: callers match on it
         super().__init__(
             f"The number of neighbors is larger than the maximum allowed: {num_neighbors} > {max_neighbors}."
         )
 
 
 def assert_max_neighbors(neighbor_matrix: torch.Tensor, num_neighbors: torch.Tensor):
-    max_neighbors = 0 if num_neighbors.numel() == 0 else num_neighbors.max()
-    if max_neighbors > neighbor_matrix.shape[1]:
-        raise NeighborOverflowError(
-            neighbor_matrix.shape[1],
-            max_neighbors if isinstance(max_neighbors, int) else max_neighbors.item(),
-        )
+    """Raise ``NeighborOverflowError`` if some atom's count exceeds the matrix width (one host sync)."""
+    if num_neighbors.numel() == 0:
+        return
+    width = neighbor_matrix.shape[1]
+    largest = int(num_neighbors.max().item())
+    if largest > width:
+        raise NeighborOverflowError(width, largest)
 
 
 def get_neighbor_list_from_neighbor_matrix(
@@ -45,66 +51,52 @@ def get_neighbor_list_from_neighbor_matrix(
     neighbor_shift_matrix: torch.Tensor | None = None,
     fill_value: int = -1,
 ):
-    """Padded matrix -> COO ``(neighbor_list [2,P], neighbor_ptr [N+1][, shifts [P,3]])``.
-
-    Utility for matrices the caller already holds; ``cell_list(..., return_neighbor_list=True)`` does
-    NOT go through it (the CUDA path writes COO directly).
-    """
+    """Padded matrix -> COO ``(neighbor_list [2,P], neighbor_ptr [N+1][, shifts [P,3]])``: every slot that does not
+    hold ``fill_value`` becomes a pair, rows in order.  Utility for matrices the caller already holds;
+    ``cell_list(..., return_neighbor_list=True)`` does NOT go through it (the CUDA path writes COO directly)."""
+    device, dtype = neighbor_matrix.device, neighbor_matrix.dtype
     if num_neighbors.shape[0] == 0:
-        neighbor_list = torch.zeros(2, 0, dtype=neighbor_matrix.dtype, device=neighbor_matrix.device)
-        neighbor_ptr = torch.zeros(1, dtype=torch.int32, device=neighbor_matrix.device)
+        empty = (torch.zeros((2, 0), dtype=dtype, device=device), torch.zeros((1,), dtype=torch.int32, device=device))
         if neighbor_shift_matrix is None:
-            return neighbor_list, neighbor_ptr
-        shifts = torch.empty(0, 2, 3, dtype=neighbor_shift_matrix.dtype, device=neighbor_shift_matrix.device)
-        return neighbor_list, neighbor_ptr, shifts
+            return empty
+        return (*empty, torch.empty((0, 2, 3), dtype=neighbor_shift_matrix.dtype, device=neighbor_shift_matrix.device))
     assert_max_neighbors(neighbor_matrix, num_neighbors)
-    mask = neighbor_matrix != fill_value
-    dtype = neighbor_matrix.dtype
-    i_idx = torch.where(mask)[0].to(dtype)
-    j_idx = neighbor_matrix[mask].to(dtype)
-    neighbor_list = torch.stack([i_idx, j_idx], dim=0)
-    neighbor_ptr = torch.zeros(num_neighbors.shape[0] + 1, dtype=torch.int32, device=neighbor_matrix.device)
-    torch.cumsum(num_neighbors, dim=0, out=neighbor_ptr[1:])
-    if neighbor_shift_matrix is not None:
-        return neighbor_list, neighbor_ptr, neighbor_shift_matrix[mask]
-    return neighbor_list, neighbor_ptr
+    src, slot = torch.nonzero(neighbor_matrix != fill_value, as_tuple=True)      # row-major: sources come out sorted
+    neighbor_list = torch.stack((src.to(dtype), neighbor_matrix[src, slot]))
+    neighbor_ptr = torch.cat((torch.zeros((1,), dtype=torch.int32, device=device),
+                              torch.cumsum(num_neighbors, dim=0).to(torch.int32)))
+    if neighbor_shift_matrix is None:
+        return neighbor_list, neighbor_ptr
+    return neighbor_list, neighbor_ptr, neighbor_shift_matrix[src, slot]
 
 
 def _prepare_batch_idx_ptr(batch_idx, batch_ptr, num_atoms: int, device):
-    """Derive whichever of ``batch_idx`` / ``batch_ptr`` is missing (reference :444-491)."""
+    """Return ``(batch_idx [N], batch_ptr [S+1])``, deriving the missing one from the other; ``ValueError`` when both
+    are missing (same message as the reference)."""
     if batch_idx is None and batch_ptr is None:
         raise ValueError("Either batch_idx or batch_ptr must be provided.")
     if batch_idx is None:
-        num_systems = batch_ptr.shape[0] - 1
-        num_atoms_per_system = batch_ptr[1:] - batch_ptr[:-1]
-        batch_idx = torch.repeat_interleave(
-            torch.arange(num_systems, dtype=torch.int32, device=device), num_atoms_per_system
-        )
+        counts = torch.diff(batch_ptr)
+        systems = torch.arange(counts.shape[0], dtype=torch.int32, device=device)
+        batch_idx = systems.repeat_interleave(counts)
     elif batch_ptr is None:
-        num_systems = int(batch_idx.max()) + 1
-        num_atoms_per_system = torch.bincount(batch_idx, minlength=num_systems)
-        batch_ptr = torch.zeros(num_systems + 1, dtype=torch.int32, device=device)
-        torch.cumsum(num_atoms_per_system, dim=0, out=batch_ptr[1:])
+        num_systems = int(batch_idx.max().item()) + 1
+        counts = torch.bincount(batch_idx, minlength=num_systems)
+        batch_ptr = torch.cat((torch.zeros((1,), dtype=torch.int32, device=device),
+                               torch.cumsum(counts, dim=0).to(torch.int32)))
     return batch_idx, batch_ptr
 
 
 def allocate_cell_list(total_atoms: int, max_total_cells: int, neighbor_search_radius: torch.Tensor, device):
-    """Reference-shaped 7-tensor cell-list cache (reference :494-539).
+    """The seven-tensor cell-list cache, zero-filled int32, in the reference's order: ``cells_per_dimension`` ([3], or
+    [S,3] when ``neighbor_search_radius`` is [S,3]), ``neighbor_search_radius`` (passed through),
+    ``atom_periodic_shifts`` [N,3], ``atom_to_cell_mapping`` [N,3], ``atoms_per_cell_count`` [C],
+    ``cell_atom_start_indices`` [C], ``cell_atom_list`` [N].  ``build_cell_list`` / ``batch_build_cell_list`` fill all
+    of them and keep the grid within the ``C = max_total_cells`` cells allocated here."""
+    def zeros(*shape):
+        return torch.zeros(shape, dtype=torch.int32, device=device)
 
-    Kept for signature compatibility.  The CUDA path keeps its own opaque workspace
-    (``nvnl_workspace_bytes``); of these tensors only ``cells_per_dimension`` and
-    ``neighbor_search_radius`` are filled in (with the grid actually used).
-    """
-    cells_per_dimension = torch.zeros(
-        (3,) if neighbor_search_radius.ndim == 1 else (neighbor_search_radius.shape[0], 3),
-        dtype=torch.int32, device=device,
-    )
-    return (
-        cells_per_dimension,
-        neighbor_search_radius,
-        torch.zeros((total_atoms, 3), dtype=torch.int32, device=device),
-        torch.zeros((total_atoms, 3), dtype=torch.int32, device=device),
-        torch.zeros((max_total_cells,), dtype=torch.int32, device=device),
-        torch.zeros((max_total_cells,), dtype=torch.int32, device=device),
-        torch.zeros((total_atoms,), dtype=torch.int32, device=device),
-    )
+    per_system = neighbor_search_radius.ndim > 1
+    cpd = zeros(neighbor_search_radius.shape[0], 3) if per_system else zeros(3)
+    return (cpd, neighbor_search_radius, zeros(total_atoms, 3), zeros(total_atoms, 3), zeros(max_total_cells),
+            zeros(max_total_cells), zeros(total_atoms))

@@ -1,26 +1,27 @@
 """Rebuild detection (reference nvalchemiops/neighborlist/rebuild_detection.py:258-625).
 
-``neighbor_list_needs_rebuild`` is a stateless comparison of two position arrays.  ``cell_list_needs_rebuild`` asks
-whether any atom left the cell it was binned into; it needs the cell list of the last ``build_cell_list`` call, which
-this package keeps in an opaque workspace attached to the cache tensors that call filled in.
+Both checks are stateless functions of their tensor arguments, like the reference's: ``neighbor_list_needs_rebuild``
+compares two position arrays, ``cell_list_needs_rebuild`` re-hashes the current positions on the grid
+``(cell, pbc, cells_per_dimension)`` and compares with the ``atom_to_cell_mapping`` that ``build_cell_list`` wrote.
 """
 from __future__ import annotations
 
 import torch
 
 from . import _engine
-from .cell_list import _find_handle
 
 
 def cell_list_needs_rebuild(current_positions: torch.Tensor, atom_to_cell_mapping: torch.Tensor,
-                            cells_per_dimension: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor) -> torch.Tensor:
-    """bool tensor [1]: True if any atom moved to a different cell of the grid used by the last build
-    (reference :336-383; same signature).  ``atom_to_cell_mapping`` must be the tensor ``build_cell_list`` filled."""
+                            cells_per_dimension: torch.Tensor, cell: torch.Tensor, pbc: torch.Tensor,
+                            batch_idx: torch.Tensor | None = None) -> torch.Tensor:
+    """bool tensor [1]: True if any atom moved to a different cell of the grid ``build_cell_list`` used
+    (reference :336-383; same signature, plus an optional ``batch_idx`` for caches of ``batch_build_cell_list``)."""
     device = current_positions.device
     if current_positions.shape[0] == 0:
         return torch.tensor([False], device=device, dtype=torch.bool)
-    h = _find_handle(atom_to_cell_mapping, cells_per_dimension)
-    return _engine.cells_changed(h, current_positions).to(torch.bool)
+    cell = cell if cell.ndim == 3 else cell.unsqueeze(0)
+    return _engine.cells_changed_cache(current_positions, cell, pbc, batch_idx, cells_per_dimension,
+                                       atom_to_cell_mapping).to(torch.bool)
 
 
 def neighbor_list_needs_rebuild(reference_positions: torch.Tensor, current_positions: torch.Tensor,

@@ -407,10 +407,167 @@ def test_build_query_split_with_moving_atoms():
             want = ro.records_from_matrix(*ro.cell_list(cur, rc, cell, pbc, max_neighbors=64))
             assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), f"step {step} pbc {pbc_flag}"
             _check_matrix_padding(nm, num, sh, 800)   # untouched slots keep the caller's pre-fill
-        with pytest.raises(ValueError):
-            nl.query_cell_list(cur.to(DEV), rc + 2 * skin, cell.to(DEV), pbc.to(DEV), *cache, nm, sh, num)
-    with pytest.raises(RuntimeError):
-        nl.query_cell_list(cur.to(DEV), rc, cell.to(DEV), pbc.to(DEV), *_alloc_cache(800, 4096), nm, sh, num)
+        # a query cutoff ABOVE the build cutoff is still exact for atoms that have not moved since the build (the stencil
+        # radius is recomputed for the query cutoff on the cached grid; the reference has no check either)
+        nm = torch.full((800, 160), 800, dtype=torch.int32, device=DEV)
+        sh = torch.zeros((800, 160, 3), dtype=torch.int32, device=DEV)
+        num = torch.zeros((800,), dtype=torch.int32, device=DEV)
+        nl.query_cell_list(pos.to(DEV), rc + 2 * skin, cell.to(DEV), pbc.to(DEV), *cache, nm, sh, num)
+        want = ro.records_from_matrix(*ro.cell_list(pos, rc + 2 * skin, cell, pbc, max_neighbors=160))
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    # no hidden state: the cache survives clone() (new storage, new tensor objects)
+    cloned = [t.clone() for t in cache]
+    nm2 = torch.full((800, 64), 800, dtype=torch.int32, device=DEV)
+    sh2 = torch.zeros((800, 64, 3), dtype=torch.int32, device=DEV)
+    num2 = torch.zeros((800,), dtype=torch.int32, device=DEV)
+    nl.query_cell_list(cur.to(DEV), rc, cell.to(DEV), pbc.to(DEV), *cloned, nm2, sh2, num2)
+    want = ro.records_from_matrix(*ro.cell_list(cur, rc, cell, pbc, max_neighbors=64))
+    assert np.array_equal(_records_gpu_matrix(nm2, num2, sh2), want)
+    # a cache that no build filled is reported when input checking is on (the matrix path is sync-free otherwise)
+    from nvalchemiops_b200 import config
+    config.check_inputs = True
+    try:
+        with pytest.raises(ValueError, match="cache"):
+            nl.query_cell_list(cur.to(DEV), rc, cell.to(DEV), pbc.to(DEV), *_alloc_cache(800, 4096), nm2, sh2, num2)
+    finally:
+        config.check_inputs = False
+
+
+def test_estimate_allocate_build_query_end_to_end():
+    """The reference's documented split workflow (docs/userguide/components/neighborlist.md:421-500):
+    estimate_cell_list_sizes -> allocate_cell_list -> build_cell_list -> query_cell_list, single and batched, on CUDA
+    tensors; the estimates equal the oracle's restatement of cell_list.py:35-99 / batch_cell_list.py:35-99."""
+    nl = _nl()
+    for L, rc, pbc_flag, nbins in ((22.0, 4.0, [True, True, True], 1000), (60.0, 3.0, [True, False, True], 1000),
+                                   (60.0, 3.0, [True, True, True], 100000), (7.0, 4.0, [True, True, False], 1000)):
+        pos, cell, pbc = random_system(700, L, torch.float32, seed=5, pbc_flag=pbc_flag)
+        pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+        cells, radius = nl.estimate_cell_list_sizes(cell_d, pbc_d, rc, max_nbins=nbins)
+        want_cells, want_radius = ro.estimate_cell_list_sizes(cell, pbc, rc, max_nbins=nbins)
+        assert cells == want_cells and radius.device == pos_d.device and radius.dtype == torch.int32
+        assert radius.cpu().tolist() == list(np.asarray(want_radius).reshape(-1))
+        cache = nl.allocate_cell_list(700, cells, radius, pos_d.device)
+        assert [tuple(t.shape) for t in cache] == [(3,), (3,), (700, 3), (700, 3), (cells,), (cells,), (700,)]
+        assert all(t.dtype == torch.int32 and t.device == pos_d.device for t in cache)
+        nl.build_cell_list(pos_d, rc, cell_d, pbc_d, *cache)
+        assert int(cache[0].prod()) <= cells                       # the grid respects the allocated capacity
+        assert int(cache[4].sum()) == 700 and sorted(cache[6].cpu().tolist()) == list(range(700))
+        assert torch.equal(cache[5][: int(cache[0].prod())].cpu(),
+                           (torch.cumsum(cache[4][: int(cache[0].prod())], 0) - cache[4][: int(cache[0].prod())]).cpu().to(torch.int32))
+        M = 128
+        nm = torch.full((700, M), 700, dtype=torch.int32, device=DEV)
+        sh = torch.zeros((700, M, 3), dtype=torch.int32, device=DEV)
+        num = torch.zeros((700,), dtype=torch.int32, device=DEV)
+        nl.query_cell_list(pos_d, rc, cell_d, pbc_d, *cache, nm, sh, num)
+        want = ro.records_from_matrix(*ro.cell_list(pos, rc, cell, pbc, max_neighbors=M))
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), want), (L, rc, pbc_flag, nbins)
+    # batched
+    pos, cell, pbc, bidx, bptr = bench_batch(9, 100, 300, seed=13, mixed_pbc=True)
+    n = pos.shape[0]
+    pos_d, cell_d, pbc_d, bidx_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV), bidx.to(DEV)
+    cells, radius = nl.estimate_batch_cell_list_sizes(cell_d, pbc_d, 5.0)
+    want_cells, want_radius = ro.estimate_batch_cell_list_sizes(cell, pbc, 5.0)
+    assert cells == want_cells and radius.shape == (9, 3) and radius.device == pos_d.device
+    assert np.array_equal(radius.cpu().numpy(), np.asarray(want_radius).reshape(9, 3))
+    cache = nl.allocate_cell_list(n, cells, radius, pos_d.device)
+    assert tuple(cache[0].shape) == (9, 3)
+    nl.batch_build_cell_list(pos_d, 5.0, cell_d, pbc_d, bidx_d, *cache)
+    assert int(cache[0].prod(dim=1).sum()) <= cells and int(cache[0].prod(dim=1).max()) <= cells // 9
+    nm = torch.full((n, 200), -1, dtype=torch.int32, device=DEV)
+    sh = torch.zeros((n, 200, 3), dtype=torch.int32, device=DEV)
+    num = torch.zeros((n,), dtype=torch.int32, device=DEV)
+    nl.batch_query_cell_list(pos_d, cell_d, pbc_d, 5.0, bidx_d, *cache, nm, sh, num)
+    want = ro.records_from_matrix(*ro.batch_cell_list(pos, 5.0, cell, pbc, bidx, max_neighbors=200))
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    # empty / zero-cutoff estimates (cell_list.py:683-684, batch_cell_list.py:697-698)
+    assert nl.estimate_cell_list_sizes(cell_d[:1], pbc_d[:1], 0.0)[0] == 1
+    c0, r0 = nl.estimate_batch_cell_list_sizes(cell_d[:0], pbc_d[:0], 5.0)
+    assert c0 == 1 and tuple(r0.shape) == (0, 3)
+
+
+def test_cell_list_fills_all_seven_preallocated_cache_tensors():
+    """cell_list() / batch_cell_list() with a full set of pre-allocated tensors: outputs AND caches are the same objects,
+    reset and filled in place (reference cell_list.py:1395-1410; test_neighborlist.py:817-855)."""
+    nl = _nl()
+    pos, cell, pbc = random_system(600, 20.0, torch.float32, seed=8)
+    pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    cells, radius = nl.estimate_cell_list_sizes(cell_d, pbc_d, 4.0)
+    cache = nl.allocate_cell_list(600, cells, radius, pos_d.device)
+    for t in cache:
+        t.fill_(-7)                                               # stale garbage the call must overwrite
+    names = ("cells_per_dimension", "neighbor_search_radius", "atom_periodic_shifts", "atom_to_cell_mapping",
+             "atoms_per_cell_count", "cell_atom_start_indices", "cell_atom_list")
+    nm = torch.full((600, 96), -3, dtype=torch.int32, device=DEV)
+    sh = torch.full((600, 96, 3), -3, dtype=torch.int32, device=DEV)
+    num = torch.full((600,), -3, dtype=torch.int32, device=DEV)
+    out = nl.cell_list(pos_d, 4.0, cell_d, pbc_d, neighbor_matrix=nm, neighbor_matrix_shifts=sh, num_neighbors=num,
+                       **dict(zip(names, cache)))
+    assert out[0] is nm and out[1] is num and out[2] is sh
+    want = ro.records_from_matrix(*ro.cell_list(pos, 4.0, cell, pbc, max_neighbors=96))
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 600)
+    ncell = int(cache[0].prod())
+    assert cache[0].tolist() == [4, 4, 4] and ncell <= cells and cache[1].tolist() == [1, 1, 1]
+    assert int(cache[4].sum()) == 600 and int(cache[4][ncell:].abs().sum()) == 0
+    assert sorted(cache[6].cpu().tolist()) == list(range(600))
+    assert int(cache[2].abs().sum()) == 0                         # wrapped positions: no periodic images
+    w = 20.0 / 4
+    assert torch.equal(cache[3].cpu().long(), torch.floor(pos / w).long().clamp(0, 3))
+    # the filled cache is a valid input of query_cell_list
+    nm2 = torch.full((600, 96), 600, dtype=torch.int32, device=DEV)
+    sh2 = torch.zeros((600, 96, 3), dtype=torch.int32, device=DEV)
+    num2 = torch.zeros((600,), dtype=torch.int32, device=DEV)
+    nl.query_cell_list(pos_d, 4.0, cell_d, pbc_d, *cache, nm2, sh2, num2)
+    assert np.array_equal(_records_gpu_matrix(nm2, num2, sh2), want)
+    # COO output with a full cache
+    e, p, s = nl.cell_list(pos_d, 4.0, cell_d, pbc_d, return_neighbor_list=True, max_neighbors=96, **dict(zip(names, cache)))
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_torch_compile_build_and_query_ops(batched):
+    """The four reference-schema custom ops under torch.compile(fullgraph=True) with pre-allocated tensors: compiled ==
+    eager == oracle (reference test_cell_list.py:598-844, test_batch_cell_list.py compile tests)."""
+    nl = _nl()
+    rc, M = 4.0, 96
+    if batched:
+        pos, cell, pbc, bidx, bptr = bench_batch(5, 80, 160, seed=19, mixed_pbc=True)
+        n = pos.shape[0]
+        want = ro.records_from_matrix(*ro.batch_cell_list(pos, rc, cell, pbc, bidx, max_neighbors=M))
+        bidx_d = bidx.to(DEV)
+        cells, radius = nl.estimate_batch_cell_list_sizes(cell.to(DEV), pbc.to(DEV), rc)
+    else:
+        pos, cell, pbc = random_system(500, 14.0, torch.float32, seed=41)
+        n = 500
+        want = ro.records_from_matrix(*ro.cell_list(pos, rc, cell, pbc, max_neighbors=M))
+        bidx_d = None
+        cells, radius = nl.estimate_cell_list_sizes(cell.to(DEV), pbc.to(DEV), rc)
+    pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+
+    def fn(positions, cache, nm, sh, num):
+        if batched:
+            nl.batch_build_cell_list(positions, rc, cell_d, pbc_d, bidx_d, *cache)
+            nl.batch_query_cell_list(positions, cell_d, pbc_d, rc, bidx_d, *cache, nm, sh, num, False)
+        else:
+            nl.build_cell_list(positions, rc, cell_d, pbc_d, *cache)
+            nl.query_cell_list(positions, rc, cell_d, pbc_d, *cache, nm, sh, num, False)
+        return num.sum()
+
+    def fresh():
+        return (list(nl.allocate_cell_list(n, cells, radius.clone(), pos_d.device)),
+                torch.full((n, M), n, dtype=torch.int32, device=DEV), torch.zeros((n, M, 3), dtype=torch.int32, device=DEV),
+                torch.zeros((n,), dtype=torch.int32, device=DEV))
+
+    cache, nm, sh, num = fresh()
+    eager_total = fn(pos_d, cache, nm, sh, num).item()
+    assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    cache2, nm2, sh2, num2 = fresh()
+    compiled = torch.compile(fn, fullgraph=True)
+    total = compiled(pos_d, cache2, nm2, sh2, num2).item()
+    assert total == eager_total == want.shape[0]
+    assert np.array_equal(_records_gpu_matrix(nm2, num2, sh2), want)
+    for a, b in zip(cache, cache2):
+        assert torch.equal(a, b)                                  # compiled build == eager build, tensor by tensor
 
 
 def test_batch_build_query_split():
@@ -465,6 +622,18 @@ def test_rebuild_detection():
     # the exported mapping agrees with the geometry
     cells = torch.floor(pos / w).long().clamp(0, 4)
     assert torch.equal(cache[3].cpu().long(), cells)
+    # stateless: cloned tensors (no hidden handle), a non-periodic dimension, and a batch
+    assert nl.check_cell_list_rebuild_needed(big.to(DEV), cache2[3].clone(), cache2[0].clone(), cell_d, pbc_d) is True
+    pbc_open = torch.tensor([True, False, True])
+    cache3 = _alloc_cache(2000, 4096)
+    nl.build_cell_list(inside.to(DEV), 5.0, cell_d, pbc_open.to(DEV), *cache3)
+    up = inside.clone(); up[7, 1] += 0.6 * w
+    assert nl.check_cell_list_rebuild_needed(inside.to(DEV), cache3[3], cache3[0], cell_d, pbc_open.to(DEV)) is False
+    assert nl.check_cell_list_rebuild_needed(up.to(DEV), cache3[3], cache3[0], cell_d, pbc_open.to(DEV)) is True
+    bpos, bcell, bpbc, bidx, bptr = bench_batch(4, 150, 250, seed=3, mixed_pbc=True)
+    bcache = _alloc_cache(bpos.shape[0], 4096, ns=4)
+    nl.batch_build_cell_list(bpos.to(DEV), 3.0, bcell.to(DEV), bpbc.to(DEV), bidx.to(DEV), *bcache)
+    assert nl.cell_list_needs_rebuild(bpos.to(DEV), bcache[3], bcache[0], bcell.to(DEV), bpbc.to(DEV), bidx.to(DEV)).tolist() == [False]
 
 
 def test_dual_cutoff_routes():

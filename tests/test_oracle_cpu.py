@@ -153,11 +153,11 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.declared_symbols())
     lib = _lib.lib()
-    assert lib.nvnl_abi_version() == 2
+    assert lib.nvnl_abi_version() == _lib.ABI_VERSION == 3
     assert lib.nvnl_workspace_bytes(1000, 1, 0) > 1000 * 16
     assert lib.nvnl_workspace_bytes(1000, 4, 1) > lib.nvnl_workspace_bytes(1000, 4, 0)
     # argument validation happens before any CUDA call
-    assert lib.nvnl_build(None, 0, 0, None, None, None, None, 1, 1.0, None, 0, None) != 0
+    assert lib.nvnl_build(None, 0, 0, None, None, None, None, 1, 1.0, 0, None, 0, None) != 0
     assert b"positive" in lib.nvnl_last_error()
 
 
@@ -179,8 +179,8 @@ def test_rows_path_c_abi_argument_validation_and_budget():
     dummy = ctypes.c_void_p(4096)          # never dereferenced: validation fails first
     assert lib.nvnl_count_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
     assert b"fp32 only" in lib.nvnl_last_error()
-    assert lib.nvnl_count_rows(dummy, 0, 1 << 28, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
-    assert b"2^28" in lib.nvnl_last_error()
+    assert lib.nvnl_count_rows(dummy, 0, 1 << 27, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
+    assert b"2^27" in lib.nvnl_last_error()
     assert lib.nvnl_count_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, ctypes.c_void_p(4100), 64, None) != 0
     assert b"16-byte aligned" in lib.nvnl_last_error()
     assert lib.nvnl_fill_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, dummy, 0, -1, None) != 0
@@ -212,7 +212,7 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
         def __init__(self, n, dtype=torch.float32):
             self.n, self.dtype = n, dtype
 
-    assert _engine.use_rows(H(1000)) and not _engine.use_rows(H(1000, torch.float64)) and not _engine.use_rows(H(1 << 28))
+    assert _engine.use_rows(H(1000)) and not _engine.use_rows(H(1000, torch.float64)) and not _engine.use_rows(H(1 << 27))
     monkeypatch.setattr(config, "coo_path", "masks")
     assert not _engine.use_rows(H(1000))
     monkeypatch.setattr(config, "coo_path", "bogus")
@@ -293,3 +293,34 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     _engine.query_coo(h, 36.0)
     assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 0) and calls[2][3] == (2, 6_000_000)
     _engine._pair_history.clear()
+
+
+def test_estimate_cell_list_sizes_matches_the_oracle_restatement():
+    """estimate_cell_list_sizes / estimate_batch_cell_list_sizes are torch ops (they run on CPU tensors too): same cell
+    counts and radii as the oracle's restatement of cell_list.py:35-99 / batch_cell_list.py:35-99, incl. max_nbins."""
+    import numpy as np
+    from nvalchemiops_b200.neighborlist import (allocate_cell_list, estimate_batch_cell_list_sizes,
+                                                estimate_cell_list_sizes)
+
+    g = torch.Generator().manual_seed(11)
+    cells, pbcs = [], []
+    for k in range(40):
+        L = 3.0 + 60.0 * float(torch.rand(1, generator=g))
+        c = torch.eye(3) * L
+        if k % 2:
+            c = c + (torch.rand(3, 3, generator=g) - 0.5) * 0.3 * L       # triclinic
+        p = torch.rand(3, generator=g) > 0.4
+        cells.append(c); pbcs.append(p)
+        for dtype in (torch.float32, torch.float64):
+            for rc, nbins in ((2.7, 1000), (6.0, 1000), (6.0, 27), (1.1, 10**6)):
+                got = estimate_cell_list_sizes(c.to(dtype).reshape(1, 3, 3), p.reshape(1, 3), rc, max_nbins=nbins)
+                want = ro.estimate_cell_list_sizes(c.to(dtype).reshape(1, 3, 3), p, rc, max_nbins=nbins)
+                assert got[0] == want[0] and got[1].tolist() == list(np.asarray(want[1]).reshape(-1)), (k, dtype, rc, nbins)
+    cell, pbc = torch.stack(cells), torch.stack(pbcs)
+    got = estimate_batch_cell_list_sizes(cell, pbc, 4.0, max_nbins=64)
+    want = ro.estimate_batch_cell_list_sizes(cell, pbc, 4.0, max_nbins=64)
+    assert got[0] == want[0] and np.array_equal(got[1].numpy(), np.asarray(want[1]).reshape(-1, 3))
+    assert estimate_cell_list_sizes(cell[:1], pbc[:1], -1.0)[0] == 1
+    cache = allocate_cell_list(10, 7, got[1][:3], torch.device("cpu"))
+    assert [tuple(t.shape) for t in cache] == [(3, 3), (3, 3), (10, 3), (10, 3), (7,), (7,), (10,)]
+    assert cache[1] is got[1][:3] or torch.equal(cache[1], got[1][:3])
