@@ -71,7 +71,8 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
 /* Device->host read of the control block (synchronizes `stream`): total number of directed pairs
  * found by the last nvnl_count, the largest per-atom count (what assert_max_neighbors checks,
  * neighbor_utils.py:352-359), number of cells, error bits, and whether any atom was outside the
- * primary periodic image, and whether any cell was left to the general kernel (both feed nvnl_fill_coo's
+ * primary periodic image (*unwrapped bit 0; bit 1 = some system searches more than one cell per side, i.e. periodic
+ * shifts may exceed +-1), and whether any cell was left to the general kernel (both feed nvnl_fill_coo's
  * launch_hint), and whether nvnl_count_rows ran out of temporary row space (then the caller repeats the query with
  * nvnl_count / nvnl_fill_coo).  The one sync of the COO path (the reference has three). Host pointers. */
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
@@ -86,7 +87,8 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
  *   bit 0 = nvnl_status' `unwrapped`, bit 1 = its `had_deferred`: only the kernels with work are launched. */
 int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
+                  int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,
+                  void* stream);
 
 /* Single-sweep COO path (fp32; same outputs as nvnl_count + nvnl_fill_coo, same reference interfaces:
  * query_cell_list cell_list.py:892-1034 + get_neighbor_list_from_neighbor_matrix neighbor_utils.py:362-441).
@@ -106,7 +108,8 @@ int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_syste
                     int32_t* prezero, int64_t prezero_ints, void* stream);
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                    double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                   int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream);
+                   int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,
+                   void* stream);
 
 /* EXPERIMENTAL (compiled, not yet measured on hardware; nvalchemiops_b200.config.speculative_fill, off by default):
  * the output kernel of the single-sweep path launched BEFORE the size sync, into buffers sized from a guess
@@ -180,15 +183,20 @@ int nvnl_cells_changed_cache(const void* positions, int dtype, int64_t n_atoms, 
 int nvnl_moved_beyond(const void* reference_positions, const void* current_positions, int dtype, int64_t n_atoms,
                       double threshold, int32_t* flag, void* stream);
 
-/* Multi-GPU re-assembly (north_star: batch_ptr-sharded ranks + ONE NCCL all-gather; the reference has
- * no distributed code).  Each rank fills a block [ src(stride) | dst(stride) | shifts(3*stride) ] with
- * nvnl_fill_coo (edge_index = block, shifts = block + 2*stride, num_pairs = stride); after the
- * all-gather `recv` holds n_ranks such blocks, block_stride_ints int32 apart (>= 5*stride_pairs; ranks may
- * append metadata after the payload), and this kernel writes the global edge_index [2,total_pairs] and
- * shifts [total_pairs,3].  counts_host: pairs per rank (HOST pointer). */
-int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, int64_t block_stride_ints,
-                         const int64_t* counts_host, int32_t* edge_index, int64_t total_pairs, int32_t* shifts,
-                         void* stream);
+/* Multi-GPU re-assembly (north_star: batch_ptr-sharded ranks + an NCCL all-gather over NVLink; the reference has no
+ * distributed code).  Ranks exchange only what cannot be recomputed: per pair the target atom (4 B, gathered straight
+ * into row 1 of the global edge_index) and the periodic shift packed into one byte, per atom num_neighbors; a pair's
+ * source atom follows from neighbor_ptr.  Each rank writes its own range of the global arrays with nvnl_fill_rows /
+ * nvnl_fill_coo (edge_index = global + own offset, row_stride = global pair count), packs its own shifts with
+ * nvnl_pack_shifts, and after the gathers expands the foreign ranges with nvnl_expand_gathered.
+ *   packed byte = (sx + 1) | (sy + 1) << 2 | (sz + 1) << 4; *bad_flag (device int32, may be NULL; caller zeroes it) is
+ *   set when a component lies outside {-1, 0, 1} (unwrapped inputs, boxes smaller than the cutoff: the caller then
+ *   gathers the int32 shifts instead). */
+int nvnl_pack_shifts(const int32_t* shifts, int64_t n_pairs, uint8_t* packed, int32_t* bad_flag, void* stream);
+/* out_i (row 0 of edge_index) and shifts [P,3] of every atom outside [atom_lo, atom_hi) from the global
+ * neighbor_ptr [n_atoms+1] and the gathered packed shifts [P]. */
+int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t atom_lo, int64_t atom_hi,
+                         const uint8_t* packed_shifts, int32_t* out_i, int32_t* shifts, void* stream);
 
 /* Size of the temporary row buffer nvnl_count_rows may use: entries_per_atom * n_atoms + slack_entries int32 entries
  * (defaults 160 and 148*4*8*2048; negative = default).  Changes nvnl_workspace_bytes(): set it before sizing a

@@ -339,9 +339,9 @@ int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, d
 
 template <bool HALF, bool FMA>
 int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, const int* neighbor_ptr,
-                int* edge_index, long long num_pairs, int* shifts, int index_offset, int hint, cudaStream_t st) {
+                int* edge_index, long long row_stride, int* shifts, int index_offset, int hint, cudaStream_t st) {
     SweepArgs<float> a = base_args<float>(ws, n, ns, batch_idx, cutoff_sq);
-    a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+    a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + row_stride; a.out_shifts = shifts;
     a.index_offset = index_offset;
     if (hint & 1) {
         // unwrapped input: the count ran on the two-pass kernels (hit masks), so does the fill
@@ -374,26 +374,51 @@ __global__ void k_get_grid(const unsigned char* __restrict__ ws, WsLayout L, int
     }
 }
 
-struct RankOffsets {
-    long long off[65];  // off[g] = first global pair of rank g, off[n_ranks] = total
-};
-
-// Re-assemble the global COO arrays from the all-gathered per-rank blocks
-//   recv[g] = [ src (stride) | dst (stride) | shifts (3*stride) ]  (int32, stride = padded pair count)
-__global__ void k_unpack_gathered(const int* __restrict__ recv, int n_ranks, long long stride, long long block_stride,
-                                  RankOffsets ro, int* __restrict__ edge_index, long long total,
-                                  int* __restrict__ shifts) {
+// ---- multi-GPU re-assembly: ranks exchange only what cannot be recomputed --------------------------------------
+// A pair's source atom follows from neighbor_ptr and its periodic shift fits one byte when every shift component is in
+// {-1, 0, 1} (wrapped inputs, search radius 1), so a rank sends 4 B (target atom) + 1 B (packed shift) per pair instead
+// of 20 B; the receiver expands the foreign ranges.
+//   packed byte = (sx + 1) | (sy + 1) << 2 | (sz + 1) << 4;   k_pack_shifts sets *bad when a component is outside {-1,0,1}
+__global__ void k_pack_shifts(const int* __restrict__ shifts, long long n_pairs, unsigned char* __restrict__ packed,
+                              int* __restrict__ bad) {
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += nthreads) {
-        int g = 0;
-        while (g + 1 < n_ranks && p >= ro.off[g + 1]) ++g;
-        const long long q = p - ro.off[g];
-        const int* blk = recv + (long long)g * block_stride;
-        edge_index[p] = blk[q];
-        edge_index[total + p] = blk[stride + q];
-        shifts[3 * p] = blk[2 * stride + 3 * q];
-        shifts[3 * p + 1] = blk[2 * stride + 3 * q + 1];
-        shifts[3 * p + 2] = blk[2 * stride + 3 * q + 2];
+    int err = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += nthreads) {
+        const int sx = shifts[3 * p] + 1, sy = shifts[3 * p + 1] + 1, sz = shifts[3 * p + 2] + 1;
+        err |= (sx | sy | sz) & ~3;
+        err |= (sx == 3) | (sy == 3) | (sz == 3);
+        packed[p] = (unsigned char)((sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4));
+    }
+    if (err && bad) atomicOr(bad, 1);
+}
+
+// out_i / shifts of every atom OUTSIDE [atom_lo, atom_hi) from neighbor_ptr and the gathered packed shifts (the rank's
+// own range was written by its fill kernels).  One warp per 32 atoms, rows written sequentially.
+__global__ void __launch_bounds__(256) k_expand_gathered(const int* __restrict__ neighbor_ptr, long long n_atoms,
+                                                         long long atom_lo, long long atom_hi,
+                                                         const unsigned char* __restrict__ packed, int* __restrict__ out_i,
+                                                         int* __restrict__ shifts) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_atoms;
+         base += nwarps * 32) {
+        if (base >= atom_lo && base + 32 <= atom_hi) continue;
+        const long long il = base + lane;
+        const int p_l = neighbor_ptr[il < n_atoms ? il : n_atoms];
+        const int e_l = neighbor_ptr[il + 1 < n_atoms ? il + 1 : n_atoms];
+        const int na = n_atoms - base < 32 ? (int)(n_atoms - base) : 32;
+        for (int t = 0; t < na; ++t) {
+            const long long i = base + t;
+            if (i >= atom_lo && i < atom_hi) continue;
+            const int p = __shfl_sync(0xffffffffu, p_l, t), cnt = __shfl_sync(0xffffffffu, e_l, t) - p;
+            for (int k = lane; k < cnt; k += 32) out_i[(size_t)p + k] = (int)i;
+            int* __restrict__ sh = shifts + 3 * (size_t)p;
+            const unsigned char* __restrict__ pk = packed + (size_t)p;
+            for (int e = lane; e < 3 * cnt; e += 32) {
+                const int k = e / 3, c = e - 3 * k;
+                sh[e] = (int)((pk[k] >> (2 * c)) & 3) - 1;
+            }
+        }
     }
 }
 
@@ -465,7 +490,7 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
     if (max_count) *max_count = h.max_count;
     if (total_cells) *total_cells = h.total_cells;
     if (error_bits) *error_bits = h.error;
-    if (unwrapped) *unwrapped = h.unwrapped;
+    if (unwrapped) *unwrapped = (h.unwrapped ? 1 : 0) | (h.wide_stencil ? 2 : 0);
     if (had_deferred) *had_deferred = h.had_deferred;
     if (rows_overflow) *rows_overflow = h.rows_overflow;
     return 0;
@@ -473,8 +498,10 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
 
 int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                   double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                  int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream) {
+                  int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,
+                  void* stream) {
     if (!workspace || !neighbor_ptr || n_atoms <= 0) return fail(-1, "nvnl_fill_coo: bad arguments");
+    if (row_stride <= 0) row_stride = num_pairs;
     if (num_pairs < 0 || num_pairs > 2147483647LL) return fail(-1, "nvnl_fill_coo: num_pairs outside int32 range");
     if (num_pairs == 0) return 0;
     if (!edge_index || !shifts) return fail(-1, "nvnl_fill_coo: null output");
@@ -482,7 +509,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (dtype == NVNL_F32) {
         SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
-        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + row_stride; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
         k_gather_ptr<float><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
                                                                               reinterpret_cast<int*>(ws + a.L.ptr_sorted));
@@ -491,7 +518,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
     }
     if (dtype == NVNL_F64) {
         SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
-        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + num_pairs; a.out_shifts = shifts;
+        a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + row_stride; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
         k_gather_ptr<double><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
                                                                                reinterpret_cast<int*>(ws + a.L.ptr_sorted));
@@ -520,8 +547,10 @@ int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_syste
 
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                    double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
-                   int64_t num_pairs, int32_t* shifts, int32_t index_offset, int32_t launch_hint, void* stream) {
+                   int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,
+                   void* stream) {
     if (!workspace || !neighbor_ptr || n_atoms <= 0) return fail(-1, "nvnl_fill_rows: bad arguments");
+    if (row_stride <= 0) row_stride = num_pairs;
     if (dtype != NVNL_F32) return fail(-1, "nvnl_fill_rows: the single-sweep path is fp32 only (use nvnl_fill_coo)");
     if (launch_hint < 0) return fail(-1, "nvnl_fill_rows: launch_hint from nvnl_status is required");
     if (num_pairs < 0 || num_pairs > 2147483647LL) return fail(-1, "nvnl_fill_rows: num_pairs outside int32 range");
@@ -530,13 +559,13 @@ int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_system
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (half_fill)
-        return fma ? fill_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+        return fma ? fill_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, row_stride,
                                              shifts, index_offset, launch_hint, st)
-                   : fill_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+                   : fill_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, row_stride,
                                               shifts, index_offset, launch_hint, st);
-    return fma ? fill_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+    return fma ? fill_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, row_stride,
                                           shifts, index_offset, launch_hint, st)
-               : fill_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, num_pairs,
+               : fill_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, neighbor_ptr, edge_index, row_stride,
                                            shifts, index_offset, launch_hint, st);
 }
 
@@ -724,28 +753,30 @@ int nvnl_moved_beyond(const void* reference_positions, const void* current_posit
     return 0;
 }
 
-int nvnl_unpack_gathered(const int32_t* recv, int32_t n_ranks, int64_t stride_pairs, int64_t block_stride_ints,
-                         const int64_t* counts_host, int32_t* edge_index, int64_t total_pairs, int32_t* shifts,
-                         void* stream) {
-    if (block_stride_ints < 5 * stride_pairs) return fail(-1, "nvnl_unpack_gathered: block stride smaller than the payload");
-    if (n_ranks <= 0 || n_ranks > 64) return fail(-1, "nvnl_unpack_gathered: n_ranks must be in [1, 64]");
-    if (!counts_host) return fail(-1, "nvnl_unpack_gathered: null counts");
-    RankOffsets ro;
-    ro.off[0] = 0;
-    for (int g = 0; g < n_ranks; ++g) {
-        if (counts_host[g] < 0 || counts_host[g] > stride_pairs) return fail(-1, "nvnl_unpack_gathered: bad count");
-        ro.off[g + 1] = ro.off[g] + counts_host[g];
-    }
-    if (ro.off[n_ranks] != total_pairs) return fail(-1, "nvnl_unpack_gathered: counts do not sum to total_pairs");
-    if (total_pairs == 0) return 0;
-    if (!recv || !edge_index || !shifts) return fail(-1, "nvnl_unpack_gathered: null pointer");
+int nvnl_pack_shifts(const int32_t* shifts, int64_t n_pairs, uint8_t* packed, int32_t* bad_flag, void* stream) {
+    if (n_pairs < 0) return fail(-1, "nvnl_pack_shifts: negative pair count");
+    if (n_pairs == 0) return 0;
+    if (!shifts || !packed) return fail(-1, "nvnl_pack_shifts: null pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    long long blocks = (total_pairs + 255) / 256;
+    long long blocks = (n_pairs + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_unpack_gathered<<<(unsigned)blocks, 256, 0, st>>>(recv, n_ranks, stride_pairs, block_stride_ints, ro, edge_index,
-                                                        total_pairs, shifts);
-    NVNL_CHECK_LAUNCH("k_unpack_gathered");
+    k_pack_shifts<<<(unsigned)blocks, 256, 0, st>>>(shifts, n_pairs, packed, bad_flag);
+    NVNL_CHECK_LAUNCH("k_pack_shifts");
+    return 0;
+}
+
+int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t atom_lo, int64_t atom_hi,
+                         const uint8_t* packed_shifts, int32_t* out_i, int32_t* shifts, void* stream) {
+    if (n_atoms < 0 || atom_lo < 0 || atom_hi < atom_lo || atom_hi > n_atoms) return fail(-1, "nvnl_expand_gathered: bad atom range");
+    if (n_atoms == 0) return 0;
+    if (!neighbor_ptr || !packed_shifts || !out_i || !shifts) return fail(-1, "nvnl_expand_gathered: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long blocks = (n_atoms + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_expand_gathered<<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, atom_lo, atom_hi, packed_shifts, out_i, shifts);
+    NVNL_CHECK_LAUNCH("k_expand_gathered");
     return 0;
 }
 

@@ -94,6 +94,7 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
         ctrl->max_count = 0;
         ctrl->n_deferred = 0;
         ctrl->had_deferred = 0;
+        ctrl->wide_stencil = 0;
     }
     int* cell_count = reinterpret_cast<int*>(ws + L.cell_count);
     for (long long i = gid; i < L.max_cells + 2; i += stride) cell_count[i] = 0;
@@ -298,6 +299,7 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
                 }
                 sp.cpd[d] = cpd;
                 sp.R[d] = R;
+                if (R > 1) ctrl->wide_stencil = 1;
                 tot *= cpd;
             }
             // caller-imposed cap (the reference-shaped cache holds cell_cap cells per system, cell_list.py:131-150)

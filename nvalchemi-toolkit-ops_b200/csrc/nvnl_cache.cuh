@@ -91,10 +91,14 @@ __global__ void k_import_sys(unsigned char* __restrict__ ws, WsLayout L, int num
                     need = (rr >= 1.0 && rr < 64.0) ? (int)rr : 1;
                     if (!(rr < 64.0)) atomicOr(&ctrl->error, ERR_IMAGE_RANGE);
                 } else {
-                    need = cpd > 1 ? 1 : 0;
+                    // capped builds grid the unit cell along open dimensions too (atoms outside sit in the edge cells)
+                    const double rr = ceil(rc * (double)cpd / sp.face[d]);
+                    need = (rr >= 1.0 && rr < 64.0) ? (int)rr : 1;
+                    need = need < cpd - 1 ? need : cpd - 1;
                 }
                 sp.cpd[d] = cpd;
                 sp.R[d] = R > need ? R : need;
+                if (sp.R[d] > 1) ctrl->wide_stencil = 1;
                 sp.fmin[d] = 0.0;
                 sp.fscale[d] = sp.pbc[d] ? (double)cpd : 0.0;
                 tot *= cpd;

@@ -63,7 +63,7 @@ struct Ctrl {
     unsigned long long total_pairs;  // 64-bit sum of num_neighbors (overflow check for int32 ptr)
     unsigned long long rows_cursor;  // single-sweep COO path: next free entry of the temporary row buffer
     int rows_overflow;               // single-sweep COO path: the temporary row buffer was too small (host falls back)
-    int pad0;
+    int wide_stencil;                // some system searches more than one cell per side (periodic shifts may exceed +-1)
 };
 
 // Sorted candidate record: position + original atom index. 16 B (float) / 32 B (double) so that a

@@ -33,13 +33,14 @@ namespace nvnl {
 #define NVNL_ROWS_MINB 4
 #endif
 #ifndef NVNL_ROWS_RING_KB
-#define NVNL_ROWS_RING_KB 44
+#define NVNL_ROWS_RING_KB 40
 #endif
 constexpr int kRowsCons = NVNL_ROWS_CONS;             // consumer warps per CTA
 constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
 constexpr int kRowsMinBlocks = NVNL_ROWS_MINB;        // CTAs per SM
 constexpr int kRowsDesc = 6;                          // tiles in flight per CTA (descriptor ring)
 constexpr int kRowsRingBytes = NVNL_ROWS_RING_KB * 1024;   // staged records of the tiles in flight
+constexpr int kRowsZeroBytes = 8 * 1024;              // shared-memory zero block behind the fused zero-fill (TMA bulk stores)
 constexpr int kRowsMaxVC = 64;                        // 32-candidate chunks per tile (two mask words per lane and target)
 constexpr int kRowsMaxSeg = 32;                       // shift segments per tile (one per image at most)
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
@@ -66,7 +67,7 @@ struct RowsSmem {
     RowsDesc desc[kRowsDesc];
     int e_st[32], e_cn[32], e_key[32], e_tag[32];                           // producer scratch (shift sort)
     unsigned long long full[kRowsDesc], empty[kRowsDesc];                   // mbarriers of the descriptor ring
-    int zero_next;                                                          // next piece of the CTA's zero-fill slice
+    alignas(128) unsigned char zeros[kRowsZeroBytes];                       // source of the TMA zero-fill stores
 };
 
 constexpr size_t rows_smem_bytes() { return (size_t)kRowsRingBytes + sizeof(RowsSmem); }
@@ -116,6 +117,13 @@ __device__ __forceinline__ int lds_b32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// 1-D TMA bulk copy shared -> global (bulk-group completion).  dst/src 16-byte aligned, bytes a positive multiple of 16.
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // m |= bit where d < rc2: one FSETP and one predicated LOP
@@ -428,11 +436,6 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
 // copy) into the byte ring.  Warps 0..kRowsCons-1 (consumers): claim four targets of the current tile at a time,
 // sweep, emit rows.  No CTA-wide barrier in the steady state.
 // ------------------------------------------------------------------------------------------------
-struct RowsZero {
-    int4* base;                 // the caller's (speculatively sized) shifts buffer, viewed as int4
-    long long pos, end;         // this CTA's slice [pos, end), handed out in 2048-int4 pieces through smem counter
-};
-
 template <bool HALF, bool FMA>
 __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const RowsArgs a) {
     using T = float;
@@ -459,44 +462,28 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
     // unwrapped inputs are served by the two-pass kernels launched next to this one
     const bool active = ctrl->unwrapped == 0;
     // Zero-fill of the caller's shifts buffer, fused into the sweep: the sweep is issue-bound and leaves HBM idle, the
-    // zero-fill is pure HBM writes.  Every CTA owns one slice, handed out in pieces through a shared counter: the
-    // producer warp takes pieces while it waits for ring space, every warp takes the remaining ones before it exits.
+    // zero-fill is pure HBM writes.  Every CTA owns one slice; its producer thread writes it with TMA bulk STORES from a
+    // zeroed shared-memory block — the copy engine moves the bytes, no SM instruction or LSU slot is spent on them —
+    // a quota per published tile (paced over the kernel's lifetime), the rest when the queue is drained.
     // (A separate memset kernel does not do: next to this kernel's large CTAs it only runs if the SM already has the
     // large shared-memory carve-out, otherwise the two serialise — profiles/r2_zero_overlap.txt.)
-    constexpr long long kZeroPiece = 2048;   // int4 per piece (32 KB)
-    int4* const zbase = reinterpret_cast<int4*>(a.prezero);
-    long long zlo = 0, zhi = 0;
+    unsigned char* const zbase = reinterpret_cast<unsigned char*>(a.prezero);
+    long long zpos = 0, zend = 0, zquota = 0;    // bytes
     if (a.prezero) {
         const long long n16 = a.prezero_ints >> 2;
         const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
-        zlo = (long long)blockIdx.x * slice;
-        zhi = zlo + slice < n16 ? zlo + slice : n16;
-        if (zlo > zhi) zlo = zhi;
+        long long lo = (long long)blockIdx.x * slice, hi = lo + slice < n16 ? lo + slice : n16;
+        if (lo > hi) lo = hi;
+        zpos = lo * 16; zend = hi * 16;
         if (blockIdx.x == 0 && tid < (int)(a.prezero_ints & 3)) a.prezero[(n16 << 2) + tid] = 0;
     }
-    const int zpieces = (int)((zhi - zlo + kZeroPiece - 1) / kZeroPiece);
-    auto zero_piece = [&]() -> bool {   // one piece by this warp; false when the slice is done
-        int pc = 0;
-        if (lane == 0) pc = atomicAdd(&sm.zero_next, 1);
-        pc = __shfl_sync(0xffffffffu, pc, 0);
-        if (pc >= zpieces) return false;
-        const long long b = zlo + (long long)pc * kZeroPiece;
-        const long long e = b + kZeroPiece < zhi ? b + kZeroPiece : zhi;
-        const int4 z4 = make_int4(0, 0, 0, 0);
-        long long k = b + lane;
-        for (; k + 224 < e; k += 256) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) zbase[k + 32 * u] = z4;
-        }
-        for (; k < e; k += 32) zbase[k] = z4;
-        return true;
-    };
+    for (int k = tid; k < kRowsZeroBytes / 16; k += kRowsThreads) reinterpret_cast<int4*>(sm.zeros)[k] = make_int4(0, 0, 0, 0);
+    fence_proxy_async_smem();   // the zero block is read by the async proxy (TMA stores)
     if (tid == 0) {
         for (int st = 0; st < kRowsDesc; ++st) {
             mbar_init(reinterpret_cast<uint64_t*>(&sm.full[st]), 1);
             mbar_init(reinterpret_cast<uint64_t*>(&sm.empty[st]), kRowsCons);
         }
-        sm.zero_next = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -509,14 +496,27 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
         int2* deferred = reinterpret_cast<int2*>(a.ws + a.L.deferred);
         int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
         const int total_cells = active ? ctrl->total_cells : 0;
+        // zero-fill quota per published tile: the slice spread over the tiles this CTA is expected to produce
+        zquota = ((zend - zpos) / (total_cells / (int)gridDim.x + 1) + kRowsZeroBytes) / kRowsZeroBytes * kRowsZeroBytes;
         // descriptor ring + byte ring (FIFO): tiles [oldest, nprod) are live
         int nprod = 0, oldest = 0;
         int head = 0, used = 0;
         int g_next = 0;
         if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
         // grid of the current system (reloaded only when the system changes)
-        int s_cur = -1, cpd0 = 1, cpd1 = 1, cpd2 = 1, R0 = 0, R1 = 0, R2 = 0, pb0 = 0, pb1 = 0, pb2 = 0, coff = 0;
-        bool zeroing = zpieces > 0;
+        int s_cur = -1, cpd0 = 1, cpd1 = 1, cpd2 = 1, R0 = 0, R1 = 0, R2 = 0, pb0 = 0, pb1 = 0, pb2 = 0, coff = 0, c01 = 1;
+        float rcp0 = 1.f, rcp01 = 1.f;   // reciprocals for the cell-coordinate division (corrected exactly below)
+        bool r111 = false;
+        auto zero_some = [&](long long quota) {   // lane 0: TMA bulk stores of zeros, up to `quota` bytes of the slice
+            long long e = zpos + quota;
+            e = e < zend ? e : zend;
+            while (zpos < e) {
+                const long long nb = e - zpos < kRowsZeroBytes ? e - zpos : kRowsZeroBytes;
+                tma_store_1d(zbase + zpos, sm.zeros, (uint32_t)nb);
+                zpos += nb;
+            }
+            tma_store_commit();
+        };
         for (;;) {
             // ---- 1. prepare the next cell entirely in registers (dependent global loads, image enumeration, shift
             //         sort, aligned layout) BEFORE waiting for ring space ----
@@ -545,6 +545,56 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     R0 = sp.R[0]; R1 = sp.R[1]; R2 = sp.R[2];
                     pb0 = sp.pbc[0]; pb1 = sp.pbc[1]; pb2 = sp.pbc[2];
                     coff = sp.cell_offset;
+                    c01 = cpd0 * cpd1;
+                    rcp0 = 1.0f / (float)cpd0;
+                    rcp01 = 1.0f / (float)c01;
+                    r111 = R0 == 1 && R1 == 1 && R2 == 1;   // the common 3 x 3 x 3 stencil
+                }
+                // cell coordinates: float-reciprocal quotient, corrected to the exact one
+                int cx, cy, cz;
+                {
+                    const int local = g - coff;
+                    int q = (int)((float)local * rcp01), r = local - q * c01;
+                    while (r < 0) { --q; r += c01; }
+                    while (r >= c01) { ++q; r -= c01; }
+                    cz = q;
+                    int q2 = (int)((float)r * rcp0), r2 = r - q2 * cpd0;
+                    while (r2 < 0) { --q2; r2 += cpd0; }
+                    while (r2 >= cpd0) { ++q2; r2 -= cpd0; }
+                    cy = q2; cx = r2;
+                }
+                auto defer_cell = [&]() {
+                    // leave the cell to the general kernel as work items of kDeferTargets target atoms; its atoms have
+                    // no temporary row
+                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
+                    int base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd(&ctrl->n_deferred, nitems);
+                        ctrl->had_deferred = 1;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
+                    for (int k = lane; k < ntarget; k += 32) row_ref[sorted[home_start + k].j] = -1;
+                };
+                if (r111 && cx >= 1 && cx <= cpd0 - 2 && cy >= 1 && cy <= cpd1 - 2 && cz >= 1 && cz <= cpd2 - 2) {
+                    // ---- interior cell (no wrap, every stencil cell in range): the stencil is nine runs of three
+                    //      x-adjacent cells, contiguous in the sorted array — nine lanes, two loads each, nine copies
+                    st = 0; cn = 0;
+                    if (lane < 9) {
+                        const int gc0 = g + (lane % 3 - 1) * cpd0 + (lane / 3 - 1) * c01 - 1;
+                        st = cell_start[gc0];
+                        cn = cell_start[gc0 + 3] - st;
+                    }
+                    const int incl = warp_incl_scan(cn, lane);
+                    aoff = incl - cn;
+                    total = __shfl_sync(0xffffffffu, incl, 31);
+                    nvc = ((total + 63) >> 6) << 1;    // chunk count padded to an even number (two chunks per trip)
+                    if (nvc > kRowsMaxVC) { defer_cell(); continue; }
+                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0; nseg = 1; hm = 1u; head_lane = lane == 0;
+                    shiftmask = 0u; key = 0; grp_cn = cn;
+                    home_slot = __shfl_sync(0xffffffffu, aoff, 4) + (home_start - __shfl_sync(0xffffffffu, st, 4));
+                    have = true;
+                    break;
                 }
                 const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
                 const int nimg = nx * ny * nzz;
@@ -552,10 +602,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 int tag = 0;
                 st = 0; cn = 0; key = kKeyEmpty;
                 if (ok && lane < nimg) {
-                    const int local = g - coff;
-                    const int cx = local % cpd0, cy = (local / cpd0) % cpd1, cz = local / (cpd0 * cpd1);
                     int dx, dy, dz;
-                    const bool r111 = R0 == 1 && R1 == 1 && R2 == 1;   // the common 3 x 3 x 3 stencil
                     if (r111) { dx = lane % 3 - 1; dy = (lane / 3) % 3 - 1; dz = lane / 9 - 1; }
                     else { dx = lane % nx - R0; dy = (lane / nx) % ny - R1; dz = lane / (nx * ny) - R2; }
                     int tx = cx + dx, ty = cy + dy, tz = cz + dz;
@@ -637,20 +684,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     }
                 }
                 ok = ok && nvc <= kRowsMaxVC && nseg <= kRowsMaxSeg;
-                if (!ok) {
-                    // leave the cell to the general kernel as work items of kDeferTargets target atoms; its atoms have
-                    // no temporary row
-                    const int nitems = (ntarget + kDeferTargets - 1) / kDeferTargets;
-                    int base = 0;
-                    if (lane == 0) {
-                        base = atomicAdd(&ctrl->n_deferred, nitems);
-                        ctrl->had_deferred = 1;
-                    }
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
-                    for (int k = lane; k < ntarget; k += 32) row_ref[sorted[home_start + k].j] = -1;
-                    continue;
-                }
+                if (!ok) { defer_cell(); continue; }
                 const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
                 const int home_lane = __ffs(tagm) - 1;
                 home_slot = __shfl_sync(0xffffffffu, aoff, home_lane);
@@ -670,7 +704,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 have = true;
                 break;
             }
-            // ---- 2. descriptor slot + ring space (FIFO release; the wait is spent zero-filling), then publish the tables
+            // ---- 2. descriptor slot + ring space (FIFO release), then publish the tables
             //         and issue the copies ----
             const int dslot = nprod % kRowsDesc;
             const int bytes = have ? nvc * 32 * (int)RS : 0;
@@ -682,7 +716,6 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 const int os = oldest % kRowsDesc;
                 uint64_t* eb = reinterpret_cast<uint64_t*>(&sm.empty[os]);
                 const uint32_t ep = (uint32_t)((oldest / kRowsDesc) & 1);
-                while (zeroing && !mbar_test(eb, ep)) zeroing = zero_piece();
                 mbar_wait_backoff(eb, ep);
                 used -= sm.desc[os].footprint;
                 ++oldest;
@@ -738,7 +771,10 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 tma_load_1d(smem_raw + data_off + (size_t)aoff * RS, sorted + st, (uint32_t)grp_cn * RS,
                             reinterpret_cast<uint64_t*>(&sm.full[dslot]));
             ++nprod;
+            if (lane == 0 && zpos < zend) zero_some(zquota);
         }
+        if (lane == 0 && zpos < zend) zero_some(zend - zpos);
+        if (lane == 0 && a.prezero) tma_store_wait_all();
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
         if (lane == 0) {
             __threadfence();
@@ -778,9 +814,6 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[dslot]));
         }
     }
-    // whatever is left of this CTA's zero-fill slice
-    if (zpieces > 0)
-        while (zero_piece()) {}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -791,7 +824,10 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
 // Atoms with row_ref < 0 were handled by the general kernel, which writes their rows itself.
 // ------------------------------------------------------------------------------------------------
 constexpr int kOutWarps = 8;
-constexpr int kOutCap = 2048;   // staging entries per warp (8 KB)
+#ifndef NVNL_OUT_CAP
+#define NVNL_OUT_CAP 2048
+#endif
+constexpr int kOutCap = NVNL_OUT_CAP;   // staging entries per warp (8 KB)
 
 __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int value, int lane) {
     int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);

@@ -36,11 +36,11 @@ _SIGNATURES = {
     "nvnl_count_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_void_p]),
     "nvnl_fill_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
-                               c_int64, c_void_p, c_int32, c_int32, c_void_p]),
+                               c_int64, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_rows_speculative": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int32,
                                            c_void_p]),
     "nvnl_fill_coo": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
-                              c_int64, c_void_p, c_int32, c_int32, c_void_p]),
+                              c_int64, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_matrix": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "nvnl_export_cache": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -51,8 +51,8 @@ _SIGNATURES = {
                                          c_void_p, c_void_p]),
     "nvnl_moved_beyond": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_double, c_void_p, c_void_p]),
     "nvnl_get_grid": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
-    "nvnl_unpack_gathered": (c_int, [c_void_p, c_int32, c_int64, c_int64, ctypes.POINTER(c_int64), c_void_p, c_int64,
-                                     c_void_p, c_void_p]),
+    "nvnl_pack_shifts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nvnl_expand_gathered": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

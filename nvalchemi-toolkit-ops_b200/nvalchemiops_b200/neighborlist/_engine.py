@@ -56,12 +56,13 @@ def cutoff_sq_in_dtype(cutoff: float, dtype: torch.dtype, python_double: bool = 
 class CellListHandle:
     """Result of ``build``: the opaque device workspace plus what the queries need."""
 
-    __slots__ = ("ws", "dtype_code", "n", "ns", "batch_idx", "dtype", "device", "cutoff", "rows_overflow")
+    __slots__ = ("ws", "dtype_code", "n", "ns", "batch_idx", "dtype", "device", "cutoff", "rows_overflow", "wide_stencil")
 
     def __init__(self, ws, dtype_code, n, ns, batch_idx, dtype, device, cutoff):
         self.ws, self.dtype_code, self.n, self.ns = ws, dtype_code, n, ns
         self.batch_idx, self.dtype, self.device, self.cutoff = batch_idx, dtype, device, cutoff
         self.rows_overflow = False
+        self.wide_stencil = False   # (known after status(): some system searches more than one cell per side)
 
 
 def _stream(device) -> ctypes.c_void_p:
@@ -197,7 +198,8 @@ def status(h: CellListHandle):
             "nvnl_status",
         )
     h.rows_overflow = bool(ro.value)
-    return tp.value, mc.value, tc.value, eb.value, (1 if uw.value else 0) | (2 if hd.value else 0)
+    h.wide_stencil = bool(uw.value & 2)
+    return tp.value, mc.value, tc.value, eb.value, (1 if (uw.value & 1) else 0) | (2 if hd.value else 0)
 
 
 def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, fill_value,
@@ -274,16 +276,17 @@ def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=Fal
 
 
 def fill_coo(h: CellListHandle, cutoff_sq, neighbor_ptr, edge_index, shifts, num_pairs, half_fill=False,
-             index_offset=0, launch_hint=-1, rows=False):
+             index_offset=0, launch_hint=-1, rows=False, row_stride=0):
     """Write COO rows at neighbor_ptr (nvnl_fill_coo, or nvnl_fill_rows after ``count(rows=True)``).  ``edge_index``
-    is [2, num_pairs] (or a block laid out as such with row stride ``num_pairs``), ``shifts`` [num_pairs, 3]."""
+    is [2, num_pairs], ``shifts`` [num_pairs, 3]; with ``row_stride`` > 0 the two rows of ``edge_index`` are
+    ``row_stride`` entries apart (a rank writing its own range of a larger global array)."""
     L = _lib.lib()
     fn, name = (L.nvnl_fill_rows, "nvnl_fill_rows") if rows else (L.nvnl_fill_coo, "nvnl_fill_coo")
     with torch.cuda.device(h.device):
         _lib.check(
             fn(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
                int(bool(half_fill)), int(bool(config.fma)), _ptr(neighbor_ptr), _ptr(edge_index),
-               int(num_pairs), _ptr(shifts), int(index_offset), int(launch_hint), _stream(h.device)),
+               int(num_pairs), int(row_stride), _ptr(shifts), int(index_offset), int(launch_hint), _stream(h.device)),
             name,
         )
 

@@ -121,8 +121,8 @@ def _estimate_grid(cell: torch.Tensor, pbc: torch.Tensor, cutoff: float, max_nbi
     col0 = torch.stack([e * i - f * h, f * g - d * i, d * h - e * g], dim=1)
     col1 = torch.stack([cc * h - b * i, a * i - cc * g, b * g - a * h], dim=1)
     col2 = torch.stack([b * f - cc * e, cc * d - a * f, a * e - b * d], dim=1)
-    inv_t = torch.stack([col0, col1, col2], dim=1) / det[:, None, None]
-    face = 1.0 / torch.linalg.vector_norm(inv_t, dim=2)
+    inv_t = torch.stack([col0, col1, col2], dim=1) * (1.0 / det)[:, None, None]
+    face = 1.0 / torch.sqrt(inv_t[:, :, 0] * inv_t[:, :, 0] + inv_t[:, :, 1] * inv_t[:, :, 1] + inv_t[:, :, 2] * inv_t[:, :, 2])
     rc = torch.tensor(cutoff, dtype=cell.dtype, device=cell.device)
     cpd = torch.clamp((face / rc).to(torch.int64), min=1)
     open_single = (cpd == 1) & ~pbc.reshape(-1, 3).to(device=cell.device, dtype=torch.bool)

@@ -1,16 +1,24 @@
-"""Batch-sharded multi-GPU neighbor lists: one process per GPU, ONE payload all-gather.
+"""Batch-sharded multi-GPU neighbor lists: one process per GPU, ranks exchange only what cannot be recomputed.
 
-The reference has no distributed code (no NCCL / torch.distributed call sites); this module is
-the multi-GPU step BASELINE.json's north_star defines: independent systems are split by ``batch_ptr`` across the
-ranks of one node, every rank builds the COO list of its own systems with GLOBAL atom indices, and a single
-``all_gather_into_tensor`` over NCCL (NVLink 5 / NVSwitch) re-assembles the global ``edge_index`` / ``shifts`` /
-``neighbor_ptr`` on every rank.  Semantics: identical to running the whole batch on one GPU, up to the order of
-entries inside a source atom's row (which the reference leaves unspecified).
+The reference has no distributed code (no NCCL / torch.distributed call sites); this module is the
+multi-GPU step BASELINE.json's north_star defines: independent systems are split by ``batch_ptr`` across the ranks of
+one node, every rank builds the COO list of its own systems with GLOBAL atom indices, and an all-gather over NCCL
+(NVLink 5 / NVSwitch) re-assembles the global ``edge_index`` / ``shifts`` / ``neighbor_ptr`` on every rank.
+Semantics: identical to running the whole batch on one GPU, up to the order of entries inside a source atom's row
+(which the reference leaves unspecified).
 
-Wire format of a rank's block (int32, all ranks padded to the same length):
-    [ src (Pmax) | dst (Pmax) | shifts (3*Pmax) | num_neighbors (Nmax) ]
-The fill kernel writes src/dst/shifts straight into the block (no pack pass); ``nvnl_unpack_gathered`` writes the
-global arrays from the gathered blocks (one kernel).
+Data flow (no padded blocks, no re-assembly pass over the payload):
+  1. local build + sweep (counts);  ONE small all-gather of (pairs, atoms, max count, error bits, flags) per rank — every
+     rank then knows every offset and raises the same errors at the same point;
+  2. every rank writes its OWN range straight into the final global arrays (``nvnl_fill_rows`` with the global row
+     stride) and packs its shifts into one byte per pair (``nvnl_pack_shifts``);
+  3. variable-size gather = one NCCL broadcast per rank and array, IN PLACE on slices of the final arrays, grouped into
+     one NCCL group: per pair only the target atom (4 B) and the packed shift (1 B) travel, per atom ``num_neighbors``
+     — 5 B/pair instead of 20;
+  4. ``neighbor_ptr`` = scan of the gathered counts; ``nvnl_expand_gathered`` writes the source atoms and int32 shifts of
+     the foreign ranges from it.
+If some shift does not fit the packed byte (unwrapped coordinates, boxes smaller than the cutoff) the source atoms and
+int32 shifts are broadcast instead (20 B/pair, still in place).
 """
 from __future__ import annotations
 
@@ -20,6 +28,8 @@ import torch
 import torch.distributed as dist
 
 from .neighbor_utils import NeighborOverflowError
+
+_partition_cache: dict = {}
 
 
 def partition_systems(batch_ptr_host, world_size: int):
@@ -43,41 +53,102 @@ def partition_systems(batch_ptr_host, world_size: int):
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
-def _default_local_coo(positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset, block_builder):
-    """CUDA path: count -> (sizes exchanged by the caller) -> fill straight into the send block."""
-    from . import _engine
-
-    h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
-    csq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
-    num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, csq, half_fill)
-    _engine._raise_on_error_bits(err)
-
-    def fill(block, pmax):
-        if total > 0:
-            _engine.fill_coo(h, csq, ptr, block[: 2 * pmax], block[2 * pmax: 5 * pmax], pmax, half_fill, index_offset,
-                             launch_hint=hint, rows=rows)
-
-    return num, total, max_count, fill
+def _partition(batch_ptr, world):
+    """Partition of ``batch_ptr`` (device tensor) over ``world`` ranks, cached per tensor identity + version so that
+    repeated calls on the same batch pay no device->host copy."""
+    key = (batch_ptr.data_ptr(), batch_ptr._version, batch_ptr.shape[0], world, str(batch_ptr.device))
+    hit = _partition_cache.get(key)
+    if hit is None:
+        ptr_host = batch_ptr.detach().cpu().tolist()
+        parts = partition_systems(ptr_host, world)
+        hit = (parts, [(ptr_host[a], ptr_host[b]) for a, b in parts], ptr_host[-1])
+        if len(_partition_cache) > 64:
+            _partition_cache.clear()
+        _partition_cache[key] = hit
+    return hit
 
 
-def _torch_unpack(recv, world, pmax, nmax, counts, natoms, total, device):
-    """Reference re-assembly with torch slicing (CPU/gloo tests; the CUDA path uses nvnl_unpack_gathered)."""
-    blk = 5 * pmax + nmax
-    edge = torch.empty((2, total), dtype=torch.int32, device=device)
-    shifts = torch.empty((total, 3), dtype=torch.int32, device=device)
-    o = 0
-    for g in range(world):
-        b = recv[g * blk:(g + 1) * blk]
-        c = counts[g]
-        edge[0, o:o + c] = b[:c]
-        edge[1, o:o + c] = b[pmax:pmax + c]
-        shifts[o:o + c] = b[2 * pmax:2 * pmax + 3 * c].reshape(c, 3)
-        o += c
-    return edge, shifts
+class _CudaShard:
+    """A rank's own systems on the CUDA path: build + count now, fill into caller-provided (global) arrays later."""
+
+    def __init__(self, positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset):
+        from . import _engine
+
+        self._e = _engine
+        self.h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
+        self.csq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
+        self.half_fill, self.index_offset = half_fill, index_offset
+        self.num, self.ptr, self.total, self.max_count, self.err, self.hint, self.rows = _engine.count_and_size(
+            self.h, self.csq, half_fill)
+        # shifts fit one byte when no atom lies outside the primary image and no stencil is wider than one cell
+        self.packable = not (self.hint & 1) and not self.h.wide_stencil
+
+    def fill(self, edge_rows, shifts, row_stride):
+        """edge_rows: flat view of the global edge_index starting at this rank's first pair of row 0 (row 1 is
+        ``row_stride`` entries further); shifts: view of the rank's own rows of the global shifts."""
+        if self.total > 0:
+            self._e.fill_coo(self.h, self.csq, self.ptr, edge_rows, shifts, self.total, self.half_fill, self.index_offset,
+                             launch_hint=self.hint, rows=self.rows, row_stride=row_stride)
+
+
+def _pack_shifts(shifts_own, packed_own):
+    if shifts_own.is_cuda:
+        from .. import _lib
+
+        with torch.cuda.device(shifts_own.device):
+            _lib.check(_lib.lib().nvnl_pack_shifts(ctypes.c_void_p(shifts_own.data_ptr()), shifts_own.shape[0],
+                                                   ctypes.c_void_p(packed_own.data_ptr()), None,
+                                                   ctypes.c_void_p(torch.cuda.current_stream(shifts_own.device).cuda_stream)),
+                       "nvnl_pack_shifts")
+    else:  # gloo tests of the plumbing (CPU tensors only ever get here through the _local_shard test hook)
+        s = (shifts_own + 1).to(torch.uint8)
+        packed_own.copy_(s[:, 0] | (s[:, 1] << 2) | (s[:, 2] << 4))
+
+
+def _expand(neighbor_ptr, n_atoms, a0, a1, packed, edge, shifts):
+    if edge.is_cuda:
+        from .. import _lib
+
+        with torch.cuda.device(edge.device):
+            _lib.check(_lib.lib().nvnl_expand_gathered(ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, a0, a1,
+                                                       ctypes.c_void_p(packed.data_ptr()), ctypes.c_void_p(edge.data_ptr()),
+                                                       ctypes.c_void_p(shifts.data_ptr()),
+                                                       ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)),
+                       "nvnl_expand_gathered")
+    else:
+        counts = torch.diff(neighbor_ptr).long()
+        src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), counts)
+        p = packed.to(torch.int32)
+        full = torch.stack([(p & 3) - 1, ((p >> 2) & 3) - 1, ((p >> 4) & 3) - 1], dim=1).to(torch.int32)
+        lo, hi = int(neighbor_ptr[a0]), int(neighbor_ptr[a1])
+        keep_e, keep_s = edge[0, lo:hi].clone(), shifts[lo:hi].clone()
+        edge[0].copy_(src)
+        shifts.copy_(full)
+        edge[0, lo:hi] = keep_e
+        shifts[lo:hi] = keep_s
+
+
+def _gather_slices(arrays_by_rank, rank, group):
+    """Variable-size all-gather IN PLACE: ``arrays_by_rank[k][g]`` is the contiguous view of array k that rank g owns
+    (already filled on rank g); afterwards every view is filled on every rank.
+    NCCL: one ``all_gather`` per array — for uneven sizes ProcessGroupNCCL issues it as ONE group of ncclBroadcasts
+    straight into the output views (no staging copy).  Other backends (the gloo tests): one broadcast per view."""
+    world = len(arrays_by_rank[0])
+    dev = arrays_by_rank[0][0].device
+    if dev.type == "cuda":
+        for views in arrays_by_rank:
+            if sum(v.numel() for v in views) > 0:
+                dist.all_gather(list(views), views[rank], group=group)
+        return
+    root = (lambda g: dist.get_global_rank(group, g)) if group is not None else (lambda g: g)
+    for views in arrays_by_rank:
+        for g in range(world):
+            if views[g].numel() > 0:
+                dist.broadcast(views[g], src=root(g), group=group)
 
 
 def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fill=False, max_neighbors=None,
-                                group=None, gather=True, _local_coo=None):
+                                group=None, gather=True, _local_shard=None, return_stats=False):
     """COO neighbor list of a batch, sharded over the ranks of ``group`` (default: WORLD).
 
     Every rank passes the SAME global tensors (on its own device): ``positions`` [N,3], ``cell`` [S,3,3],
@@ -85,79 +156,101 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     ``(neighbor_list [2,P] int32, neighbor_ptr [N+1] int32, shifts [P,3] int32)`` with global atom indices.
     With ``gather=False`` the collective is skipped and the rank's own shard is returned as
     ``(neighbor_list, neighbor_ptr_local, shifts, (atom_lo, atom_hi))`` — the "kernels only" figure of the bench.
+    ``return_stats=True`` appends a dict (bytes received from peers, packed or not).
 
-    ``_local_coo`` is a test hook (CPU/gloo tests inject the oracle); the product path leaves it None.
+    ``_local_shard`` is a test hook (CPU/gloo tests inject an oracle-backed shard); the product path leaves it None.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = positions.device
-    ptr_host = batch_ptr.detach().cpu().tolist()
-    S = len(ptr_host) - 1
     N = positions.shape[0]
-    s0, s1 = partition_systems(ptr_host, world)[rank]
-    a0, a1 = ptr_host[s0], ptr_host[s1]
+    parts, atom_ranges, n_total = _partition(batch_ptr, world)
+    if n_total != N:
+        raise ValueError("batch_ptr[-1] must equal the number of atoms")
+    s0, s1 = parts[rank]
+    a0, a1 = atom_ranges[rank]
     n_loc = a1 - a0
-    local_fn = _local_coo or _default_local_coo
+    make = _local_shard or _CudaShard
     if n_loc > 0:
         lptr = (batch_ptr[s0:s1 + 1] - a0).to(torch.int32)
         lidx = torch.repeat_interleave(torch.arange(s1 - s0, dtype=torch.int32, device=dev),
                                        (lptr[1:] - lptr[:-1]).long())
-        num, total, max_count, fill = local_fn(positions[a0:a1], cutoff, cell[s0:s1], pbc[s0:s1], lidx, lptr,
-                                               half_fill, a0, None)
+        shard = make(positions[a0:a1], cutoff, cell[s0:s1], pbc[s0:s1], lidx, lptr, half_fill, a0)
+        total, max_count, err, packable, num = shard.total, shard.max_count, shard.err, shard.packable, shard.num
     else:
+        shard, total, max_count, err, packable = None, 0, 0, 0, True
         num = torch.zeros(0, dtype=torch.int32, device=dev)
-        total, max_count = 0, 0
-
-        def fill(block, pmax):
-            return None
-
-    if max_neighbors is not None and max_count > max_neighbors:
-        raise NeighborOverflowError(max_neighbors, max_count)
 
     if not gather or world == 1:
-        block = torch.empty(5 * max(total, 1), dtype=torch.int32, device=dev)
-        fill(block, total)
-        edge = block[:2 * total].reshape(2, total)
-        shifts = block[2 * total:5 * total].reshape(total, 3)
+        from ._engine import _raise_on_error_bits
+
+        _raise_on_error_bits(err)
+        if max_neighbors is not None and max_count > max_neighbors:
+            raise NeighborOverflowError(max_neighbors, max_count)
+        edge = torch.empty((2, total), dtype=torch.int32, device=dev)
+        shifts = torch.empty((total, 3), dtype=torch.int32, device=dev)
+        if shard is not None:
+            shard.fill(edge.view(-1), shifts, total)
         lp = torch.zeros(n_loc + 1, dtype=torch.int32, device=dev)
         torch.cumsum(num, 0, out=lp[1:])
         if world == 1:
-            return edge, lp, shifts
+            return (edge, lp, shifts, {"peer_bytes": 0, "packed": False}) if return_stats else (edge, lp, shifts)
         return edge, lp, shifts, (a0, a1)
 
-    # ---- sizes (tiny all-gather), then ONE payload all-gather ----
-    sizes = torch.tensor([total, n_loc], dtype=torch.int64, device=dev)
-    all_sizes = torch.empty(2 * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-    all_sizes = all_sizes.cpu().tolist()
-    counts = all_sizes[0::2]
-    natoms = all_sizes[1::2]
-    pmax, nmax = max(max(counts), 1), max(max(natoms), 1)
+    # ---- 1. one small all-gather: every rank learns every size and raises the same errors at the same point ----
+    mine = torch.tensor([total, max_count, err, 1 if packable else 0], dtype=torch.int64, device=dev)
+    everyone = torch.empty(4 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(everyone, mine, group=group)
+    everyone = everyone.cpu().tolist()
+    counts = everyone[0::4]
+    from ._engine import _raise_on_error_bits
+
+    err_all = 0
+    for e in everyone[2::4]:
+        err_all |= int(e)
+    _raise_on_error_bits(err_all)
+    worst = max(everyone[1::4])
+    if max_neighbors is not None and worst > max_neighbors:
+        raise NeighborOverflowError(max_neighbors, worst)
     P = sum(counts)
     if P > 2**31 - 1:
         raise OverflowError(f"{P} pairs do not fit int32 indices")
-    blk = 5 * pmax + nmax
-    block = torch.empty(blk, dtype=torch.int32, device=dev)
-    fill(block, pmax)
-    block[5 * pmax:5 * pmax + n_loc] = num
-    recv = torch.empty(world * blk, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(recv, block, group=group)
+    packed_ok = all(everyone[3::4])
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
 
-    if dev.type == "cuda" and _local_coo is None:
-        from .. import _lib
+    # ---- 2. every rank writes its own range of the final arrays ----
+    edge = torch.empty((2, P), dtype=torch.int32, device=dev)
+    shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
+    num_all = torch.empty((N,), dtype=torch.int32, device=dev)
+    o0, o1 = offs[rank], offs[rank + 1]
+    if shard is not None:
+        shard.fill(edge.view(-1)[o0:], shifts[o0:o1], P)
+        num_all[a0:a1] = num
+    packed = None
+    if packed_ok:
+        packed = torch.empty((P,), dtype=torch.uint8, device=dev)
+        if o1 > o0:
+            _pack_shifts(shifts[o0:o1], packed[o0:o1])
 
-        edge = torch.empty((2, P), dtype=torch.int32, device=dev)
-        shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
-        cnt_arr = (ctypes.c_int64 * world)(*counts)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().nvnl_unpack_gathered(ctypes.c_void_p(recv.data_ptr()), world, pmax, blk, cnt_arr,
-                                                       ctypes.c_void_p(edge.data_ptr()), P,
-                                                       ctypes.c_void_p(shifts.data_ptr()),
-                                                       ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
-                       "nvnl_unpack_gathered")
+    # ---- 3. variable-size gather, in place ----
+    arrays = [[edge[1, offs[g]:offs[g + 1]] for g in range(world)],
+              [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]]
+    if packed_ok:
+        arrays.append([packed[offs[g]:offs[g + 1]] for g in range(world)])
     else:
-        edge, shifts = _torch_unpack(recv, world, pmax, nmax, counts, natoms, P, dev)
-    num_all = torch.cat([recv[g * blk + 5 * pmax: g * blk + 5 * pmax + natoms[g]] for g in range(world)])
+        arrays.append([edge[0, offs[g]:offs[g + 1]] for g in range(world)])
+        arrays.append([shifts[offs[g]:offs[g + 1]] for g in range(world)])
+    _gather_slices(arrays, rank, group)
+
+    # ---- 4. neighbor_ptr, then the source atoms and shifts of the foreign ranges ----
     neighbor_ptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
     torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
+    if packed_ok:
+        _expand(neighbor_ptr, N, a0, a1, packed, edge, shifts)
+    if return_stats:
+        per_pair = 5 if packed_ok else 20
+        return edge, neighbor_ptr, shifts, {"peer_bytes": per_pair * (P - counts[rank]) + 4 * (N - n_loc),
+                                            "packed": packed_ok}
     return edge, neighbor_ptr, shifts

@@ -83,3 +83,23 @@ def bench_batch(num_systems, atoms_lo, atoms_hi, seed, density=0.1, mixed_pbc=Tr
     else:
         pbc = torch.ones((num_systems, 3), dtype=torch.bool)
     return positions, cell, pbc, batch_idx, batch_ptr
+
+
+def load_published_fcc():
+    """Pair counts the reference publishes for its own FCC benchmark workload (tests/golden/make_fcc_golden.py)."""
+    with open(os.path.join(GOLDEN, "reference_published_fcc.json")) as f:
+        return json.load(f)
+
+
+def fcc_benchmark_system(num_atoms, lattice_constant=4.0, dtype=torch.float32):
+    """The reference benchmark's crystal (benchmarks/systems.py:874-971, restated vectorised): the first ``num_atoms``
+    sites of the n^3 FCC supercell, n = ceil((num_atoms / 4)^(1/3)), enumerated in (i, j, k, basis) order; cubic
+    periodic cell of edge n * a."""
+    n = int(np.ceil((num_atoms / 4) ** (1 / 3)))
+    basis = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.5]], dtype=torch.float64)
+    r = torch.arange(n, dtype=torch.float64)
+    origin = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), dim=-1).reshape(-1, 1, 3)     # i slowest, k fastest
+    positions = ((origin + basis) * lattice_constant).reshape(-1, 3)[:num_atoms].to(dtype)
+    cell = (torch.eye(3, dtype=dtype) * (n * lattice_constant)).reshape(1, 3, 3)
+    pbc = torch.tensor([True, True, True]).reshape(1, 3)
+    return positions, cell, pbc

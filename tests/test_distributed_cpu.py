@@ -1,5 +1,5 @@
-"""world_size-2 gloo tests (CPU) of the batch-sharding logic: partitioning, global index offsets, the size
-exchange, the padded payload all-gather and the re-assembly.  The per-rank neighbor lists come from the oracle
+"""world_size-2/3 gloo tests (CPU) of the batch-sharding logic: partitioning, global index offsets, the size
+exchange, in-place writes of a rank's own range, the variable-size broadcasts and the expansion of the foreign ranges.  The per-rank neighbor lists come from the oracle
 through the module's test hook — the collective plumbing is what is under test here; the CUDA local path is
 covered by the -m gpu tests."""
 import os
@@ -14,20 +14,26 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _oracle_local(positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset, _bb):
-    import reference_oracle as ro
+class _OracleShard:
+    """Test hook for ``sharded_batch_neighbor_list(_local_shard=...)``: a rank's own systems computed by the oracle."""
 
-    e, p, s = ro.batch_cell_list(positions, cutoff, cell, pbc, batch_idx, max_neighbors=2048, half_fill=half_fill,
-                                 return_neighbor_list=True)
-    num = torch.from_numpy(np.diff(p).astype(np.int32))
-    total = int(e.shape[1])
+    def __init__(self, positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset):
+        import reference_oracle as ro
 
-    def fill(block, pmax):
-        block[:total] = torch.from_numpy(e[0]) + index_offset
-        block[pmax:pmax + total] = torch.from_numpy(e[1]) + index_offset
-        block[2 * pmax:2 * pmax + 3 * total] = torch.from_numpy(np.ascontiguousarray(s)).reshape(-1)
+        e, p, s = ro.batch_cell_list(positions, cutoff, cell, pbc, batch_idx, max_neighbors=2048, half_fill=half_fill,
+                                     return_neighbor_list=True)
+        self.e, self.s, self.off = e, np.ascontiguousarray(s), index_offset
+        self.num = torch.from_numpy(np.diff(p).astype(np.int32))
+        self.total = int(e.shape[1])
+        self.max_count = int(self.num.max()) if self.num.numel() else 0
+        self.err = 0
+        self.packable = bool(np.abs(self.s).max() <= 1) if self.total else True
 
-    return num, total, int(num.max()) if num.numel() else 0, fill
+    def fill(self, edge_rows, shifts, row_stride):
+        t = self.total
+        edge_rows[:t] = torch.from_numpy(self.e[0]) + self.off
+        edge_rows[row_stride:row_stride + t] = torch.from_numpy(self.e[1]) + self.off
+        shifts[:t] = torch.from_numpy(self.s)
 
 
 def _worker(rank, world, port, out_dir):
@@ -42,9 +48,9 @@ def _worker(rank, world, port, out_dir):
     from systems import bench_batch
 
     pos, cell, pbc, bidx, bptr = bench_batch(9, 60, 140, seed=5, mixed_pbc=True)
-    e, ptr, s = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_coo=_oracle_local)
+    e, ptr, s = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_shard=_OracleShard)
     torch.save({"e": e, "ptr": ptr, "s": s}, os.path.join(out_dir, f"r{rank}.pt"))
-    shard = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, gather=False, _local_coo=_oracle_local)
+    shard = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, gather=False, _local_shard=_OracleShard)
     torch.save({"e": shard[0], "range": shard[3]}, os.path.join(out_dir, f"s{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -329,10 +329,10 @@ def test_large_cells_multi_tile_path():
         _check_matrix_padding(nm, num, sh, 3000)
 
 
-def test_sharded_blocks_fill_and_unpack_on_one_gpu():
-    """The multi-GPU data path without the collective: two 'ranks' are emulated on one device — each fills its
-    [src | dst | shifts | num] block with global indices (index_offset), the blocks are concatenated the way
-    all_gather_into_tensor would, and nvnl_unpack_gathered re-assembles the global COO arrays."""
+def test_sharded_ranges_fill_pack_and_expand_on_one_gpu():
+    """The multi-GPU data path without the collective: two 'ranks' are emulated on one device — each writes its own range
+    of the FINAL global arrays in place (index_offset + row_stride) and packs its shifts into one byte per pair; what a
+    peer would receive (target atoms, packed shifts, counts) is then expanded by nvnl_expand_gathered."""
     import ctypes
 
     from nvalchemiops_b200 import _lib
@@ -340,6 +340,7 @@ def test_sharded_blocks_fill_and_unpack_on_one_gpu():
     from nvalchemiops_b200.neighborlist.distributed import partition_systems
 
     pos, cell, pbc, bidx, bptr = bench_batch(10, 300, 700, seed=8, mixed_pbc=True)
+    N = pos.shape[0]
     want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1024))
     pos, cell, pbc, bptr_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV), bptr.to(DEV)
     world = 2
@@ -350,28 +351,46 @@ def test_sharded_blocks_fill_and_unpack_on_one_gpu():
         lptr = (bptr_d[s0:s1 + 1] - a0).to(torch.int32)
         lidx = torch.repeat_interleave(torch.arange(s1 - s0, dtype=torch.int32, device=DEV), (lptr[1:] - lptr[:-1]).long())
         h = _engine.build(pos[a0:a1], 6.0, cell[s0:s1], pbc[s0:s1], batch_idx=lidx, batch_ptr=lptr)
-        num, ptr = _engine.count(h, 36.0)
-        total = _engine.status(h)[0]
-        locals_.append((h, num, ptr, total, a0, a1))
-    pmax = max(t[3] for t in locals_)
-    nmax = max(t[5] - t[4] for t in locals_)
-    blk = 5 * pmax + nmax
-    recv = torch.full((world * blk,), -7, dtype=torch.int32, device=DEV)
-    for g, (h, num, ptr, total, a0, a1) in enumerate(locals_):
-        block = recv[g * blk:(g + 1) * blk]
-        _engine.fill_coo(h, 36.0, ptr, block[:2 * pmax], block[2 * pmax:5 * pmax], pmax, False, a0)
-        block[5 * pmax:5 * pmax + (a1 - a0)] = num
+        num, ptr, total, max_count, err, hint, rows = _engine.count_and_size(h, 36.0)
+        assert err == 0 and not h.wide_stencil and not (hint & 1)
+        locals_.append((h, num, ptr, total, a0, a1, hint, rows))
     counts = [t[3] for t in locals_]
     P = sum(counts)
-    edge = torch.empty((2, P), dtype=torch.int32, device=DEV)
-    shifts = torch.empty((P, 3), dtype=torch.int32, device=DEV)
-    cnt_arr = (ctypes.c_int64 * world)(*counts)
-    _lib.check(_lib.lib().nvnl_unpack_gathered(ctypes.c_void_p(recv.data_ptr()), world, pmax, blk, cnt_arr,
-                                               ctypes.c_void_p(edge.data_ptr()), P, ctypes.c_void_p(shifts.data_ptr()),
-                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "unpack")
+    edge = torch.full((2, P), -7, dtype=torch.int32, device=DEV)
+    shifts = torch.full((P, 3), -7, dtype=torch.int32, device=DEV)
+    packed = torch.zeros((P,), dtype=torch.uint8, device=DEV)
+    num_all = torch.empty((N,), dtype=torch.int32, device=DEV)
+    bad = torch.zeros((1,), dtype=torch.int32, device=DEV)
+    off = 0
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (h, num, ptr, total, a0, a1, hint, rows) in locals_:
+        _engine.fill_coo(h, 36.0, ptr, edge[0, off:], shifts[off:off + total], total, False, a0, launch_hint=hint, rows=rows,
+                         row_stride=P)
+        num_all[a0:a1] = num
+        _lib.check(_lib.lib().nvnl_pack_shifts(ctypes.c_void_p(shifts[off:].data_ptr()), total,
+                                               ctypes.c_void_p(packed[off:].data_ptr()), ctypes.c_void_p(bad.data_ptr()), st), "pack")
+        off += total
     torch.cuda.synchronize()
+    assert int(bad.item()) == 0
     assert np.array_equal(ro.records_from_coo(edge.cpu(), shifts.cpu()), want)
     assert (edge[0, 1:] >= edge[0, :-1]).all()
+    nptr = torch.zeros(N + 1, dtype=torch.int32, device=DEV)
+    torch.cumsum(num_all, 0, out=nptr[1:])
+    # what "rank 0" holds after the gather: its own range complete, of the peer only row 1, the packed shifts, the counts
+    a0, a1 = locals_[0][4], locals_[0][5]
+    e2, s2 = edge.clone(), shifts.clone()
+    e2[0, counts[0]:] = -9
+    s2[counts[0]:] = -9
+    _lib.check(_lib.lib().nvnl_expand_gathered(ctypes.c_void_p(nptr.data_ptr()), N, a0, a1, ctypes.c_void_p(packed.data_ptr()),
+                                               ctypes.c_void_p(e2.data_ptr()), ctypes.c_void_p(s2.data_ptr()), st), "expand")
+    torch.cuda.synchronize()
+    assert torch.equal(e2, edge) and torch.equal(s2, shifts)
+    # a shift outside {-1, 0, 1} is reported by the pack kernel
+    s3 = shifts[:100].clone(); s3[17, 1] = 2
+    bad.zero_()
+    _lib.check(_lib.lib().nvnl_pack_shifts(ctypes.c_void_p(s3.data_ptr()), 100, ctypes.c_void_p(packed.data_ptr()),
+                                           ctypes.c_void_p(bad.data_ptr()), st), "pack")
+    assert int(bad.item()) == 1
 
 
 # ----------------------------------------------------------------------------------------------
@@ -438,9 +457,11 @@ def test_estimate_allocate_build_query_end_to_end():
     estimate_cell_list_sizes -> allocate_cell_list -> build_cell_list -> query_cell_list, single and batched, on CUDA
     tensors; the estimates equal the oracle's restatement of cell_list.py:35-99 / batch_cell_list.py:35-99."""
     nl = _nl()
-    for L, rc, pbc_flag, nbins in ((22.0, 4.0, [True, True, True], 1000), (60.0, 3.0, [True, False, True], 1000),
-                                   (60.0, 3.0, [True, True, True], 100000), (7.0, 4.0, [True, True, False], 1000)):
+    for L, rc, pbc_flag, nbins in ((22.0, 4.0, [True, True, True], 1000), (60.4, 3.0, [True, False, True], 1000),
+                                   (60.4, 3.0, [True, True, True], 100000), (7.0, 4.0, [True, True, False], 1000)):
         pos, cell, pbc = random_system(700, L, torch.float32, seed=5, pbc_flag=pbc_flag)
+        if L < 10:
+            pos = pos[:100].clone().repeat(7, 1) + torch.arange(7).repeat_interleave(100)[:, None] * torch.tensor([0.0, 0.0, 40.0])   # sparse stack along the open z
         pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
         cells, radius = nl.estimate_cell_list_sizes(cell_d, pbc_d, rc, max_nbins=nbins)
         want_cells, want_radius = ro.estimate_cell_list_sizes(cell, pbc, rc, max_nbins=nbins)
@@ -566,8 +587,13 @@ def test_torch_compile_build_and_query_ops(batched):
     total = compiled(pos_d, cache2, nm2, sh2, num2).item()
     assert total == eager_total == want.shape[0]
     assert np.array_equal(_records_gpu_matrix(nm2, num2, sh2), want)
-    for a, b in zip(cache, cache2):
+    for a, b in zip(cache[:6], cache2[:6]):
         assert torch.equal(a, b)                                  # compiled build == eager build, tensor by tensor
+    # (the order of atoms inside a cell is not deterministic: compare cell_atom_list cell by cell)
+    starts, counts = cache[5].cpu().tolist(), cache[4].cpu().tolist()
+    la, lb = cache[6].cpu().tolist(), cache2[6].cpu().tolist()
+    for st, cn in zip(starts, counts):
+        assert sorted(la[st:st + cn]) == sorted(lb[st:st + cn])
 
 
 def test_batch_build_query_split():
@@ -971,3 +997,110 @@ def test_experimental_speculative_fill_matches_the_regular_path():
     finally:
         config.prezero_min_pairs, config.speculative_fill = old_min, old_spec
         _engine._pair_history.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 5 at FULL size, and the reference's own published workload
+# ----------------------------------------------------------------------------------------------
+def test_config3_full_size_512_systems_mixed_pbc(coo_path):
+    """Config 3 as BASELINE.json states it: 512 systems x 150-250 atoms, the 8 PBC patterns 64 times each, batch_idx +
+    batch_ptr, COO output — exact set equality with the oracle, on both COO paths."""
+    pos, cell, pbc, bidx, bptr = bench_batch(512, 150, 250, seed=3, mixed_pbc=True)
+    assert sorted({tuple(p) for p in pbc.tolist()}) == sorted({(bool(a), bool(b), bool(c)) for a in (0, 1) for b in (0, 1) for c in (0, 1)})
+    o = ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=320, nthreads=8)
+    assert o[1].max() <= 320
+    want = ro.records_from_matrix(*o)
+    e, p, s = _nl().neighbor_list(pos.to(DEV), 6.0, cell=cell.to(DEV), pbc=pbc.to(DEV), batch_idx=bidx.to(DEV),
+                                  batch_ptr=bptr.to(DEV), return_neighbor_list=True, method="batch_cell_list")
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+    assert np.array_equal((p[1:] - p[:-1]).cpu().numpy(), o[1])
+    assert (e[0, 1:] >= e[0, :-1]).all()
+    b = bidx.to(DEV).long()
+    assert torch.equal(b[e[0].long()], b[e[1].long()]), "no pair crosses a system boundary"
+
+
+def test_config5_full_size_4096_systems_of_1000_atoms():
+    """Config 5 at full size (4096 x 1000 atoms, 3 cells per dimension: every cell touches the periodic boundary):
+    invariants on the complete 3.7e8-pair output, exact per-atom counts and exact set equality with the oracle on every
+    16th system (256 systems, 2.3e7 pairs)."""
+    S, n1 = 4096, 1000
+    pos, cell, pbc, bidx, bptr = bench_batch(S, n1, n1, seed=5, mixed_pbc=False)
+    n = S * n1
+    e, p, s = _nl().neighbor_list(pos.to(DEV), 6.0, cell=cell.to(DEV), pbc=pbc.to(DEV), batch_idx=bidx.to(DEV),
+                                  batch_ptr=bptr.to(DEV), return_neighbor_list=True, method="batch_cell_list")
+    P = e.shape[1]
+    assert p[0].item() == 0 and p[-1].item() == P and (p[1:] >= p[:-1]).all()
+    assert (e[0, 1:] >= e[0, :-1]).all()
+    assert torch.equal(torch.bincount(e[0].long(), minlength=n).to(torch.int32), p[1:] - p[:-1])
+    assert torch.equal(e[0] // n1, e[1] // n1), "no pair crosses a system boundary"
+    assert s.abs().max().item() <= 1 and abs(P / n - 90.4) < 0.5
+    # symmetry {(i, j, s)} == {(j, i, -s)} through an order-independent 64-bit checksum of a mixing hash of the records
+    def mix(i, j, sh):
+        k = (i.long() * 4194301 + j.long()) * 27 + (sh[:, 0].long() + 1) * 9 + (sh[:, 1].long() + 1) * 3 + (sh[:, 2].long() + 1)
+        k = (k ^ (k >> 29)) * -4658895280553007687
+        return int((k ^ (k >> 32)).sum().item())
+    assert mix(e[0], e[1], s) == mix(e[1], e[0], -s)
+    # exact comparison on a sample of the systems
+    sel = torch.arange(0, S, 16)
+    atoms = (sel[:, None] * n1 + torch.arange(n1)[None, :]).reshape(-1)
+    o = ro.batch_cell_list(pos[atoms], 6.0, cell[sel], pbc[sel], torch.arange(sel.numel(), dtype=torch.int32).repeat_interleave(n1),
+                           max_neighbors=176, nthreads=8)
+    assert o[1].max() <= 176
+    counts = (p[1:] - p[:-1]).cpu()
+    assert np.array_equal(counts[atoms].numpy(), o[1])
+    want = ro.records_from_matrix(*o)                              # indices local to the sample
+    in_sample = ((e[0] // n1) % 16 == 0)
+    ee, ss = e[:, in_sample].cpu(), s[in_sample].cpu()
+    remap = lambda g: (g // n1) // 16 * n1 + g % n1                # noqa: E731  global -> sample-local atom index
+    got = ro.records_from_coo(torch.stack([remap(ee[0]), remap(ee[1])]), ss)
+    assert np.array_equal(got, want)
+
+
+def test_reference_published_fcc_benchmark_pair_counts():
+    """The reference's own benchmark workload (FCC a = 4 A, r_cut = 5 A, fp32, max_neighbors = 192,
+    benchmarks/neighborlist/benchmark_config.yaml) at every size it publishes results for: the total neighbor count must
+    equal the number the real Warp kernels produced on an H100 (tests/golden/reference_published_fcc.json), through the
+    matrix API with pre-allocated outputs exactly as the benchmark calls it, and through the COO path."""
+    from systems import fcc_benchmark_system, load_published_fcc
+
+    g = load_published_fcc()
+    for n_str, want in g["cell_list_total_neighbors"].items():
+        n = int(n_str)
+        pos, cell, pbc = fcc_benchmark_system(n)
+        pos_d, cell_d, pbc_d = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+        nm = torch.empty((n, 192), dtype=torch.int32, device=DEV)
+        sh = torch.empty((n, 192, 3), dtype=torch.int32, device=DEV)
+        num = torch.empty((n,), dtype=torch.int32, device=DEV)
+        _nl().neighbor_list(pos_d, 5.0, cell=cell_d, pbc=pbc_d, method="cell_list", neighbor_matrix=nm,
+                            neighbor_matrix_shifts=sh, num_neighbors=num)
+        assert int(num.sum().item()) == want, (n, int(num.sum().item()), want)
+        e, p, s = _nl().neighbor_list(pos_d, 5.0, cell=cell_d, pbc=pbc_d, method="cell_list", return_neighbor_list=True,
+                                      max_neighbors=192)
+        assert e.shape[1] == want and torch.equal(p[1:] - p[:-1], num)
+
+
+def test_real_warp_reference_when_installed():
+    """Primary oracle when available: the REAL reference (Warp CPU and Warp CUDA) on a knife-edge-rich input — decides
+    the FMA mode by evidence.  Skipped where warp-lang / nvalchemiops are not installed."""
+    import warp_reference as wr
+
+    if not wr.available():
+        pytest.skip("real reference not importable here: " + wr.why_unavailable())
+    from nvalchemiops_b200 import config
+
+    pos, cell, pbc = bench_box(200_000, seed=4)
+
+    def ours(fma):
+        old = config.fma
+        config.fma = fma
+        try:
+            e, p, s = _nl().neighbor_list(pos.to(DEV), 6.0, cell=cell.to(DEV), pbc=pbc.to(DEV), return_neighbor_list=True)
+        finally:
+            config.fma = old
+        return ro.records_from_coo(e.cpu(), s.cpu())
+
+    for device in ("cpu", DEV):
+        mode, d_fma, d_sep = wr.decide_fma_mode(pos, 6.0, cell, pbc, ours, device=device, max_neighbors=160)
+        assert min(d_fma, d_sep) == 0, f"neither arithmetic variant reproduces the reference on {device}: {d_fma} / {d_sep}"
+        if mode is not None:
+            assert mode == config.fma, f"config.fma default disagrees with the real reference on {device}"

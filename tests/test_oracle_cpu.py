@@ -183,9 +183,9 @@ def test_rows_path_c_abi_argument_validation_and_budget():
     assert b"2^27" in lib.nvnl_last_error()
     assert lib.nvnl_count_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, ctypes.c_void_p(4100), 64, None) != 0
     assert b"16-byte aligned" in lib.nvnl_last_error()
-    assert lib.nvnl_fill_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, dummy, 0, -1, None) != 0
+    assert lib.nvnl_fill_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, 0, dummy, 0, -1, None) != 0
     assert b"launch_hint" in lib.nvnl_last_error()
-    assert lib.nvnl_fill_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, dummy, 0, 0, None) != 0
+    assert lib.nvnl_fill_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, 0, dummy, 0, 0, None) != 0
     base = lib.nvnl_workspace_bytes(100000, 1, 0)
     try:
         lib.nvnl_set_rows_budget(8, 0)
@@ -324,3 +324,28 @@ def test_estimate_cell_list_sizes_matches_the_oracle_restatement():
     cache = allocate_cell_list(10, 7, got[1][:3], torch.device("cpu"))
     assert [tuple(t.shape) for t in cache] == [(3, 3), (3, 3), (10, 3), (10, 3), (7,), (7,), (10,)]
     assert cache[1] is got[1][:3] or torch.equal(cache[1], got[1][:3])
+
+
+def test_oracle_reproduces_the_pair_counts_the_reference_publishes():
+    """Pins the oracle to OUTPUTS OF THE REAL REFERENCE: total_neighbors of its own FCC benchmark workload as measured
+    with the Warp kernels and published in docs/benchmarks/benchmark_results/*.csv (tests/golden/make_fcc_golden.py).
+    The cell-list restatement and the independent image-sum brute force must both give the published totals."""
+    from systems import fcc_benchmark_system, load_published_fcc
+
+    g = load_published_fcc()
+    assert g["workload"]["cutoff"] == 5.0 and g["workload"]["lattice_constant"] == 4.0
+    for n_str, want in g["cell_list_total_neighbors"].items():
+        n = int(n_str)
+        if n > 16384:
+            continue                                       # (larger sizes: GPU suite, against the same published numbers)
+        pos, cell, pbc = fcc_benchmark_system(n)
+        assert pos.shape[0] == n
+        nm, num, sh = ro.cell_list(pos, 5.0, cell, pbc, max_neighbors=192)
+        assert int(num.sum()) == want, (n, int(num.sum()), want)
+    for n_str, want in g["naive_total_neighbors"].items():
+        n = int(n_str)
+        if n > 1536:
+            continue
+        # (the published naive totals equal the cell-list ones; checked here against the independent brute force)
+        pos, cell, pbc = fcc_benchmark_system(n)
+        assert ro.brute_force(pos, 5.0, cell, pbc).shape[0] == want, ("brute force", n)
