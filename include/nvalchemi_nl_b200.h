@@ -102,10 +102,14 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
  * issue-bound, the zero_() of the shifts output (cell_list.py:1358-1373) is pure HBM writes.  A caller that can guess
  * the pair count (e.g. from its previous query) passes its shifts buffer here and sets launch_hint bit 2 (value 4) of
  * nvnl_fill_rows: `shifts` is already zero — only rows of cells at a periodic boundary write their image shifts.
- * Atom indices must be below 2^28 on this path. */
+ * Atom indices must be below 2^27 on this path.
+ *   launch_hint: -1 = launch every kernel variant (the ones without work retire at once); >= 0 = the launch_hint
+ *   nvnl_status reported for an earlier query of this kind (bit 0: atoms outside the primary image, bit 1: cells left to
+ *   the general kernel): variants that would find no work are not launched.  The caller compares with nvnl_status
+ *   afterwards and repeats the call with -1 if the hint missed a bit. */
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
-                    int32_t* prezero, int64_t prezero_ints, void* stream);
+                    int32_t* prezero, int64_t prezero_ints, int32_t launch_hint, void* stream);
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                    double cutoff_sq, int half_fill, int fma, const int32_t* neighbor_ptr, int32_t* edge_index,
                    int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,

@@ -307,7 +307,7 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
 
 template <bool HALF, bool FMA>
 int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double cutoff_sq, int* num_neighbors,
-                 int* neighbor_ptr, int* prezero, long long prezero_ints, cudaStream_t st) {
+                 int* neighbor_ptr, int* prezero, long long prezero_ints, int hint, cudaStream_t st) {
     SweepArgs<float> a = base_args<float>(ws, n, ns, batch_idx, cutoff_sq);
     a.num_neighbors = num_neighbors;
     int rc = launch_query_reset(ws, a.L, n, 1, st);
@@ -319,13 +319,19 @@ int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, d
     r.prezero_ints = prezero_ints > 0 ? prezero_ints : 0;
     rc = launch_rows_t<HALF, FMA>(r, st);                                   // wrapped inputs: the single sweep
     if (rc) return rc;
-    a.queue = 0;
-    rc = launch_fast_t<float, FAST_COUNT, HALF, FMA, true>(a, st);          // unwrapped inputs: two-pass count (else retires)
-    if (rc) return rc;
-    a.queue = 3;
-    a.keep_deferred = 1;
-    rc = launch_sweep_t<float, MODE_COUNT, HALF, FMA>(a, st);               // whatever the lean kernels deferred
-    if (rc) return rc;
+    // hint >= 0 (what nvnl_status reported for an earlier query with this signature): the kernels that would find no
+    // work are not launched; the caller checks nvnl_status afterwards and repeats the call with hint = -1 if it was wrong
+    if (hint < 0 || (hint & 1)) {
+        a.queue = 0;
+        rc = launch_fast_t<float, FAST_COUNT, HALF, FMA, true>(a, st);      // unwrapped inputs: two-pass count (else retires)
+        if (rc) return rc;
+    }
+    if (hint < 0 || (hint & 2)) {
+        a.queue = 3;
+        a.keep_deferred = 1;
+        rc = launch_sweep_t<float, MODE_COUNT, HALF, FMA>(a, st);           // whatever the lean kernel deferred
+        if (rc) return rc;
+    }
     if (neighbor_ptr) {
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
         const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
@@ -530,7 +536,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
 
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
-                    int32_t* prezero, int64_t prezero_ints, void* stream) {
+                    int32_t* prezero, int64_t prezero_ints, int32_t launch_hint, void* stream) {
     if (!workspace || !num_neighbors || n_atoms <= 0) return fail(-1, "nvnl_count_rows: bad arguments");
     if (dtype != NVNL_F32) return fail(-1, "nvnl_count_rows: the single-sweep path is fp32 only (use nvnl_count)");
     if (n_atoms >= (1LL << 27)) return fail(-1, "nvnl_count_rows: the single-sweep path takes fewer than 2^27 atoms (use nvnl_count)");
@@ -539,10 +545,10 @@ int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_syste
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     if (half_fill)
-        return fma ? count_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st)
-                   : count_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st);
-    return fma ? count_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st)
-               : count_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, st);
+        return fma ? count_rows_t<true, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, launch_hint, st)
+                   : count_rows_t<true, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, launch_hint, st);
+    return fma ? count_rows_t<false, true>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, launch_hint, st)
+               : count_rows_t<false, false>(ws, n_atoms, n_systems, batch_idx, cutoff_sq, num_neighbors, neighbor_ptr, prezero, prezero_ints, launch_hint, st);
 }
 
 int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,

@@ -86,6 +86,7 @@ struct RowsArgs {
 
 // the k_rows barriers are polled with a short sleep between tries: a spinning warp would otherwise take issue slots
 // from the sweeping warps of its scheduler
+template <int SLEEP_NS = 64>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -93,11 +94,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra NVNL_BDONE_%=;\n\t"
         "NVNL_BWAIT_%=:\n\t"
-        "nanosleep.u32 64;\n\t"
+        "nanosleep.u32 %2;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra NVNL_BWAIT_%=;\n\t"
         "NVNL_BDONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "n"(SLEEP_NS) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 const int os = oldest % kRowsDesc;
                 uint64_t* eb = reinterpret_cast<uint64_t*>(&sm.empty[os]);
                 const uint32_t ep = (uint32_t)((oldest / kRowsDesc) & 1);
-                mbar_wait_backoff(eb, ep);
+                mbar_wait_backoff<400>(eb, ep);   // (the ring is full: the producer is tiles ahead, long naps cost nothing)
                 used -= sm.desc[os].footprint;
                 ++oldest;
                 if (oldest == nprod) { head = 0; used = 0; }   // ring drained: start over at its beginning
@@ -846,9 +847,10 @@ struct RowsOutSmem {
     unsigned long long bar[kOutWarps];
 };
 
-// writes one row (already in shared or global memory at `row`, header of `hdr` keys in front of it)
-__device__ __forceinline__ void rows_out_row(const int* row, int hdr, int cnt, int iv, int index_offset, int shifts_zeroed,
-                                             int* __restrict__ oi, int* __restrict__ oj, int* __restrict__ sh, int lane) {
+// writes one row (already in shared or global memory at `row`, header of `hdr` keys in front of it): the general case,
+// kept out of line so that the hot loop of k_rows_out stays small
+__device__ __noinline__ void rows_out_row(const int* row, int hdr, int cnt, int iv, int index_offset, int shifts_zeroed,
+                                          int* __restrict__ oi, int* __restrict__ oj, int* __restrict__ sh, int lane) {
     if (hdr == 0) {
         for (int k = lane; k < cnt; k += 32) {
             oj[k] = row[k] + index_offset;
@@ -944,13 +946,32 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
                 if (lane >= s && lane < e && v > 0) tma_load_1d(buf + (incl - v), src, (uint32_t)v * 4u, bar);
                 mbar_wait(bar, parity);
                 parity ^= 1u;
+                // per-row metadata in one word: row length (16 bits) | header kind (2 bits) | offset in the staging buffer
+                const int meta = cnt | ((ref & 3) << 16) | ((incl - v) << 18);
+                const uint32_t buf_addr = smem_u32(buf) + (uint32_t)lane * 4u;
+#pragma unroll 1
                 for (int t = s; t < e; ++t) {
-                    const int cnt_t = __shfl_sync(0xffffffffu, cnt, t), v_t = __shfl_sync(0xffffffffu, v, t);
-                    if (v_t == 0) continue;
-                    const int off_t = __shfl_sync(0xffffffffu, incl, t) - v_t;
-                    const int p_t = __shfl_sync(0xffffffffu, p, t), hdr_t = __shfl_sync(0xffffffffu, hdr, t);
-                    rows_out_row(buf + off_t + hdr_t, hdr_t, cnt_t, (int)(base + t) + index_offset, index_offset, shifts_zeroed,
-                                 out_i + (size_t)p_t, out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
+                    const int m_t = __shfl_sync(0xffffffffu, meta, t), p_t = __shfl_sync(0xffffffffu, p, t);
+                    const int cnt_t = m_t & 0xffff, kind_t = (m_t >> 16) & 3, off_t = (int)((unsigned)m_t >> 18);
+                    if (cnt_t == 0 || __shfl_sync(0xffffffffu, ref, t) < 0) continue;
+                    const int iv = (int)(base + t) + index_offset;
+                    if (kind_t == 0 && cnt_t <= 96 && shifts_zeroed) {
+                        // the common case, unrolled: interior row, shifts already zero
+                        int* __restrict__ oj = out_j + (size_t)p_t + lane;
+                        int* __restrict__ oi = out_i + (size_t)p_t + lane;
+                        const uint32_t ra = buf_addr + (uint32_t)off_t * 4u;
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            if (lane + 32 * u < cnt_t) {
+                                oj[32 * u] = lds_b32(ra + 128u * u) + index_offset;
+                                oi[32 * u] = iv;
+                            }
+                        }
+                    } else {
+                        const int hdr_t = kind_t == 0 ? 0 : (kind_t == 1 ? 8 : 32);
+                        rows_out_row(buf + off_t + hdr_t, hdr_t, cnt_t, iv, index_offset, shifts_zeroed, out_i + (size_t)p_t,
+                                     out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
+                    }
                 }
                 __syncwarp();   // every lane is done with the buffer before the next batch lands in it
             }

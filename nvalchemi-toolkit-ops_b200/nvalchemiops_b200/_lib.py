@@ -34,7 +34,7 @@ _SIGNATURES = {
                             ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
                             ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_void_p]),
     "nvnl_count_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
-                                c_void_p, c_int64, c_void_p]),
+                                c_void_p, c_int64, c_int32, c_void_p]),
     "nvnl_fill_rows": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p,
                                c_int64, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
     "nvnl_fill_rows_speculative": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int32,

@@ -14,16 +14,18 @@ fma: bool = True
 # fp64 inputs always take "masks".  Both produce the same sets (tests/test_gpu_parity.py runs both).
 coo_path: str = "rows"
 
-# Single-sweep COO path: zero the shifts output on a side stream while the sweep runs, sized from the pair count of the
-# previous query with the same (device, atoms, systems, cutoff, half_fill) signature.  False = always zero after the
+# Single-sweep COO path: let the sweep kernel zero-fill the shifts output while it runs (TMA bulk stores from its producer
+# warps), sized from the pair count of the previous query with the same (device, stream, atoms, systems, cutoff, half_fill)
+# signature.  False = always zero after the
 # size sync (inside the output kernel).
 prezero_shifts: bool = True
 prezero_min_pairs: int = 1_000_000   # below this the extra launch + event cost more than the overlap saves
 
-# EXPERIMENTAL, off: with a speculative shifts buffer in hand, also launch the output kernel BEFORE the size sync, into an
-# edge_index buffer of the guessed size (nvnl_fill_rows_speculative); the host then only creates the views.  Removes the
-# ~25 us the GPU idles at the sync.  Compiled and covered by host-logic tests, not yet measured on hardware.
-speculative_fill: bool = False
+# With a speculative shifts buffer in hand, also launch the output kernel BEFORE the size sync, into an edge_index buffer
+# of the guessed size (nvnl_fill_rows_speculative, which reads the pair count on the device); the host then only
+# creates the views.  Removes the ~30 us the GPU idles at the sync.  A wrong guess is detected after the sync and the
+# output kernel is run again the regular way.
+speculative_fill: bool = True
 
 # Debug: validate inputs on the padded-matrix path too.  That path is sync-free (CUDA-graph capturable) and therefore
 # does not read the device error word: an out-of-range batch_idx is clamped to a valid system, a search radius of 64+

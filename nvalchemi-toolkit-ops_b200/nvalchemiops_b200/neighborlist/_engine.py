@@ -236,23 +236,55 @@ def use_rows(h: CellListHandle) -> bool:
     return config.coo_path == "rows" and h.dtype == torch.float32 and h.n < (1 << 27)
 
 
-# Pair count of the last COO query per (device, atoms, systems, cutoff^2, half_fill): lets the next query with the same
-# signature (MD steps, repeated evaluations) hand the sweep kernel a shifts buffer to zero-fill WHILE it sweeps, instead
-# of zero-filling after the size sync.  Only a size is remembered — never an output; a wrong guess costs nothing but
-# the overlap.
-_pair_history: dict = {}
+class _QueryHistory:
+    """What the last COO query with a given signature (device, stream, atoms, systems, cutoff^2, half_fill) reported: its
+    pair count and launch hint.  The next query with the same signature (MD steps, repeated evaluations) uses them to
+    hand the sweep a shifts buffer to zero-fill WHILE it sweeps, to launch the output kernel before the size sync, and to
+    skip kernel variants that had no work.  Only sizes and flags are remembered — never an output — and every guess is
+    verified against the device's own report after the sync; a wrong guess costs a repeated stage, nothing else.
+    Thread-safe; keyed per stream so that concurrent streams do not share entries."""
+
+    def __init__(self, capacity=256):
+        import threading
+
+        self._lock = threading.Lock()
+        self._entries: dict = {}
+        self._capacity = capacity
+
+    def get(self, key):
+        with self._lock:
+            return self._entries.get(key)
+
+    def put(self, key, total, hint):
+        with self._lock:
+            if len(self._entries) >= self._capacity and key not in self._entries:
+                self._entries.clear()
+            self._entries[key] = (int(total), int(hint))
+
+    def clear(self):
+        with self._lock:
+            self._entries.clear()
 
 
-def _guess_shifts_buffer(h: CellListHandle, key):
+_pair_history = _QueryHistory()
+
+
+def _history_key(h: CellListHandle, cutoff_sq, half_fill):
+    dev = torch.device(h.device)
+    stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+    return (dev.index or 0, stream, h.n, h.ns, float(cutoff_sq), bool(half_fill))
+
+
+def _guess_shifts_buffer(h: CellListHandle, last):
     """Speculatively allocate a shifts buffer sized from the last query with this signature (or None)."""
-    guess, last_hint = _pair_history.get(key, (0, 0))
+    guess, last_hint = last if last is not None else (0, 0)
     # (inputs that were outside the primary periodic image last time take the two-pass kernels: nothing to overlap)
     if not config.prezero_shifts or not guess or guess < config.prezero_min_pairs or (last_hint & 1):
         return None
     return torch.empty(3 * (int(guess * 1.02) + 1024), dtype=torch.int32, device=h.device)
 
 
-def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False, prezero=None):
+def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=False, prezero=None, launch_hint=-1):
     """num_neighbors [N] and (optionally) neighbor_ptr [N+1] (nvnl_count / nvnl_count_rows); asynchronous.
     ``rows=True`` also leaves every atom's neighbors in the workspace's temporary row buffer for ``fill_coo(rows=True)``."""
     num = torch.empty(h.n, dtype=torch.int32, device=h.device)
@@ -263,7 +295,7 @@ def count(h: CellListHandle, cutoff_sq, half_fill=False, want_ptr=True, rows=Fal
             _lib.check(
                 L.nvnl_count_rows(_ptr(h.ws), h.dtype_code, h.n, h.ns, _ptr(h.batch_idx), float(cutoff_sq),
                                   int(bool(half_fill)), int(bool(config.fma)), _ptr(num), _ptr(ptr), _ptr(prezero),
-                                  prezero.numel() if prezero is not None else 0, _stream(h.device)),
+                                  prezero.numel() if prezero is not None else 0, int(launch_hint), _stream(h.device)),
                 "nvnl_count_rows",
             )
         else:
@@ -295,21 +327,23 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
     """COO outputs ``(neighbor_list [2,P], neighbor_ptr [N+1], shifts [P,3])``: count -> scan -> one sync for the
     size -> fill.  Raises NeighborOverflowError like the reference's COO conversion when an atom exceeds
     ``max_neighbors`` (neighbor_utils.py:352-359)."""
-    key = (torch.device(h.device).index or 0, h.n, h.ns, float(cutoff_sq), bool(half_fill))
-    zbuf = _guess_shifts_buffer(h, key) if use_rows(h) else None
+    key = _history_key(h, cutoff_sq, half_fill)
+    last = _pair_history.get(key)
+    zbuf = _guess_shifts_buffer(h, last) if use_rows(h) else None
     ebuf = None
     if zbuf is not None and config.speculative_fill:
         ebuf = torch.empty(2 * (zbuf.numel() // 3), dtype=torch.int32, device=h.device)
-    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill, prezero=zbuf, spec_edge=ebuf)
+    num, ptr, total, max_count, err, hint, rows = count_and_size(h, cutoff_sq, half_fill, prezero=zbuf, spec_edge=ebuf,
+                                                                 launch_hint=last[1] if last is not None else -1)
     _raise_on_error_bits(err)
     if max_neighbors is not None and max_count > max_neighbors:
         raise NeighborOverflowError(max_neighbors, max_count)
     if total > 2**31 - 1:
         raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
-    if len(_pair_history) > 256:
-        _pair_history.clear()
-    _pair_history[key] = (total, hint)
-    fits = rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel() and not (hint & 1)
+    _pair_history.put(key, total, hint & 3)
+    fits = (rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel()
+            and not (hint & 1) and not (hint & 16))
+    hint &= 15
     if fits and ebuf is not None:
         # the output kernel already ran (before the sync) into the speculative buffers: the outputs are their prefixes
         edge_index = ebuf[: 2 * total].view(2, total)
@@ -344,15 +378,24 @@ def fill_rows_speculative(h: CellListHandle, neighbor_ptr, edge_buffer, shifts_z
         )
 
 
-def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, spec_edge=None):
+def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, spec_edge=None, launch_hint=-1):
     """Count stage + the one host sync: ``(num, ptr, total, max_count, error_bits, launch_hint, rows)``.  ``rows``
     tells ``fill_coo`` which path the count ran on (single sweep unless fp64 / configured off / its temporary row
-    buffer overflowed, in which case the count is repeated on the two-pass path)."""
+    buffer overflowed, in which case the count is repeated on the two-pass path).  ``launch_hint`` >= 0 (from an earlier
+    query with this signature) skips the kernel variants that had no work then; if the device reports work for a
+    skipped variant the count is repeated with everything launched."""
     rows = use_rows(h)
-    num, ptr = count(h, cutoff_sq, half_fill, rows=rows, prezero=prezero if rows else None)
+    num, ptr = count(h, cutoff_sq, half_fill, rows=rows, prezero=prezero if rows else None,
+                     launch_hint=launch_hint if rows else -1)
     if rows and prezero is not None and spec_edge is not None:
         fill_rows_speculative(h, ptr, spec_edge, prezero)      # runs while the host waits for the size
     total, max_count, _cells, err, hint = status(h)
+    if rows and launch_hint >= 0 and (hint & ~launch_hint & 3):
+        # a variant that was not launched had work: repeat the count with every variant (the speculative outputs, if any,
+        # are discarded by the caller because the totals cannot have been right)
+        num, ptr = count(h, cutoff_sq, half_fill, rows=True, prezero=None, launch_hint=-1)
+        total, max_count, _cells, err, hint = status(h)
+        hint |= 16   # (tells the caller that speculative buffers were not filled consistently)
     if rows and h.rows_overflow:
         rows = False
         num, ptr = count(h, cutoff_sq, half_fill)

@@ -965,9 +965,7 @@ def test_rows_path_prezeroed_shifts_on_repeated_queries():
         config.prezero_min_pairs = old_min
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("NVNL_EXPERIMENTAL"),
-                    reason="experimental path (config.speculative_fill), not yet validated on hardware: set NVNL_EXPERIMENTAL=1")
-def test_experimental_speculative_fill_matches_the_regular_path():
+def test_speculative_fill_matches_the_regular_path():
     """The output kernel launched before the size sync (nvnl_fill_rows_speculative) must give the same COO outputs:
     interior/boundary cells, a batch with cells left to the general kernel, a guess that is too small, unwrapped input."""
     from nvalchemiops_b200 import config

@@ -177,11 +177,11 @@ def test_rows_path_c_abi_argument_validation_and_budget():
 
     lib = _lib.lib()
     dummy = ctypes.c_void_p(4096)          # never dereferenced: validation fails first
-    assert lib.nvnl_count_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
+    assert lib.nvnl_count_rows(dummy, 1, 100, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, -1, None) != 0
     assert b"fp32 only" in lib.nvnl_last_error()
-    assert lib.nvnl_count_rows(dummy, 0, 1 << 27, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, None) != 0
+    assert lib.nvnl_count_rows(dummy, 0, 1 << 27, 1, None, 36.0, 0, 1, dummy, dummy, None, 0, -1, None) != 0
     assert b"2^27" in lib.nvnl_last_error()
-    assert lib.nvnl_count_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, ctypes.c_void_p(4100), 64, None) != 0
+    assert lib.nvnl_count_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, ctypes.c_void_p(4100), 64, -1, None) != 0
     assert b"16-byte aligned" in lib.nvnl_last_error()
     assert lib.nvnl_fill_rows(dummy, 0, 100, 1, None, 36.0, 0, 1, dummy, dummy, 10, 0, dummy, 0, -1, None) != 0
     assert b"launch_hint" in lib.nvnl_last_error()
@@ -223,7 +223,10 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     calls = []
     state = {"total": 5_000_000, "hint": 0, "overflow_once": False}
 
-    def fake_count(h, csq, half_fill=False, want_ptr=True, rows=False, prezero=None):
+    hints = []
+
+    def fake_count(h, csq, half_fill=False, want_ptr=True, rows=False, prezero=None, launch_hint=-1):
+        hints.append(launch_hint)
         calls.append(("count", rows, None if prezero is None else prezero.numel()))
         return torch.zeros(h.n, dtype=torch.int32), torch.zeros(h.n + 1, dtype=torch.int32)
 
@@ -231,12 +234,13 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
         h.rows_overflow = state["overflow_once"] and calls[-1][1]
         return state["total"], 100, 10, 0, state["hint"]
 
-    def fake_fill(h, csq, ptr, edge, shifts, total, half_fill=False, index_offset=0, launch_hint=-1, rows=False):
+    def fake_fill(h, csq, ptr, edge, shifts, total, half_fill=False, index_offset=0, launch_hint=-1, rows=False, row_stride=0):
         calls.append(("fill", rows, launch_hint, tuple(edge.shape), tuple(shifts.shape), shifts.is_contiguous()))
 
     monkeypatch.setattr(_engine, "count", fake_count)
     monkeypatch.setattr(_engine, "status", fake_status)
     monkeypatch.setattr(_engine, "fill_coo", fake_fill)
+    monkeypatch.setattr(config, "speculative_fill", False)
     _engine._pair_history.clear()
     h = H(60_000)
     # first query: nothing known -> no speculative buffer, the output kernel zero-fills (bit 2 clear)
@@ -259,13 +263,14 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     calls.clear()
     _engine.query_coo(h, 25.0)
     assert calls[0] == ("count", True, None)
-    # unwrapped inputs: two-pass kernels served the query -> never "pre-zeroed", and no speculation next time
-    calls.clear(); state["hint"] = 1
+    # unwrapped inputs: the hint of the last query (0: only the lean kernel was launched) misses the bit -> the count is
+    # repeated with every variant; two-pass kernels served the query -> never "pre-zeroed", and no speculation next time
+    calls.clear(); hints.clear(); state["hint"] = 1
     _engine.query_coo(h, 36.0)
-    assert calls[1][2] == 1
-    calls.clear()
+    assert [c[0] for c in calls] == ["count", "count", "fill"] and hints == [0, -1] and calls[2][2] == 1
+    calls.clear(); hints.clear()
     _engine.query_coo(h, 36.0)
-    assert calls[0] == ("count", True, None) and calls[1][2] == 1
+    assert calls[0] == ("count", True, None) and calls[1][2] == 1 and hints == [1]
     # temporary rows overflow: the count is repeated on the two-pass path and the fill follows it
     calls.clear(); state.update(hint=0, overflow_once=True)
     _engine.query_coo(h, 36.0)
@@ -274,7 +279,7 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     calls.clear(); state.update(total=10_000, overflow_once=False)
     _engine.query_coo(h, 4.0); _engine.query_coo(h, 4.0)
     assert calls[2] == ("count", True, None)
-    # experimental: output kernel launched before the size sync into buffers of the guessed size
+    # output kernel launched before the size sync into buffers of the guessed size (the default)
     monkeypatch.setattr(config, "speculative_fill", True)
     monkeypatch.setattr(_engine, "fill_rows_speculative",
                         lambda h, ptr, ebuf, zbuf, index_offset=0: calls.append(("spec", ebuf.numel(), zbuf.numel())))
@@ -286,9 +291,12 @@ def test_engine_coo_path_selection_fallback_and_speculative_shifts(monkeypatch):
     cap = int(5_000_000 * 1.02) + 1024
     assert calls == [("count", True, 3 * cap), ("spec", 2 * cap, 3 * cap)]
     assert e.shape == (2, 5_000_000) and e.is_contiguous() and s.shape == (5_000_000, 3) and s.is_contiguous()
-    calls.clear(); state["hint"] = 2                # cells left to the general kernel: only that launch remains (bits 2|3)
+    calls.clear(); hints.clear(); state["hint"] = 2   # cells left to the general kernel, but the hint (0) did not launch it:
+    _engine.query_coo(h, 36.0)                        # count repeated with every variant, speculative outputs dropped
+    assert [c[0] for c in calls] == ["count", "spec", "count", "fill"] and hints == [0, -1] and calls[3][:3] == ("fill", True, 2)
+    calls.clear(); hints.clear()                      # next time the hint is right: only the general kernel's rows remain
     _engine.query_coo(h, 36.0)
-    assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 2 | 4 | 8)
+    assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 2 | 4 | 8) and hints == [2]
     calls.clear(); state.update(total=6_000_000, hint=0)   # guess too small: the regular fill, nothing pre-zeroed
     _engine.query_coo(h, 36.0)
     assert calls[1][0] == "spec" and calls[2][:3] == ("fill", True, 0) and calls[2][3] == (2, 6_000_000)
