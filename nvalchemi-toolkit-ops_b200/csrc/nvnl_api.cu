@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "../../include/nvalchemi_nl_b200.h"
 #include "nvnl_cache.cuh"
@@ -30,6 +31,31 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
         cudaError_t e__ = cudaGetLastError();                     \
         if (e__ != cudaSuccess) return fail(-2, what, e__);       \
     } while (0)
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may be scheduled while its predecessor
+// in the stream still runs; every kernel launched this way starts with pdl_enter(), which waits for the predecessor
+// grid to complete and flush.  NVNL_NO_PDL=1 in the environment (read once) turns the attribute off.
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("NVNL_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);   // errors surface in NVNL_CHECK_LAUNCH
+}
 
 // temporary-row budget of the single-sweep COO path (nvnl_set_rows_budget; tests shrink it to force the fallback)
 std::atomic<long long> g_rows_per_atom{kRowsPerAtom};
@@ -78,7 +104,7 @@ int launch_sweep_t(const SweepArgs<T>& a, cudaStream_t st) {
     long long grid = (long long)sm_count() * blocks_per_sm;
     const long long max_items = a.L.max_cells;
     if (grid > max_items) grid = max_items > 0 ? max_items : 1;
-    kern<<<(unsigned)grid, kSweepThreads, kSweepSmemBytes, st>>>(a);
+    launch_pdl(kern, (unsigned)grid, kSweepThreads, kSweepSmemBytes, st, a);
     NVNL_CHECK_LAUNCH("k_sweep");
     return 0;
 }
@@ -100,7 +126,7 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     long long grid = (long long)sm_count() * blocks_per_sm;
     const long long max_items = a.L.max_cells;
     if (grid > max_items) grid = max_items > 0 ? max_items : 1;
-    kern<<<(unsigned)grid, kFastThreads, smem, st>>>(a);
+    launch_pdl(kern, (unsigned)grid, kFastThreads, smem, st, a);
     NVNL_CHECK_LAUNCH("k_fast");
     return 0;
 }
@@ -123,7 +149,7 @@ int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
     long long grid = (long long)sm_count() * blocks_per_sm;
     const long long max_items = a.L.max_cells;
     if (grid > max_items) grid = max_items > 0 ? max_items : 1;
-    kern<<<(unsigned)grid, kRowsThreads, smem, st>>>(a);
+    launch_pdl(kern, (unsigned)grid, kRowsThreads, smem, st, a);
     NVNL_CHECK_LAUNCH("k_rows");
     return 0;
 }
@@ -148,7 +174,7 @@ int launch_rows_out(const unsigned char* ws, const WsLayout& L, long long n, con
     const long long cap = (long long)sm_count() * blocks_per_sm * 4;   // a few waves: the tail is short
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kOutWarps * 32, smem, st>>>(ws, L, n, neighbor_ptr, out_i, out_j, out_shifts, index_offset,
+    launch_pdl(kern, (unsigned)grid, kOutWarps * 32, smem, st, ws, L, n, neighbor_ptr, out_i, out_j, out_shifts, index_offset,
                                                       shifts_zeroed, spec_cap);
     NVNL_CHECK_LAUNCH("k_rows_out");
     return 0;
@@ -157,7 +183,7 @@ int launch_rows_out(const unsigned char* ws, const WsLayout& L, long long n, con
 // Start of every query: empty deferred list, empty temporary row buffer (and, for the single-sweep COO path,
 // row_ref = -1 for every atom).
 int launch_query_reset(unsigned char* ws, const WsLayout& L, long long n, int with_rows, cudaStream_t st) {
-    k_query_reset<<<1, 32, 0, st>>>(ws, L, n, with_rows);
+    launch_pdl(k_query_reset, 1, 32, 0, st, ws, L, n, with_rows);
     NVNL_CHECK_LAUNCH("k_query_reset");
     return 0;
 }
@@ -198,7 +224,7 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         long long blocks = (work + 255) / 256;
         if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
         if (blocks < 1) blocks = 1;
-        k_init<T><<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, ns, cell, pbc, batch_ptr, nullptr);
+        launch_pdl(k_init<T>, (unsigned)blocks, 256, 0, st, ws, L, n, ns, cell, pbc, batch_ptr, nullptr);
         NVNL_CHECK_LAUNCH("k_init");
     }
     {
@@ -206,26 +232,26 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         long long blocks = (n + 2047) / 2048;
         if (blocks > (long long)sms * 4) blocks = (long long)sms * 4;
         if (blocks < 1) blocks = 1;
-        k_bbox<T><<<(unsigned)blocks, kSmallBlock, 0, st>>>(ws, L, n, ns, pos, batch_idx, need_counts);
+        launch_pdl(k_bbox<T>, (unsigned)blocks, kSmallBlock, 0, st, ws, L, n, ns, pos, batch_idx, need_counts);
         NVNL_CHECK_LAUNCH("k_bbox");
     }
-    k_grid<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff, max_cells > 0 ? (max_cells / ns > 0 ? max_cells / ns : 1) : 0);
+    launch_pdl(k_grid, 1, ns > kSmallBlock ? 1024 : kSmallBlock, 0, st, ws, L, ns, cutoff, max_cells > 0 ? (max_cells / ns > 0 ? max_cells / ns : 1) : 0);
     NVNL_CHECK_LAUNCH("k_grid");
     const bool vec = (reinterpret_cast<uintptr_t>(pos) % 16) == 0;
     {
         const long long threads = (n + 3) / 4;
         const unsigned blocks = (unsigned)((threads + 255) / 256);
         if (vec)
-            k_hash<T, true><<<blocks, 256, 0, st>>>(ws, L, n, ns, pos, batch_idx);
+            launch_pdl(k_hash<T, true>, blocks, 256, 0, st, ws, L, n, ns, pos, batch_idx);
         else
-            k_hash<T, false><<<blocks, 256, 0, st>>>(ws, L, n, ns, pos, batch_idx);
+            launch_pdl(k_hash<T, false>, blocks, 256, 0, st, ws, L, n, ns, pos, batch_idx);
         NVNL_CHECK_LAUNCH("k_hash");
     }
     {
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
         const long long cnt = L.max_cells + 1;  // out has cnt + 1 entries
         const unsigned blocks = (unsigned)((cnt + 1 + kScanTile - 1) / kScanTile);
-        k_scan<<<blocks, kScanThreads, 0, st>>>(reinterpret_cast<const int*>(ws + L.cell_count),
+        launch_pdl(k_scan, blocks, kScanThreads, 0, st, reinterpret_cast<const int*>(ws + L.cell_count),
                                                reinterpret_cast<int*>(ws + L.cell_start), cnt,
                                                reinterpret_cast<unsigned long long*>(ws + L.scan_status0),
                                                &ctrl->scan_tile[0], nullptr, nullptr, &ctrl->total_cells);
@@ -235,9 +261,9 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
         const long long threads = (n + 3) / 4;
         const unsigned blocks = (unsigned)((threads + 255) / 256);
         if (vec)
-            k_scatter<T, true><<<blocks, 256, 0, st>>>(ws, L, n, pos);
+            launch_pdl(k_scatter<T, true>, blocks, 256, 0, st, ws, L, n, pos);
         else
-            k_scatter<T, false><<<blocks, 256, 0, st>>>(ws, L, n, pos);
+            launch_pdl(k_scatter<T, false>, blocks, 256, 0, st, ws, L, n, pos);
         NVNL_CHECK_LAUNCH("k_scatter");
     }
     return 0;
@@ -254,7 +280,7 @@ int import_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const
         long long blocks = (work + 255) / 256;
         if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
         if (blocks < 1) blocks = 1;
-        k_init<T><<<(unsigned)blocks, 256, 0, st>>>(ws, L, n, ns, cell, pbc, nullptr, nullptr);
+        launch_pdl(k_init<T>, (unsigned)blocks, 256, 0, st, ws, L, n, ns, cell, pbc, nullptr, nullptr);
         NVNL_CHECK_LAUNCH("k_init");
     }
     k_import_sys<<<1, kSmallBlock, 0, st>>>(ws, L, ns, cutoff, cpd, radius, cache_cells);
@@ -297,7 +323,7 @@ int count_t(unsigned char* ws, long long n, int ns, const int* batch_idx, double
     if (neighbor_ptr) {
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
         const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
-        k_scan<<<blocks, kScanThreads, 0, st>>>(num_neighbors, neighbor_ptr, n,
+        launch_pdl(k_scan, blocks, kScanThreads, 0, st, num_neighbors, neighbor_ptr, n,
                                                reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
                                                &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count, nullptr);
         NVNL_CHECK_LAUNCH("k_scan(neighbors)");
@@ -335,7 +361,7 @@ int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, d
     if (neighbor_ptr) {
         Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + a.L.ctrl);
         const unsigned blocks = (unsigned)((n + 1 + kScanTile - 1) / kScanTile);
-        k_scan<<<blocks, kScanThreads, 0, st>>>(num_neighbors, neighbor_ptr, n,
+        launch_pdl(k_scan, blocks, kScanThreads, 0, st, num_neighbors, neighbor_ptr, n,
                                                reinterpret_cast<unsigned long long*>(ws + a.L.scan_status1),
                                                &ctrl->scan_tile[1], &ctrl->total_pairs, &ctrl->max_count, nullptr);
         NVNL_CHECK_LAUNCH("k_scan(neighbors)");
@@ -352,7 +378,7 @@ int fill_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, do
     if (hint & 1) {
         // unwrapped input: the count ran on the two-pass kernels (hit masks), so does the fill
         a.queue = 1;
-        k_gather_ptr<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, a.L, n, neighbor_ptr,
+        launch_pdl(k_gather_ptr<float>, (unsigned)((n + 255) / 256), 256, 0, st, ws, a.L, n, neighbor_ptr,
                                                                        reinterpret_cast<int*>(ws + a.L.ptr_sorted));
         NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_pair<float, MODE_FILL_COO, HALF, FMA>(a, hint, st);
@@ -517,7 +543,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
         SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + row_stride; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
-        k_gather_ptr<float><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
+        launch_pdl(k_gather_ptr<float>, (unsigned)((n_atoms + 255) / 256), 256, 0, st, ws, a.L, n_atoms, neighbor_ptr,
                                                                               reinterpret_cast<int*>(ws + a.L.ptr_sorted));
         NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_sweep<float, MODE_FILL_COO>(a, half_fill, fma, st, launch_hint);
@@ -526,7 +552,7 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
         SweepArgs<double> a = base_args<double>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
         a.neighbor_ptr = neighbor_ptr; a.out_i = edge_index; a.out_j = edge_index + row_stride; a.out_shifts = shifts;
         a.index_offset = index_offset; a.queue = 1;
-        k_gather_ptr<double><<<(unsigned)((n_atoms + 255) / 256), 256, 0, st>>>(ws, a.L, n_atoms, neighbor_ptr,
+        launch_pdl(k_gather_ptr<double>, (unsigned)((n_atoms + 255) / 256), 256, 0, st, ws, a.L, n_atoms, neighbor_ptr,
                                                                                reinterpret_cast<int*>(ws + a.L.ptr_sorted));
         NVNL_CHECK_LAUNCH("k_gather_ptr");
         return launch_sweep<double, MODE_FILL_COO>(a, half_fill, fma, st, launch_hint);

@@ -19,7 +19,7 @@ namespace nvnl {
 // ------------------------------------------------------------------------------------------------
 struct WsLayout {
     size_t ctrl, sys, bbox, cell_count, cell_start, atom_cell, atom_rank, atom_ashift, sorted, sorted_ashift,
-        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, row_ref, rows, total;
+        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, row_ref, split, rows, total;
     long long max_cells;  // N + S (upper bound on the number of cells, see k_grid)
     long long rows_cap;   // entries of the temporary row buffer (single-sweep COO path, nvnl_rows.cuh)
 };
@@ -57,6 +57,9 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     // order.  Budget: kRowsPerAtom entries per atom + one reservation block per resident warp; more pairs than that
     // (very large cutoffs) make the query fall back to the two-pass path.
     L.row_ref = take(sizeof(int) * (size_t)n);
+    // parts of cells with many targets: (cell + 1, first target) — a cell of more than 64 targets is cut into parts of
+    // 32, so there are fewer than n / 16 + 1 of them
+    L.split = take(sizeof(int2) * (size_t)(n / 16 + 2));
     L.rows_cap = rows_per_atom * n + rows_slack;
     if (L.rows_cap < 1) L.rows_cap = 1;
     if (L.rows_cap > (1LL << 29) - 1) L.rows_cap = (1LL << 29) - 1;   // row_ref = first entry << 2 | header kind
@@ -81,6 +84,7 @@ template <typename T>
 __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, int num_systems,
                        const T* __restrict__ cell, const unsigned char* __restrict__ pbc,
                        const int* __restrict__ batch_ptr, int* __restrict__ num_neighbors) {
+    pdl_enter();
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
@@ -95,6 +99,12 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
         ctrl->n_deferred = 0;
         ctrl->had_deferred = 0;
         ctrl->wide_stencil = 0;
+        ctrl->shift_heavy = 0;
+        ctrl->split_reserved = ctrl->split_next = ctrl->cells_done = 0;
+    }
+    {
+        int2* split = reinterpret_cast<int2*>(ws + L.split);   // (entry.x == 0: not pushed yet)
+        for (long long i = gid; i < n / 16 + 2; i += stride) split[i] = make_int2(0, 0);
     }
     int* cell_count = reinterpret_cast<int*>(ws + L.cell_count);
     for (long long i = gid; i < L.max_cells + 2; i += stride) cell_count[i] = 0;
@@ -148,6 +158,7 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
 template <typename T>
 __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, int num_systems,
                        const T* __restrict__ pos, const int* __restrict__ batch_idx, int need_counts) {
+    pdl_enter();
     SysParams* sys = reinterpret_cast<SysParams*>(ws + L.sys);
     long long* bbox = reinterpret_cast<long long*>(ws + L.bbox);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
@@ -257,12 +268,15 @@ __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, 
 // precision; the margin guarantees every pair the fp test accepts lies inside the stencil.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_systems, double cutoff, long long cell_cap) {
+    pdl_enter();
     SysParams* sys = reinterpret_cast<SysParams*>(ws + L.sys);
     const long long* bbox = reinterpret_cast<const long long*>(ws + L.bbox);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
-    __shared__ int s_warp[kSmallBlock / 32];
+    __shared__ int s_warp[32];   // (launched with up to 1024 threads: many small systems)
     __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    __shared__ unsigned long long s_atoms[2];   // atoms in cells at a periodic boundary (estimate), all atoms
+    unsigned long long my_bnd = 0ull, my_all = 0ull;
+    if (threadIdx.x == 0) { s_carry = 0; s_atoms[0] = s_atoms[1] = 0ull; }
     __syncthreads();
     const double rc = cutoff * (1.0 + 1e-3);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -322,6 +336,12 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
             }
             ncells = (int)tot;
             sp.ncells = ncells;
+            // share of the system's cells whose stencil crosses a periodic boundary (their neighbor rows carry shifts)
+            long long interior = 1;
+            for (int d = 0; d < 3; ++d) interior *= sp.pbc[d] ? (sp.cpd[d] > 2 ? sp.cpd[d] - 2 : 0) : sp.cpd[d];
+            const long long na = sp.natoms > 0 ? sp.natoms : 0;
+            my_bnd += (unsigned long long)(na * (tot - interior) / (tot > 0 ? tot : 1));
+            my_all += (unsigned long long)na;
         }
         // block-wide exclusive scan of ncells with carry
         int incl = warp_incl_scan(ncells, lane);
@@ -340,7 +360,20 @@ __global__ void k_grid(unsigned char* __restrict__ ws, WsLayout L, int num_syste
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + warp_off + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) ctrl->total_cells = s_carry;
+    // (one shared-memory atomic per warp: 64-bit shared atomics serialise)
+    for (int o = 16; o > 0; o >>= 1) {
+        my_bnd += __shfl_down_sync(0xffffffffu, my_bnd, o);
+        my_all += __shfl_down_sync(0xffffffffu, my_all, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_atoms[0], my_bnd);
+        atomicAdd(&s_atoms[1], my_all);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctrl->total_cells = s_carry;
+        ctrl->shift_heavy = 2ull * s_atoms[0] > s_atoms[1] ? 1 : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,6 +433,7 @@ __device__ __forceinline__ void load4(const T* __restrict__ pos, long long i0, l
 template <typename T, bool VEC>
 __global__ void k_hash(unsigned char* __restrict__ ws, WsLayout L, long long n, int num_systems,
                        const T* __restrict__ pos, const int* __restrict__ batch_idx) {
+    pdl_enter();
     const SysParams* sys = reinterpret_cast<const SysParams*>(ws + L.sys);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
     int* cell_count = reinterpret_cast<int*>(ws + L.cell_count);
@@ -442,6 +476,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const int* __restrict__ i
                                                        int* __restrict__ tile_counter,
                                                        unsigned long long* __restrict__ total64,
                                                        int* __restrict__ max_out, const int* __restrict__ live_ptr) {
+    pdl_enter();
     __shared__ int s_tile;
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_prefix;
@@ -475,26 +510,33 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const int* __restrict__ i
     }
     __syncthreads();
     const int block_agg = s_warp[kScanThreads / 32 - 1];
-    if (threadIdx.x == 0) {
+    if (wid == 0) {
+        // decoupled look-back, one warp wide: lane l inspects predecessor tile t - l; the window slides back by 32 tiles
+        // until it contains an inclusive prefix (flag 2).  Flag and value share one 64-bit word (single store/load).
         volatile unsigned long long* st = status;
+        if (lane == 0) st[tile] = ((tile == 0 ? 2ull : 1ull) << 32) | (unsigned)block_agg;
         int prefix = 0;
-        if (tile == 0) {
-            st[0] = (2ull << 32) | (unsigned)block_agg;
-        } else {
-            st[tile] = (1ull << 32) | (unsigned)block_agg;
+        if (tile > 0) {
             int t = tile - 1;
             for (;;) {
-                const unsigned long long w = st[t];
+                const int idx = t - lane;
+                const unsigned long long w = idx >= 0 ? st[idx] : (2ull << 32);   // before tile 0: inclusive prefix 0
                 const unsigned flag = (unsigned)(w >> 32);
-                if (flag == 0) continue;
-                prefix += (int)(unsigned)w;
-                if (flag == 2) break;
-                --t;
+                const unsigned inc = __ballot_sync(0xffffffffu, flag == 2u);
+                const unsigned none = __ballot_sync(0xffffffffu, flag == 0u);
+                const int first = inc ? __ffs((int)inc) - 1 : 31;                    // nearest inclusive predecessor
+                const unsigned need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+                if (none & need) continue;                                           // some aggregate not posted yet
+                prefix += __reduce_add_sync(0xffffffffu, lane <= first ? (int)(unsigned)w : 0);
+                if (inc) break;
+                t -= 32;
             }
-            st[tile] = (2ull << 32) | (unsigned)(prefix + block_agg);
+            if (lane == 0) st[tile] = (2ull << 32) | (unsigned)(prefix + block_agg);
         }
-        s_prefix = prefix;
-        if (total64 && block_agg) atomicAdd(total64, (unsigned long long)(unsigned)block_agg);
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (total64 && block_agg) atomicAdd(total64, (unsigned long long)(unsigned)block_agg);
+        }
     }
     __syncthreads();
     int run = s_prefix + (wid > 0 ? s_warp[wid - 1] : 0) + incl - tsum;
@@ -510,6 +552,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const int* __restrict__ i
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
 __global__ void k_scatter(unsigned char* __restrict__ ws, WsLayout L, long long n, const T* __restrict__ pos) {
+    pdl_enter();
     const Ctrl* ctrl = reinterpret_cast<const Ctrl*>(ws + L.ctrl);
     const int* cell_start = reinterpret_cast<const int*>(ws + L.cell_start);
     const int* atom_cell = reinterpret_cast<const int*>(ws + L.atom_cell);

@@ -64,7 +64,24 @@ struct Ctrl {
     unsigned long long rows_cursor;  // single-sweep COO path: next free entry of the temporary row buffer
     int rows_overflow;               // single-sweep COO path: the temporary row buffer was too small (host falls back)
     int wide_stencil;                // some system searches more than one cell per side (periodic shifts may exceed +-1)
+    int shift_heavy;                 // most atoms sit in cells at a periodic boundary (small boxes): their rows carry shifts,
+                                     // so the single-sweep path writes the shifts output densely instead of pre-zeroing it
+    // single-sweep COO path: cells with many targets are swept in parts by several CTAs (nvnl_rows.cuh)
+    int split_reserved;              // entries of the part list handed out to pushers
+    int split_next;                  // next entry to pop
+    int cells_done;                  // cells whose parts (if any) have been pushed; == total_cells ends the pop loop
 };
+
+// Programmatic dependent launch (PDL): kernels of the hot chain are launched with the programmatic-stream-serialization
+// attribute, so the NEXT kernel's launch latency overlaps this kernel's execution.  First statement of every such
+// kernel: let the dependents launch, then wait until the predecessor grid has completed and flushed its writes
+// (a no-op when the kernel was launched without the attribute).
+__device__ __forceinline__ void pdl_enter() {
+#ifndef NVNL_NO_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 // Sorted candidate record: position + original atom index. 16 B (float) / 32 B (double) so that a
 // cell's run is a 16-byte-aligned, 16-byte-granular block — a legal cp.async.bulk (TMA 1-D) source.

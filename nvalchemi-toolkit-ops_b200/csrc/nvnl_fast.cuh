@@ -434,6 +434,7 @@ __device__ __forceinline__ int fast_expand2(const SweepArgs<T>& a, const FastSta
 template <typename T>
 __global__ void k_gather_ptr(const unsigned char* __restrict__ ws, WsLayout L, long long n,
                              const int* __restrict__ neighbor_ptr, int* __restrict__ ptr_sorted) {
+    pdl_enter();
     const Rec<T>* sorted = reinterpret_cast<const Rec<T>*>(ws + L.sorted);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) ptr_sorted[k] = neighbor_ptr[sorted[k].j];
@@ -451,6 +452,7 @@ __global__ void k_gather_ptr(const unsigned char* __restrict__ ws, WsLayout L, l
 template <typename T, int MODE, bool HALF, bool FMA, bool UNW>
 __global__ void __launch_bounds__(kFastThreads, UNW ? (MODE == 1 ? 2 : 3) : (MODE == 1 ? 4 : 5))
 k_fast(const SweepArgs<T> a) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kStageBytes = UNW ? kFastStageBytesU : kFastStageBytes;
     constexpr int kAshOffset = kCandBytes + kFastSlackBytes;  // unwrapped variant: periodic images behind the records

@@ -40,9 +40,13 @@ constexpr int kRowsThreads = (kRowsCons + 1) * 32;    // + producer warp
 constexpr int kRowsMinBlocks = NVNL_ROWS_MINB;        // CTAs per SM
 constexpr int kRowsDesc = 6;                          // tiles in flight per CTA (descriptor ring)
 constexpr int kRowsRingBytes = NVNL_ROWS_RING_KB * 1024;   // staged records of the tiles in flight
-constexpr int kRowsZeroBytes = 8 * 1024;              // shared-memory zero block behind the fused zero-fill (TMA bulk stores)
+constexpr int kRowsZeroBytes = 4 * 1024;              // shared-memory zero block behind the fused zero-fill (TMA bulk stores)
 constexpr int kRowsMaxVC = 64;                        // 32-candidate chunks per tile (two mask words per lane and target)
+constexpr int kRowsMaxVCAlias = 192;                  // ... of an aliased tile (single-cell system: every image = the same records)
+constexpr int kRowsHugeWords = kRowsMaxVCAlias / 32;  // mask words per lane and target of such a tile
 constexpr int kRowsMaxSeg = 32;                       // shift segments per tile (one per image at most)
+constexpr int kRowsSplitAbove = 64;                   // cells with more targets are swept in parts, by several CTAs
+constexpr int kRowsSplitPart = 32;                    // targets per part
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
 constexpr int kRowsSegShift = 27;                     // boundary rows: entry = atom | segment << 27 (atoms < 2^27)
 constexpr float kRowsFar = 3.0e18f;                   // sentinel coordinate: squares stay finite, never within any cutoff
@@ -56,11 +60,14 @@ struct RowsDesc {
     int shifted;                      // some segment has a non-zero shift
     int next_target;                  // consumer claim counter
     int footprint;                    // producer-private: ring bytes held by this tile
-    int pad0[3];
-    int seg_vc[kRowsMaxSeg + 1];      // first chunk of every segment (segment s covers slots 32 * seg_vc[s] ...)
+    int aliased;                      // every segment is an image of the SAME staged records (single-cell system)
+    int pad0[2];
+    int seg_vc[kRowsMaxSeg + 1];      // first (virtual) chunk of every segment; the mask bits count virtual chunks
+    int seg_phys[kRowsMaxSeg];        // the staged chunk it starts at (== seg_vc unless aliased)
     int seg_key[kRowsMaxSeg];         // packed integer shift of the segment
-    float segS[kRowsMaxSeg][4];       // its lattice vector s·cell
-    unsigned char vc_seg[kRowsMaxVC]; // chunk -> segment
+    float segS[kRowsMaxSeg][3];       // its lattice vector s·cell
+    unsigned char vc_seg[kRowsMaxVCAlias];  // virtual chunk -> segment
+    unsigned char vc_phys[kRowsMaxVCAlias]; // virtual chunk -> staged chunk (aliased tiles)
 };
 
 struct RowsSmem {
@@ -215,8 +222,9 @@ __device__ __forceinline__ void rows_run_shift(uint32_t addr, int v0, int v1, co
     }
 }
 
-// Sweep of the four targets over chunks [32 w, 32 w + 32) of the staged tile: m = their hit masks (bit = chunk - 32 w).
-// (One call per mask word, so that the masks stay in registers; word 1 only exists for tiles of more than 1024 slots.)
+// Sweep of the four targets over (virtual) chunks [32 w, 32 w + 32) of the staged tile: m = their hit masks
+// (bit = chunk - 32 w).  One call per mask word, so that the masks stay in registers; words past 0 only exist for tiles
+// of more than 1024 slots.
 template <bool HALF, bool FMA>
 __device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile_addr, const RowsTargets& t, float rc2,
                                                 int lane, int w, unsigned (&m)[4]) {
@@ -235,7 +243,7 @@ __device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile
         v0 = v0 > wb ? v0 : wb;
         v1 = v1 < we ? v1 : we;
         if (v0 >= v1) continue;
-        const uint32_t addr = lane_addr + (uint32_t)v0 * (32u * RS);
+        const uint32_t addr = lane_addr + (uint32_t)(d.seg_phys[s] + (v0 - d.seg_vc[s])) * (32u * RS);
         const int key = d.seg_key[s];
         if (key == 0) {
             rows_run_zero<HALF, FMA>(addr, v0, v1, t, rc2, m);
@@ -255,7 +263,7 @@ __device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile
 // its piece of the row, p[k]).  Branch-free: a lane that has run out of bits keeps executing with its load and store
 // predicated off (the loop runs to the longest list of the warp).  SHIFTED rows carry the entry's shift segment in the
 // top bits.  Advances p[k] past the entries written.
-template <bool SHIFTED>
+template <bool SHIFTED, bool ALIAS>
 __device__ __forceinline__ void rows_gather_word(const RowsDesc& d, uint32_t tile_addr, const unsigned (&mw)[4], int w,
                                                  int lane, int* __restrict__ (&p)[4]) {
     constexpr uint32_t RS = sizeof(Rec<float>);
@@ -271,6 +279,8 @@ __device__ __forceinline__ void rows_gather_word(const RowsDesc& d, uint32_t til
     // address of .j of this lane's candidate of chunk 0 of the word; chunk b is b * 512 bytes above
     const uint32_t bot_addr = tile_addr + (uint32_t)lane * RS + 12u + (uint32_t)(w * 32) * (32u * RS);
     const uint32_t seg_bot = smem_u32(&d.vc_seg[0]) + (uint32_t)(w * 32);
+    const uint32_t phys_bot = smem_u32(&d.vc_phys[0]) + (uint32_t)(w * 32);
+    const uint32_t lane_j = tile_addr + (uint32_t)lane * RS + 12u;
 #pragma unroll 2
     for (int r = 0; r < mx; ++r) {
 #pragma unroll
@@ -282,7 +292,14 @@ __device__ __forceinline__ void rows_gather_word(const RowsDesc& d, uint32_t til
             asm("shl.b32 %0, %1, %2;" : "=r"(one) : "r"(1u), "r"(b));   // (clamped shift: 0 for b = -1)
             m[k] = mk ^ one;
             const int b0 = b < 0 ? 0 : b;                           // a lane without bits reads chunk 0 and stores nothing
-            int j = lds_b32(bot_addr + (uint32_t)b0 * (32u * RS));
+            int j;
+            if (ALIAS) {
+                int pc;   // the staged chunk behind virtual chunk 32 w + b0
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pc) : "r"(phys_bot + (uint32_t)b0));
+                j = lds_b32(lane_j + (uint32_t)pc * (32u * RS));
+            } else {
+                j = lds_b32(bot_addr + (uint32_t)b0 * (32u * RS));
+            }
             if (SHIFTED) {
                 int sg;
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sg) : "r"(seg_bot + (uint32_t)b0));
@@ -304,19 +321,24 @@ struct RowsAlloc {
 //   interior cell:        [entries ... padded to 4]                                   row_ref = start << 2
 //   cell at a boundary:   [8 or 32 packed image keys][entries = atom | segment << 27]  row_ref = start << 2 | 1 or 2
 // Epilogue of a trip: popcounts, ONE packed scan pair, ONE reservation, then every lane walks its own set bits.
-// BIG: the tile has more than 32 chunks (second mask word hi); s0 = tile slot of the trip's first target.
-template <bool BIG>
+// W = mask words per lane and target (1: tiles of <= 32 chunks, 2: <= 64, kRowsHugeWords: aliased single-cell tiles);
+// s0 = tile slot of the trip's first target.
+template <int W>
 __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d, Ctrl* ctrl, uint32_t tile_addr,
-                                           unsigned (&lo)[4], unsigned (&hi)[4], int s0, int nt, int lane,
-                                           RowsAlloc& al, int* __restrict__ rows, int* __restrict__ row_ref) {
+                                           unsigned (&m)[W][4], int s0, int nt, int lane, RowsAlloc& al,
+                                           int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
     int n[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (k >= nt) { lo[k] = 0u; if (BIG) hi[k] = 0u; }   // targets past the end of the cell
-        n[k] = __popc(lo[k]) + (BIG ? __popc(hi[k]) : 0);
+        n[k] = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if (k >= nt) m[w][k] = 0u;   // targets past the end of the cell
+            n[k] += __popc(m[w][k]);
+        }
     }
-    // a lane holds <= 64 hits per target, a row <= 2048 entries: two 16-bit fields per scan word
+    // a lane holds <= 192 hits per target, a row < 65536 entries: two 16-bit fields per scan word
     const int pa = n[0] | (n[1] << 16), pb = n[2] | (n[3] << 16);
     int ia = pa, ib = pb;
 #pragma unroll
@@ -326,8 +348,8 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
     }
     const int ta = __shfl_sync(0xffffffffu, ia, 31), tb = __shfl_sync(0xffffffffu, ib, 31);
     const int ea = ia - pa, eb = ib - pb;
-    const int cnt[4] = {ta & 0xffff, ta >> 16, tb & 0xffff, tb >> 16};
-    const int ex[4] = {ea & 0xffff, ea >> 16, eb & 0xffff, eb >> 16};
+    const int cnt[4] = {ta & 0xffff, (int)((unsigned)ta >> 16), tb & 0xffff, (int)((unsigned)tb >> 16)};
+    const int ex[4] = {ea & 0xffff, (int)((unsigned)ea >> 16), eb & 0xffff, (int)((unsigned)eb >> 16)};
     const bool shifted = d.shifted != 0;
     const int hdr = shifted ? (d.nseg <= 8 ? 8 : 32) : 0;
     int start[4];
@@ -371,12 +393,16 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
                     if (k < nt) rows[start[k] + lane] = key;
             }
         }
-        if (shifted) {
-            rows_gather_word<true>(d, tile_addr, lo, 0, lane, p);
-            if (BIG) rows_gather_word<true>(d, tile_addr, hi, 1, lane, p);
+        if (W > 2 || d.aliased != 0) {
+            // (only aliased tiles have more than two mask words; aliased tiles always carry shifts)
+#pragma unroll
+            for (int w = 0; w < W; ++w) rows_gather_word<true, true>(d, tile_addr, m[w], w, lane, p);
+        } else if (shifted) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) rows_gather_word<true, false>(d, tile_addr, m[w], w, lane, p);
         } else {
-            rows_gather_word<false>(d, tile_addr, lo, 0, lane, p);
-            if (BIG) rows_gather_word<false>(d, tile_addr, hi, 1, lane, p);
+#pragma unroll
+            for (int w = 0; w < W; ++w) rows_gather_word<false, false>(d, tile_addr, m[w], w, lane, p);
         }
         // padding entries of every row (read by the bulk copies of the output kernel, never used)
         if (lane < 3) {
@@ -396,7 +422,7 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
 
 // One trip of a consumer warp: four targets (tile slots s0 .. s0 + nt - 1) against the staged tile, then their rows.
 // Four targets share every candidate load; two packed pairs share every FP instruction.
-template <bool HALF, bool FMA, bool BIG>
+template <bool HALF, bool FMA, int W>
 __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds, Ctrl* ctrl, uint32_t tile_addr, int s0,
                                           int nt, float rc2, int lane, RowsAlloc& al, int* __restrict__ rows,
                                           int* __restrict__ row_ref) {
@@ -413,21 +439,28 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
         tg.X01 = add2(pack2(x[0], x[1]), nz); tg.Y01 = add2(pack2(y[0], y[1]), nz); tg.Z01 = add2(pack2(z[0], z[1]), nz);
         tg.X23 = add2(pack2(x[2], x[3]), nz); tg.Y23 = add2(pack2(y[2], y[3]), nz); tg.Z23 = add2(pack2(z[2], z[3]), nz);
     }
-    unsigned lo[4] = {0u, 0u, 0u, 0u}, hi[4] = {0u, 0u, 0u, 0u};
-    rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, 0, lo);
-    if (BIG) rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, 1, hi);
+    unsigned m[W][4];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[w][k] = 0u;
+        if (w == 0 || (w << 5) < ds.nvc) rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, w, m[w]);
+    }
     if (!HALF) {
-        // (i, i, 0) is not a pair: the targets sit in the zero-shift home segment (chunk = slot / 32)
+        // (i, i, 0) is not a pair: the targets sit in the zero-shift home segment, whose virtual chunks are its staged
+        // chunks (chunk = slot / 32)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int sl = s0 + (k < nt ? k : nt - 1);
             if (lane == (sl & 31)) {
                 const unsigned bit = 1u << ((sl >> 5) & 31);
-                if (!BIG || sl < 1024) lo[k] &= ~bit; else hi[k] &= ~bit;
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    if (W == 1 || (sl >> 10) == w) m[w][k] &= ~bit;
             }
         }
     }
-    rows_emit4<BIG>(a, ds, ctrl, tile_addr, lo, hi, s0, nt, lane, al, rows, row_ref);
+    rows_emit4<W>(a, ds, ctrl, tile_addr, m, s0, nt, lane, al, rows, row_ref);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,6 +472,7 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
 // ------------------------------------------------------------------------------------------------
 template <bool HALF, bool FMA>
 __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const RowsArgs a) {
+    pdl_enter();
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kRowsRingBytes);
@@ -468,9 +502,11 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
     // a quota per published tile (paced over the kernel's lifetime), the rest when the queue is drained.
     // (A separate memset kernel does not do: next to this kernel's large CTAs it only runs if the SM already has the
     // large shared-memory carve-out, otherwise the two serialise — profiles/r2_zero_overlap.txt.)
+    // Workloads whose rows mostly carry shifts (small periodic boxes; Ctrl::shift_heavy, set by k_grid) are not
+    // pre-zeroed: the output kernel writes their shifts densely, zeros included, in one pass.
     unsigned char* const zbase = reinterpret_cast<unsigned char*>(a.prezero);
     long long zpos = 0, zend = 0, zquota = 0;    // bytes
-    if (a.prezero) {
+    if (a.prezero && ctrl->shift_heavy == 0) {
         const long long n16 = a.prezero_ints >> 2;
         const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
         long long lo = (long long)blockIdx.x * slice, hi = lo + slice < n16 ? lo + slice : n16;
@@ -504,6 +540,13 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
         int head = 0, used = 0;
         int g_next = 0;
         if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+        // cells with many targets (small systems that are one or a few cells) are not swept by one CTA: whoever meets
+        // such a cell pushes it to the split list as parts of kRowsSplitPart targets; once the cell queue is drained
+        // every CTA pops parts until all cells have been classified and the list is empty
+        int2* split = reinterpret_cast<int2*>(a.ws + a.L.split);
+        const int split_cap = (int)(a.n / 16 + 2);
+        bool phase2 = false;
+        int my_cells = 0;
         // grid of the current system (reloaded only when the system changes)
         int s_cur = -1, cpd0 = 1, cpd1 = 1, cpd2 = 1, R0 = 0, R1 = 0, R2 = 0, pb0 = 0, pb1 = 0, pb2 = 0, coff = 0, c01 = 1;
         float rcp0 = 1.f, rcp01 = 1.f;   // reciprocals for the cell-coordinate division (corrected exactly below)
@@ -523,14 +566,49 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             //         sort, aligned layout) BEFORE waiting for ring space ----
             bool have = false;
             int g = 0, ntarget = 0, st = 0, cn = 0, key = kKeyEmpty, aoff = 0, total = 0, nseg = 1, nvc = 0;
-            int home_slot = 0, si = 0, seg_len = 0, seg_vcb = 0, seg_nch = 0, grp_cn = 0;
+            int home_slot = 0, si = 0, seg_len = 0, seg_vcb = 0, seg_nch = 0, grp_cn = 0, seg_ph = 0;
+            int tgt0 = 0, tgt1 = 0;          // the targets of the cell this work item covers
             unsigned shiftmask = 0u, hm = 1u;
-            bool head_lane = false;
+            bool head_lane = false, alias = false;
             T Sx = (T)0, Sy = (T)0, Sz = (T)0;
             for (;;) {
-                g = __shfl_sync(0xffffffffu, g_next, 0);
-                if (g >= total_cells) break;
-                if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+                bool part = false;           // the item is a part of a cell, popped from the split list
+                if (!phase2) {
+                    g = __shfl_sync(0xffffffffu, g_next, 0);
+                    if (g >= total_cells) {
+                        // cell queue drained: publish how many cells this CTA has classified, then serve the split list
+                        phase2 = true;
+                        if (lane == 0) {
+                            __threadfence();
+                            atomicAdd(&ctrl->cells_done, my_cells);
+                        }
+                        continue;
+                    }
+                    if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+                    ++my_cells;
+                } else {
+                    int ix = 0, iy = 0;
+                    if (lane == 0) {
+                        const int t = atomicAdd(&ctrl->split_next, 1);
+                        volatile int* vdone = &ctrl->cells_done;
+                        volatile int* vres = &ctrl->split_reserved;
+                        for (;;) {
+                            if (t >= split_cap) break;
+                            const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&split[t]);
+                            ix = (int)(unsigned)w; iy = (int)(w >> 32);
+                            if (ix != 0) break;                       // the part has been pushed
+                            if (*vdone >= total_cells) {              // every cell classified: the list is final
+                                __threadfence();
+                                if (t >= *vres) break;                // ... and entry t does not exist
+                            }
+                            __nanosleep(200);
+                        }
+                    }
+                    ix = __shfl_sync(0xffffffffu, ix, 0);
+                    iy = __shfl_sync(0xffffffffu, iy, 0);
+                    if (ix == 0) break;                               // nothing left
+                    g = ix - 1; tgt0 = iy; part = true;
+                }
                 const int home_start = cell_start[g];
                 ntarget = cell_start[g + 1] - home_start;
                 if (ntarget == 0) continue;
@@ -577,6 +655,22 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     for (int k = lane; k < nitems; k += 32) deferred[base + k] = make_int2(g, k * kDeferTargets);
                     for (int k = lane; k < ntarget; k += 32) row_ref[sorted[home_start + k].j] = -1;
                 };
+                auto split_cell = [&]() -> bool {
+                    // a cell with many targets (met in the cell queue): push it as parts instead of sweeping it here
+                    if (part || ntarget <= kRowsSplitAbove) return false;
+                    const int nparts = (ntarget + kRowsSplitPart - 1) / kRowsSplitPart;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&ctrl->split_reserved, nparts);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (int k = lane; k < nparts; k += 32)
+                        if (base + k < split_cap)
+                            *reinterpret_cast<volatile unsigned long long*>(&split[base + k]) =
+                                (unsigned long long)(unsigned)(g + 1) | ((unsigned long long)(unsigned)(k * kRowsSplitPart) << 32);
+                    __threadfence();     // (every lane's entries are visible before this CTA reports its cells as classified)
+                    __syncwarp();
+                    return true;
+                };
+                alias = false;
                 if (r111 && cx >= 1 && cx <= cpd0 - 2 && cy >= 1 && cy <= cpd1 - 2 && cz >= 1 && cz <= cpd2 - 2) {
                     // ---- interior cell (no wrap, every stencil cell in range): the stencil is nine runs of three
                     //      x-adjacent cells, contiguous in the sorted array — nine lanes, two loads each, nine copies
@@ -592,8 +686,11 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     nvc = ((total + 63) >> 6) << 1;    // chunk count padded to an even number (two chunks per trip)
                     if (nvc > kRowsMaxVC) { defer_cell(); continue; }
                     seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0; nseg = 1; hm = 1u; head_lane = lane == 0;
-                    shiftmask = 0u; key = 0; grp_cn = cn;
+                    shiftmask = 0u; key = 0; grp_cn = cn; seg_ph = 0;
                     home_slot = __shfl_sync(0xffffffffu, aoff, 4) + (home_start - __shfl_sync(0xffffffffu, st, 4));
+                    if (split_cell()) continue;
+                    if (!part) tgt0 = 0;
+                    tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
                     have = true;
                     break;
                 }
@@ -649,11 +746,47 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 nseg = 1;
                 hm = 1u;
                 head_lane = lane == 0;
+                // a system that is ONE cell: every image is the same run of records -> stage it once and let the image
+                // segments alias it (virtual chunks = image * chunks-per-image; up to kRowsMaxVCAlias of them)
+                alias = ok && shiftmask != 0u && sp.ncells == 1;
+                if (alias) {
+                    const unsigned nonempty = __ballot_sync(0xffffffffu, cn > 0);
+                    const int cn1 = __shfl_sync(0xffffffffu, cn, 0), st1 = __shfl_sync(0xffffffffu, st, 0);   // (zero shift first)
+                    const int nch = (cn1 + 31) >> 5;
+                    nseg = __popc(nonempty);
+                    hm = nonempty;
+                    head_lane = cn > 0;
+                    si = __popc(nonempty & (0xffffffffu >> (31 - lane))) - 1;
+                    seg_len = cn > 0 ? cn1 : 0;
+                    seg_nch = cn > 0 ? nch : 0;
+                    seg_vcb = si * nch;
+                    seg_ph = 0;
+                    nvc = nseg * nch;
+                    total = cn1;                       // records staged
+                    aoff = 0;
+                    st = st1;
+                    grp_cn = lane == 0 ? cn1 : 0;
+                    home_slot = home_start - st1;
+                    if (head_lane) {
+                        int csx, csy, csz;
+                        unpack_key(key, csx, csy, csz);
+                        T cm[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
+                        shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
+                    }
+                    if (nvc > kRowsMaxVCAlias || nch * 32 * (int)RS > kRowsRingBytes) { defer_cell(); continue; }
+                    if (split_cell()) continue;
+                    if (!part) tgt0 = 0;
+                    tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
+                    have = true;
+                    break;
+                }
                 if (!shiftmask) {
                     // interior cell: one zero-shift segment, chunk count padded to an even number (two chunks per trip)
                     aoff = off;
                     nvc = ((total + 63) >> 6) << 1;
-                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0;
+                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0; seg_ph = 0;
                 } else {
                     // segments = runs of equal shift among the non-empty images; each starts on a 32-slot boundary
                     const int pk = __shfl_up_sync(0xffffffffu, key, 1);
@@ -670,6 +803,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     seg_nch = (seg_len + 31) >> 5;
                     const int vincl = warp_incl_scan(seg_nch, lane);
                     seg_vcb = vincl - seg_nch;
+                    seg_ph = seg_vcb;
                     nvc = __shfl_sync(0xffffffffu, vincl, 31);
                     si = __popc(hm & le) - 1;
                     const int seg_off = __shfl_sync(0xffffffffu, off, hl);
@@ -702,13 +836,16 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     const int incl_last = __shfl_sync(0xffffffffu, incl, last);
                     grp_cn = cont ? 0 : incl_last - off;
                 }
+                if (split_cell()) continue;
+                if (!part) tgt0 = 0;
+                tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
                 have = true;
                 break;
             }
             // ---- 2. descriptor slot + ring space (FIFO release), then publish the tables
             //         and issue the copies ----
             const int dslot = nprod % kRowsDesc;
-            const int bytes = have ? nvc * 32 * (int)RS : 0;
+            const int bytes = have ? (alias ? ((total + 31) >> 5) : nvc) * 32 * (int)RS : 0;
             int foot, data_off;
             for (;;) {
                 foot = bytes; data_off = head;
@@ -736,16 +873,27 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             const uint32_t tile_addr = ring_addr + (uint32_t)data_off;
             if (head_lane) {
                 ds.seg_vc[si] = seg_vcb;
+                ds.seg_phys[si] = seg_ph;
                 ds.seg_key[si] = shiftmask ? key : 0;
-                ds.segS[si][0] = Sx; ds.segS[si][1] = Sy; ds.segS[si][2] = Sz; ds.segS[si][3] = (T)0;
+                ds.segS[si][0] = Sx; ds.segS[si][1] = Sy; ds.segS[si][2] = Sz;
             }
             if (lane == 0) {
                 ds.seg_vc[nseg] = nvc;
-                ds.item = g; ds.ntarget = ntarget; ds.home_slot = home_slot; ds.nseg = nseg; ds.nvc = nvc;
-                ds.data_off = data_off; ds.shifted = shiftmask ? 1 : 0; ds.next_target = 0; ds.footprint = foot;
+                ds.item = g; ds.ntarget = tgt1; ds.home_slot = home_slot; ds.nseg = nseg; ds.nvc = nvc;
+                ds.data_off = data_off; ds.shifted = shiftmask ? 1 : 0; ds.next_target = tgt0; ds.footprint = foot;
+                ds.aliased = alias ? 1 : 0;
             }
             // sentinel records behind every segment (up to its padded end) and the chunk -> segment table
-            {
+            if (alias) {
+                const int nch = (total + 31) >> 5;
+                for (int q = total + lane; q < (nch << 5); q += 32)
+                    sts_rec(tile_addr + (uint32_t)q * RS, kRowsFar, kRowsFar, kRowsFar, -1);
+                for (int v = lane; v < nvc; v += 32) {
+                    const int sg = v / nch;
+                    ds.vc_seg[v] = (unsigned char)sg;
+                    ds.vc_phys[v] = (unsigned char)(v - sg * nch);
+                }
+            } else {
                 int myseg0 = 0, myseg1 = 0;
                 unsigned rest = hm;
                 while (rest) {
@@ -775,14 +923,27 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             if (lane == 0 && zpos < zend) zero_some(zquota);
         }
         if (lane == 0 && zpos < zend) zero_some(zend - zpos);
-        if (lane == 0 && a.prezero) tma_store_wait_all();
+        if (lane == 0 && zend > 0) tma_store_wait_all();
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
-        if (lane == 0) {
-            __threadfence();
-            const int dn = atomicAdd(&ctrl->done[0], 1);
+        {
+            int dn = 0;
+            if (lane == 0) {
+                __threadfence();
+                dn = atomicAdd(&ctrl->done[0], 1);
+            }
+            dn = __shfl_sync(0xffffffffu, dn, 0);
             if (dn == (int)gridDim.x - 1) {
-                ctrl->work_counter[0] = 0;
-                ctrl->done[0] = 0;
+                // (every other CTA has left its pop loop: the split list can be cleared for the next query)
+                const int used_parts = *reinterpret_cast<volatile int*>(&ctrl->split_reserved);
+                for (int k = lane; k < used_parts && k < split_cap; k += 32) split[k] = make_int2(0, 0);
+                __syncwarp();
+                if (lane == 0) {
+                    ctrl->work_counter[0] = 0;
+                    ctrl->done[0] = 0;
+                    ctrl->split_reserved = 0;
+                    ctrl->split_next = 0;
+                    ctrl->cells_done = 0;
+                }
             }
         }
     } else {
@@ -799,17 +960,20 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             if (ds.item < 0) break;
             const uint32_t tile_addr = ring_addr + (uint32_t)ds.data_off;
             const int ntarget = ds.ntarget, home_slot = ds.home_slot;
-            const bool big = ds.nvc > 32;   // (rare: tiles of more than 1024 slots need a second mask word)
+            const int words = ds.nvc <= 32 ? 1 : (ds.nvc <= 64 ? 2 : kRowsHugeWords);   // mask words per lane and target
             for (;;) {
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&ds.next_target, 4);
                 t0 = __shfl_sync(0xffffffffu, t0, 0);
                 if (t0 >= ntarget) break;
                 const int nt = ntarget - t0 < 4 ? ntarget - t0 : 4;
-                if (big)
-                    rows_trip<HALF, FMA, true>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
+                if (words == 1)
+                    rows_trip<HALF, FMA, 1>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
+                else if (words == 2)
+                    rows_trip<HALF, FMA, 2>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
                 else
-                    rows_trip<HALF, FMA, false>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
+                    rows_trip<HALF, FMA, kRowsHugeWords>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows,
+                                                         row_ref);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[dslot]));
@@ -857,12 +1021,36 @@ __device__ __noinline__ void rows_out_row(const int* row, int hdr, int cnt, int 
             oi[k] = iv;
         }
         if (!shifts_zeroed) warp_fill(sh, 3 * cnt, 0, lane);
+    } else if (!shifts_zeroed) {
+        // every component of every shift, zeros included, as coalesced stores: element e = lane + 32 u of a group of 32
+        // pairs (96 ints) belongs to pair e / 3, component e % 3
+        const int keyl = lane < hdr ? row[lane - hdr] : 0;
+        int q[3], c8[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int e = lane + 32 * u;
+            q[u] = e / 3;
+            c8[u] = 8 * (e - 3 * q[u]);
+        }
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
+            const int e = k < cnt ? row[k] : 0;
+            if (k < cnt) {
+                oj[k] = (e & ((1 << kRowsSegShift) - 1)) + index_offset;
+                oi[k] = iv;
+            }
+            const int key = __shfl_sync(0xffffffffu, keyl, ((unsigned)e >> kRowsSegShift) & 31);
+            const int pk = key == 0 ? kZeroPack : key - 1;           // bytes = shift component + 128
+            int* __restrict__ shg = sh + 3 * k0;
+            const int nel = 3 * (cnt - k0);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int pq = __shfl_sync(0xffffffffu, pk, q[u]);
+                if (lane + 32 * u < nel) shg[lane + 32 * u] = ((pq >> c8[u]) & 255) - 128;
+            }
+        }
     } else {
         const int keyl = lane < hdr ? row[lane - hdr] : 0;
-        if (!shifts_zeroed) {
-            warp_fill(sh, 3 * cnt, 0, lane);
-            __syncwarp();  // the zeros of other lanes precede the image shifts written below
-        }
         for (int k0 = 0; k0 < cnt; k0 += 32) {
             const int k = k0 + lane;
             const int e = k < cnt ? row[k] : 0;
@@ -890,6 +1078,7 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
                                                              const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
                                                              int* __restrict__ out_j_arg, int* __restrict__ out_shifts,
                                                              int index_offset, int shifts_zeroed, long long spec_cap) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char out_smem_raw[];
     RowsOutSmem& sm = *reinterpret_cast<RowsOutSmem*>(out_smem_raw);
     int* __restrict__ out_j = out_j_arg;
@@ -899,6 +1088,8 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
         if (ctrl->unwrapped != 0 || ctrl->rows_overflow != 0 || total > (unsigned long long)spec_cap) return;
         out_j = out_i + total;
     }
+    // (the sweep did not pre-zero the shifts of a shift-heavy workload, whatever buffer it was handed)
+    if (reinterpret_cast<const Ctrl*>(ws + L.ctrl)->shift_heavy != 0) shifts_zeroed = 0;
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
     const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -982,12 +1173,16 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
 
 // resets the per-query state of the control block
 __global__ void k_query_reset(unsigned char* __restrict__ ws, WsLayout L, long long n, int with_rows) {
+    pdl_enter();
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid == 0) {
         ctrl->n_deferred = 0;
         ctrl->rows_cursor = 0ull;
         ctrl->rows_overflow = 0;
+        ctrl->split_next = 0;
+        ctrl->cells_done = 0;
+        // (split_reserved counts entries the last sweep may not have cleared if it was aborted; k_rows clears and resets it)
     }
     (void)n; (void)with_rows;
 }

@@ -230,6 +230,7 @@ __device__ __forceinline__ int sweep_target(const SweepArgs<T>& a, const SweepSm
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool HALF, bool FMA>
 __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const SweepArgs<T> a) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Rec<T>* cand = reinterpret_cast<Rec<T>*>(smem_raw);
     int* rows = reinterpret_cast<int*>(smem_raw + kSweepCandBytes);

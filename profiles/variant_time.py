@@ -60,3 +60,20 @@ for it in range(6):
     a.record(); out = neighbor_list(b5[0], 6.0, cell=b5[1], pbc=b5[2], batch_idx=b5[3], batch_ptr=b5[4], return_neighbor_list=True, method='batch_cell_list'); b.record()
     torch.cuda.synchronize(); ts.append(a.elapsed_time(b)); del out
 print('%s cfg5 api ms %.3f' % (os.path.basename(sys.argv[1]), sorted(ts)[len(ts) // 2]))
+# config 5 without the fused zero-fill (every row of a 3-cell box carries shifts), and config 3
+config.prezero_shifts = False
+ts = []
+for it in range(6):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); out = neighbor_list(b5[0], 6.0, cell=b5[1], pbc=b5[2], batch_idx=b5[3], batch_ptr=b5[4], return_neighbor_list=True, method='batch_cell_list'); b.record()
+    torch.cuda.synchronize(); ts.append(a.elapsed_time(b)); del out
+print('%s cfg5 api ms (prezero off) %.3f' % (os.path.basename(sys.argv[1]), sorted(ts)[len(ts) // 2]))
+config.prezero_shifts = True
+del b5
+b3 = [t.to(dev) for t in bench_batch(512, 150, 250, seed=3, mixed_pbc=True)]
+ts = []
+for it in range(12):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); out = neighbor_list(b3[0], 6.0, cell=b3[1], pbc=b3[2], batch_idx=b3[3], batch_ptr=b3[4], return_neighbor_list=True, method='batch_cell_list'); b.record()
+    torch.cuda.synchronize(); ts.append(a.elapsed_time(b)); del out
+print('%s cfg3 api ms %.3f' % (os.path.basename(sys.argv[1]), sorted(ts)[len(ts) // 2]))

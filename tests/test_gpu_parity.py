@@ -850,6 +850,55 @@ def test_coo_paths_coincident_atoms_and_small_periodic_box(coo_path):
     assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), coo_path
 
 
+def test_coo_paths_single_cell_systems_and_many_target_cells(coo_path):
+    """Systems that are ONE cell (box edge < 2 rc): every image of the stencil is the same run of records — staged once,
+    aliased by up to 27 shift segments — and cells with more than 64 targets, which several CTAs sweep in parts.
+    All 8 PBC patterns, both fill modes, batched next to ordinary systems; plus one dense box whose 8 cells hold
+    ~250 atoms each."""
+    from nvalchemiops_b200 import config
+
+    g = torch.Generator().manual_seed(77)
+    counts = [40, 97, 150, 172, 60, 130, 166, 33, 171, 90, 165, 120, 20, 173, 101, 149, 400, 650]
+    Ls = [9.5, 10.0, 11.45, 11.98, 7.0, 11.0, 11.9, 6.5, 11.95, 8.0, 11.8, 10.5, 6.2, 12.0, 9.9, 11.4, 16.0, 19.0]
+    pos, cells, pbcs, bidx = [], [], [], []
+    for s, (n, L) in enumerate(zip(counts, Ls)):
+        pos.append(torch.rand(n, 3, generator=g) * L)
+        cells.append(torch.eye(3) * L)
+        pbcs.append(torch.tensor([(s & 1) > 0, (s & 2) > 0, (s & 4) > 0]) if s % 9 != 8 else torch.tensor([True, True, True]))
+        bidx.append(torch.full((n,), s, dtype=torch.int32))
+    # every fully periodic single-cell case once more, so that 27-image tiles of several sizes occur
+    for n, L in ((170, 11.9), (64, 9.0), (33, 6.3)):
+        s = len(pos)
+        pos.append(torch.rand(n, 3, generator=g) * L); cells.append(torch.eye(3) * L)
+        pbcs.append(torch.tensor([True, True, True])); bidx.append(torch.full((n,), s, dtype=torch.int32))
+    pos, cell, pbc, bidx = torch.cat(pos), torch.stack(cells), torch.stack(pbcs), torch.cat(bidx)
+    d = [t.to(DEV) for t in (pos, cell, pbc, bidx)]
+    for half in (False, True):
+        for fma in (True, False):
+            config.fma = fma
+            try:
+                want = ro.records_from_matrix(*ro.batch_cell_list(pos, 6.0, cell, pbc, bidx, max_neighbors=1536, half_fill=half,
+                                                                  fma_mode=int(fma), nthreads=8))
+                e, p, sft = _nl().batch_cell_list(d[0], 6.0, d[1], d[2], d[3], half_fill=half, return_neighbor_list=True)
+            finally:
+                config.fma = True
+            got = ro.records_from_coo(e.cpu(), sft.cpu())
+            if half:
+                assert np.array_equal(np.unique(ro.canonical_undirected(got), axis=0),
+                                      np.unique(ro.canonical_undirected(want), axis=0)), (coo_path, fma)
+                assert got.shape[0] == want.shape[0]
+            else:
+                assert np.array_equal(got, want), (coo_path, fma)
+            num = (p[1:] - p[:-1]).cpu().numpy()
+            assert np.array_equal(num, np.bincount(got[:, 0], minlength=pos.shape[0]))
+    # a dense periodic box: 2 x 2 x 2 cells of ~250 atoms (> 64 targets per cell -> swept in parts), repeated queries
+    pos, cell, pbc = random_system(2000, 12.6, torch.float32, seed=9)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=2048, nthreads=8))
+    for _ in range(2):
+        e, p, sft = _nl().cell_list(pos.to(DEV), 6.0, cell.to(DEV), pbc.to(DEV), return_neighbor_list=True)
+        assert np.array_equal(ro.records_from_coo(e.cpu(), sft.cpu()), want), coo_path
+
+
 def test_coo_paths_batch_and_sharded_blocks(coo_path):
     """Batched mixed-PBC systems through the public API, and the rank-sharded fill (index_offset, block layout)."""
     from nvalchemiops_b200.neighborlist import _engine
