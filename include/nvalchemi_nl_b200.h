@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NVNL_ABI_VERSION 3
+#define NVNL_ABI_VERSION 4
 #define NVNL_F32 0
 #define NVNL_F64 1
 
@@ -72,8 +72,9 @@ int nvnl_count(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, c
  * found by the last nvnl_count, the largest per-atom count (what assert_max_neighbors checks,
  * neighbor_utils.py:352-359), number of cells, error bits, and whether any atom was outside the
  * primary periodic image (*unwrapped bit 0; bit 1 = some system searches more than one cell per side, i.e. periodic
- * shifts may exceed +-1), and whether any cell was left to the general kernel (both feed nvnl_fill_coo's
- * launch_hint), and whether nvnl_count_rows ran out of temporary row space (then the caller repeats the query with
+ * shifts may exceed +-1), and whether any cell was left to the general kernel (*had_deferred bit 0; bit 1 = some
+ * single-cell system needed the second single-sweep launch of nvnl_count_rows, its launch_hint bit 5) (both feed
+ * nvnl_fill_coo's launch_hint), and whether nvnl_count_rows ran out of temporary row space (then the caller repeats the query with
  * nvnl_count / nvnl_fill_coo).  The one sync of the COO path (the reference has three). Host pointers. */
 int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, int64_t* total_pairs,
                 int32_t* max_count, int32_t* total_cells, int32_t* error_bits, int32_t* unwrapped, int32_t* had_deferred,
@@ -102,10 +103,14 @@ int nvnl_fill_coo(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems
  * issue-bound, the zero_() of the shifts output (cell_list.py:1358-1373) is pure HBM writes.  A caller that can guess
  * the pair count (e.g. from its previous query) passes its shifts buffer here and sets launch_hint bit 2 (value 4) of
  * nvnl_fill_rows: `shifts` is already zero — only rows of cells at a periodic boundary write their image shifts.
+ * Workloads whose rows mostly carry shifts (small periodic boxes; decided on the device when the grid is built) are
+ * not pre-zeroed whatever buffer is passed: nvnl_fill_rows / _speculative then write every shift component themselves.
+ * Cells with more than 64 target atoms are swept in parts of 32 targets by several CTAs (device-side work list).
  * Atom indices must be below 2^27 on this path.
  *   launch_hint: -1 = launch every kernel variant (the ones without work retire at once); >= 0 = the launch_hint
  *   nvnl_status reported for an earlier query of this kind (bit 0: atoms outside the primary image, bit 1: cells left to
- *   the general kernel): variants that would find no work are not launched.  The caller compares with nvnl_status
+ *   the general kernel, bit 5 = value 32: single-cell periodic systems whose 27 images take the second launch with six
+ *   mask words): variants that would find no work are not launched.  The caller compares with nvnl_status
  *   afterwards and repeats the call with -1 if the hint missed a bit. */
 int nvnl_count_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
                     double cutoff_sq, int half_fill, int fma, int32_t* num_neighbors, int32_t* neighbor_ptr,
@@ -115,7 +120,7 @@ int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_system
                    int64_t num_pairs, int64_t row_stride, int32_t* shifts, int32_t index_offset, int32_t launch_hint,
                    void* stream);
 
-/* EXPERIMENTAL (compiled, not yet measured on hardware; nvalchemiops_b200.config.speculative_fill, off by default):
+/* Speculative output launch (nvalchemiops_b200.config.speculative_fill, on by default):
  * the output kernel of the single-sweep path launched BEFORE the size sync, into buffers sized from a guess
  * (edge_buffer: 2 * capacity_pairs int32, shifts_zeroed: 3 * capacity_pairs int32, already zero — e.g. the prezero
  * buffer of nvnl_count_rows).  The kernel reads the pair count P on the device: if P <= capacity_pairs (and the query was
@@ -125,6 +130,32 @@ int nvnl_fill_rows(void* workspace, int dtype, int64_t n_atoms, int32_t n_system
 int nvnl_fill_rows_speculative(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* neighbor_ptr,
                                int32_t* edge_buffer, int64_t capacity_pairs, int32_t* shifts_zeroed, int32_t index_offset,
                                void* stream);
+
+/* SURVEY.md §8f rank 2 — the stencil sweep fused with a pair consumer: the neighbor list is never written.
+ * Consumer = the reference's real-space Coulomb / Ewald energies and forces
+ * (nvalchemiops/interactions/electrostatics/coulomb.py:1540 coulomb_energy_forces; kernels :206-292 list format,
+ * :352-428 matrix format): per directed entry (i, j, s) with r = |r_i - r_j - s·cell|, skipped when r >= cutoff or
+ * r < 1e-10:  E_i += q_i q_j erfc(alpha r) / (2 r);  f = q_i q_j/2 [erfc(alpha r)/r^3 + 2 alpha/sqrt(pi) exp(-alpha^2 r^2)/r^2] r_ij;
+ * F_i += f, F_j -= f.  alpha = 0: plain Coulomb.  Everything in float64, charges/energies/forces are double arrays.
+ *
+ * nvnl_coulomb_fused: after nvnl_build.  The entries are the ones nvnl_count_rows / the reference's cell_list would list
+ * (fp32 predicate d^2 < cutoff_sq, full list); the pair terms are evaluated in fp64 from the staged records while the
+ * sweep runs.  energies [n_atoms], forces [n_atoms,3] are written (not accumulated) for every atom the sweep handled.
+ * The caller MUST read nvnl_status afterwards: if *unwrapped bit 0 or *had_deferred is set, some atoms were not handled
+ * (atoms outside the primary image, stencils wider than one cell, over-full cells) and the result must be recomputed
+ * with nvnl_count_rows/nvnl_fill_rows + nvnl_coulomb_list — the Python binding does exactly that.  fp32 positions only.
+ *
+ * nvnl_coulomb_list: the same consumer over an EXISTING neighbor list — COO (neighbor_ptr [n_atoms+1], neighbors [P] = row 1
+ * of edge_index, shifts [P,3]) or, with neighbor_ptr == NULL, the padded matrix (neighbors [n_atoms,max_neighbors],
+ * shifts [n_atoms,max_neighbors,3], entries >= fill_value are padding).  Any list (also half lists): the reaction on j
+ * is accumulated with fp64 atomics, as the reference does.  cell [n_systems,3,3] in the dtype of positions. */
+int nvnl_coulomb_fused(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                       double cutoff_sq, int fma, const double* charges, double cutoff, double alpha, double* energies,
+                       double* forces, void* stream);
+int nvnl_coulomb_list(const void* positions, int dtype, int64_t n_atoms, const void* cell, int32_t n_systems,
+                      const int32_t* batch_idx, const double* charges, double cutoff, double alpha, const int32_t* neighbor_ptr,
+                      const int32_t* neighbors, const int32_t* shifts, int32_t max_neighbors, int32_t fill_value,
+                      double* energies, double* forces, void* stream);
 
 /* query_cell_list / batch_query_cell_list (cell_list.py:892-1034, batch_cell_list.py:915-1067)
  * fused with the fill_()/zero_() of the outputs (cell_list.py:1358-1373): every slot of

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libnvalchemi_nl_b200.so")
 SOURCES = ["nvnl_api.cu"]
-HEADERS = ["nvnl_common.cuh", "nvnl_build.cuh", "nvnl_sweep.cuh", "nvnl_fast.cuh", "nvnl_rows.cuh", "nvnl_cache.cuh", os.path.join("..", "..", "include", "nvalchemi_nl_b200.h")]
+HEADERS = ["nvnl_common.cuh", "nvnl_build.cuh", "nvnl_sweep.cuh", "nvnl_fast.cuh", "nvnl_rows.cuh", "nvnl_pair.cuh", "nvnl_cache.cuh", os.path.join("..", "..", "include", "nvalchemi_nl_b200.h")]
 
 
 def _nvcc() -> str:

@@ -131,10 +131,10 @@ int launch_fast_t(const SweepArgs<T>& a, cudaStream_t st) {
     return 0;
 }
 
-template <bool HALF, bool FMA>
+template <bool HALF, bool FMA, bool HUGE, bool PAIR = false>
 int launch_rows_t(const RowsArgs& a, cudaStream_t st) {
-    auto kern = k_rows<HALF, FMA>;
-    constexpr size_t smem = rows_smem_bytes();
+    auto kern = k_rows<HALF, FMA, HUGE, PAIR>;
+    constexpr size_t smem = rows_smem_bytes(PAIR);
     static std::atomic<int> bps[kMaxDevices];
     int blocks_per_sm = bps[current_device()].load(std::memory_order_relaxed);
     if (blocks_per_sm == 0) {
@@ -343,8 +343,13 @@ int count_rows_t(unsigned char* ws, long long n, int ns, const int* batch_idx, d
     r.num_neighbors = num_neighbors;
     r.prezero = prezero_ints > 0 ? prezero : nullptr;
     r.prezero_ints = prezero_ints > 0 ? prezero_ints : 0;
-    rc = launch_rows_t<HALF, FMA>(r, st);                                   // wrapped inputs: the single sweep
+    r.q_sorted = nullptr; r.pair_energies = nullptr; r.pair_forces = nullptr; r.pair_cutoff = 0.0; r.pair_alpha = 0.0;
+    rc = launch_rows_t<HALF, FMA, false>(r, st);                            // wrapped inputs: the single sweep
     if (rc) return rc;
+    if (hint < 0 || (hint & 32)) {
+        rc = launch_rows_t<HALF, FMA, true>(r, st);                         // single-cell systems with 27 images (else retires)
+        if (rc) return rc;
+    }
     // hint >= 0 (what nvnl_status reported for an earlier query with this signature): the kernels that would find no
     // work are not launched; the caller checks nvnl_status afterwards and repeats the call with hint = -1 if it was wrong
     if (hint < 0 || (hint & 1)) {
@@ -523,7 +528,7 @@ int nvnl_status(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, 
     if (total_cells) *total_cells = h.total_cells;
     if (error_bits) *error_bits = h.error;
     if (unwrapped) *unwrapped = (h.unwrapped ? 1 : 0) | (h.wide_stencil ? 2 : 0);
-    if (had_deferred) *had_deferred = h.had_deferred;
+    if (had_deferred) *had_deferred = (h.had_deferred ? 1 : 0) | (h.had_huge ? 2 : 0);
     if (rows_overflow) *rows_overflow = h.rows_overflow;
     return 0;
 }
@@ -613,6 +618,63 @@ int nvnl_fill_rows_speculative(void* workspace, int dtype, int64_t n_atoms, int3
     const WsLayout L = mk_layout(n_atoms, n_systems, rec_bytes(dtype));
     return launch_rows_out<true>(ws, L, n_atoms, neighbor_ptr, edge_buffer, nullptr, shifts_zeroed, index_offset, 1,
                                  capacity_pairs, st);
+}
+
+int nvnl_coulomb_fused(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,
+                       double cutoff_sq, int fma, const double* charges, double cutoff, double alpha, double* energies,
+                       double* forces, void* stream) {
+    if (!workspace || !charges || !energies || !forces || n_atoms <= 0) return fail(-1, "nvnl_coulomb_fused: bad arguments");
+    if (dtype != NVNL_F32) return fail(-1, "nvnl_coulomb_fused: the fused sweep is fp32-position only");
+    if (n_atoms >= (1LL << 27)) return fail(-1, "nvnl_coulomb_fused: atom indices must be below 2^27");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    SweepArgs<float> a = base_args<float>(ws, n_atoms, n_systems, batch_idx, cutoff_sq);
+    int rc = launch_query_reset(ws, a.L, n_atoms, 1, st);
+    if (rc) return rc;
+    // charges in cell-sorted order; they live in the hit-mask region of the workspace, which this path does not use
+    double* q_sorted = reinterpret_cast<double*>(ws + a.L.masks);
+    {
+        long long blocks = (n_atoms + 255) / 256;
+        if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+        launch_pdl(k_gather_q, (unsigned)blocks, 256, 0, st, ws, a.L, n_atoms, charges, q_sorted);
+        NVNL_CHECK_LAUNCH("k_gather_q");
+    }
+    RowsArgs r;
+    r.ws = ws; r.L = a.L; r.batch_idx = batch_idx; r.num_systems = n_systems; r.n = n_atoms; r.cutoff_sq = (float)cutoff_sq;
+    r.num_neighbors = nullptr; r.prezero = nullptr; r.prezero_ints = 0;
+    r.q_sorted = q_sorted; r.pair_energies = energies; r.pair_forces = forces; r.pair_cutoff = cutoff; r.pair_alpha = alpha;
+    return fma ? launch_rows_t<false, true, false, true>(r, st) : launch_rows_t<false, false, false, true>(r, st);
+}
+
+int nvnl_coulomb_list(const void* positions, int dtype, int64_t n_atoms, const void* cell, int32_t n_systems,
+                      const int32_t* batch_idx, const double* charges, double cutoff, double alpha, const int32_t* neighbor_ptr,
+                      const int32_t* neighbors, const int32_t* shifts, int32_t max_neighbors, int32_t fill_value,
+                      double* energies, double* forces, void* stream) {
+    if (!positions || !cell || !charges || !energies || !forces || n_atoms <= 0 || n_systems <= 0)
+        return fail(-1, "nvnl_coulomb_list: bad arguments");
+    if (!neighbor_ptr && max_neighbors < 0) return fail(-1, "nvnl_coulomb_list: matrix format needs max_neighbors >= 0");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(energies, 0, sizeof(double) * (size_t)n_atoms, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(forces, 0, sizeof(double) * 3 * (size_t)n_atoms, st);
+    if (e != cudaSuccess) return fail(-2, "nvnl_coulomb_list: memset", e);
+    if ((!neighbor_ptr && max_neighbors == 0) || !neighbors || !shifts) return 0;
+    long long blocks = (n_atoms * 32 + 255) / 256;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
+    if (dtype == NVNL_F32) {
+        k_coulomb_list<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(positions), charges,
+                                                                 static_cast<const float*>(cell), batch_idx, n_systems, n_atoms,
+                                                                 neighbor_ptr, neighbors, shifts, max_neighbors, fill_value,
+                                                                 cutoff, alpha, energies, forces);
+    } else if (dtype == NVNL_F64) {
+        k_coulomb_list<double><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const double*>(positions), charges,
+                                                                  static_cast<const double*>(cell), batch_idx, n_systems, n_atoms,
+                                                                  neighbor_ptr, neighbors, shifts, max_neighbors, fill_value,
+                                                                  cutoff, alpha, energies, forces);
+    } else {
+        return fail(-1, "nvnl_coulomb_list: unsupported dtype");
+    }
+    NVNL_CHECK_LAUNCH("k_coulomb_list");
+    return 0;
 }
 
 int nvnl_fill_matrix(void* workspace, int dtype, int64_t n_atoms, int32_t n_systems, const int32_t* batch_idx,

@@ -19,7 +19,7 @@ namespace nvnl {
 // ------------------------------------------------------------------------------------------------
 struct WsLayout {
     size_t ctrl, sys, bbox, cell_count, cell_start, atom_cell, atom_rank, atom_ashift, sorted, sorted_ashift,
-        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, row_ref, split, rows, total;
+        cursor, scan_status0, scan_status1, masks, deferred, ptr_sorted, row_ref, split, huge, rows, total;
     long long max_cells;  // N + S (upper bound on the number of cells, see k_grid)
     long long rows_cap;   // entries of the temporary row buffer (single-sweep COO path, nvnl_rows.cuh)
 };
@@ -60,6 +60,8 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     // parts of cells with many targets: (cell + 1, first target) — a cell of more than 64 targets is cut into parts of
     // 32, so there are fewer than n / 16 + 1 of them
     L.split = take(sizeof(int2) * (size_t)(n / 16 + 2));
+    // parts (32 targets) of single-cell systems that take the six-mask-word launch: (cell, first target)
+    L.huge = take(sizeof(int2) * (size_t)(n / 32 + s + 2));
     L.rows_cap = rows_per_atom * n + rows_slack;
     if (L.rows_cap < 1) L.rows_cap = 1;
     if (L.rows_cap > (1LL << 29) - 1) L.rows_cap = (1LL << 29) - 1;   // row_ref = first entry << 2 | header kind
@@ -101,6 +103,7 @@ __global__ void k_init(unsigned char* __restrict__ ws, WsLayout L, long long n, 
         ctrl->wide_stencil = 0;
         ctrl->shift_heavy = 0;
         ctrl->split_reserved = ctrl->split_next = ctrl->cells_done = 0;
+        ctrl->n_huge = ctrl->huge_next = ctrl->huge_done = ctrl->had_huge = 0;
     }
     {
         int2* split = reinterpret_cast<int2*>(ws + L.split);   // (entry.x == 0: not pushed yet)
@@ -232,12 +235,43 @@ __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, 
             if (need_counts && threadIdx.x == 0) atomicAdd(&sys[s_first].natoms, (int)(end - base));
         } else {
             (void)cnt; (void)s_cnt;
-            for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-                const int s = batch_idx[i];
-                if (s < 0 || s >= num_systems) {
+            // several systems in the chunk: warps whose 32 atoms belong to ONE system (the usual case, systems of a few
+            // hundred atoms) reduce in registers and issue one atomic per value; mixed warps fall back to per-atom atomics
+            const int lane = threadIdx.x & 31;
+            for (long long i0 = base + (threadIdx.x & ~31); i0 < end; i0 += blockDim.x) {
+                const long long i = i0 + lane;
+                bool act = i < end;
+                int s = act ? batch_idx[i] : -1;
+                if (act && (s < 0 || s >= num_systems)) {
                     atomicOr(&ctrl->error, ERR_BAD_BATCH_IDX);
+                    act = false;
+                    s = -1;
+                }
+                const int s0 = __shfl_sync(0xffffffffu, s, 0);
+                if (__all_sync(0xffffffffu, act && s == s0)) {
+                    const SysParams& sp = sys[s0];
+                    if (need_counts && lane == 0) atomicAdd(&sys[s0].natoms, 32);
+                    if (sp.pbc[0] && sp.pbc[1] && sp.pbc[2]) continue;
+                    const double px = (double)pos[3 * i], py = (double)pos[3 * i + 1], pz = (double)pos[3 * i + 2];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        if (!sp.pbc[d]) {
+                            const double fr = px * sp.inv[d] + py * sp.inv[3 + d] + pz * sp.inv[6 + d];
+                            long long lo = order_key(fr), hi = lo;
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const long long u = __shfl_xor_sync(0xffffffffu, lo, o), v = __shfl_xor_sync(0xffffffffu, hi, o);
+                                lo = u < lo ? u : lo;
+                                hi = v > hi ? v : hi;
+                            }
+                            if (lane == 0) {
+                                atomicMin(&bbox[s0 * 6 + d], lo);
+                                atomicMax(&bbox[s0 * 6 + 3 + d], hi);
+                            }
+                        }
+                    }
                     continue;
                 }
+                if (!act) continue;
                 const SysParams& sp = sys[s];
                 if (need_counts) atomicAdd(&sys[s].natoms, 1);
                 if (sp.pbc[0] && sp.pbc[1] && sp.pbc[2]) continue;

@@ -70,6 +70,10 @@ struct Ctrl {
     int split_reserved;              // entries of the part list handed out to pushers
     int split_next;                  // next entry to pop
     int cells_done;                  // cells whose parts (if any) have been pushed; == total_cells ends the pop loop
+    // ... and single-cell systems whose 27 images need more than 64 chunks go to a second launch (k_rows<HUGE>)
+    int n_huge;                      // entries of the huge list (parts of such cells)
+    int huge_next, huge_done;        // pop counter / CTAs that drained it
+    int had_huge;                    // sticky since the last build: some cell went to the huge list
 };
 
 // Programmatic dependent launch (PDL): kernels of the hot chain are launched with the programmatic-stream-serialization

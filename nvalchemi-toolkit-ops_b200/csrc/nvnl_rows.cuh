@@ -63,7 +63,6 @@ struct RowsDesc {
     int aliased;                      // every segment is an image of the SAME staged records (single-cell system)
     int pad0[2];
     int seg_vc[kRowsMaxSeg + 1];      // first (virtual) chunk of every segment; the mask bits count virtual chunks
-    int seg_phys[kRowsMaxSeg];        // the staged chunk it starts at (== seg_vc unless aliased)
     int seg_key[kRowsMaxSeg];         // packed integer shift of the segment
     float segS[kRowsMaxSeg][3];       // its lattice vector s·cell
     unsigned char vc_seg[kRowsMaxVCAlias];  // virtual chunk -> segment
@@ -77,7 +76,11 @@ struct RowsSmem {
     alignas(128) unsigned char zeros[kRowsZeroBytes];                       // source of the TMA zero-fill stores
 };
 
-constexpr size_t rows_smem_bytes() { return (size_t)kRowsRingBytes + sizeof(RowsSmem); }
+// PAIR mode keeps the fp64 lattice vector of every shift segment of every tile in flight behind RowsSmem
+constexpr size_t kRowsPairS64Bytes = sizeof(double) * 3 * kRowsMaxSeg * kRowsDesc;
+constexpr size_t rows_smem_bytes(bool pair = false) {
+    return (size_t)kRowsRingBytes + sizeof(RowsSmem) + (pair ? kRowsPairS64Bytes : 0);
+}
 
 struct RowsArgs {
     unsigned char* ws;
@@ -89,6 +92,11 @@ struct RowsArgs {
     int* num_neighbors;
     int* prezero;             // optional: buffer the kernel zero-fills while it sweeps (the shifts output, sized by the caller's guess)
     long long prezero_ints;
+    // PAIR mode (nvnl_pair.cuh): the sweep feeds a pair consumer instead of writing rows
+    const double* q_sorted;   // charges in cell-sorted order
+    double* pair_energies;    // [n]
+    double* pair_forces;      // [n, 3]
+    double pair_cutoff, pair_alpha;
 };
 
 // the k_rows barriers are polled with a short sleep between tries: a spinning warp would otherwise take issue slots
@@ -225,7 +233,7 @@ __device__ __forceinline__ void rows_run_shift(uint32_t addr, int v0, int v1, co
 // Sweep of the four targets over (virtual) chunks [32 w, 32 w + 32) of the staged tile: m = their hit masks
 // (bit = chunk - 32 w).  One call per mask word, so that the masks stay in registers; words past 0 only exist for tiles
 // of more than 1024 slots.
-template <bool HALF, bool FMA>
+template <bool HALF, bool FMA, bool ALIAS>
 __device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile_addr, const RowsTargets& t, float rc2,
                                                 int lane, int w, unsigned (&m)[4]) {
     constexpr uint32_t RS = sizeof(Rec<float>);
@@ -243,7 +251,8 @@ __device__ __forceinline__ void rows_sweep_word(const RowsDesc& d, uint32_t tile
         v0 = v0 > wb ? v0 : wb;
         v1 = v1 < we ? v1 : we;
         if (v0 >= v1) continue;
-        const uint32_t addr = lane_addr + (uint32_t)(d.seg_phys[s] + (v0 - d.seg_vc[s])) * (32u * RS);
+        // (aliased tiles: the segment's records are the staged chunks 0 ..; else virtual chunk == staged chunk)
+        const uint32_t addr = lane_addr + (uint32_t)(ALIAS ? v0 - d.seg_vc[s] : v0) * (32u * RS);   // ALIAS: see rows_trip
         const int key = d.seg_key[s];
         if (key == 0) {
             rows_run_zero<HALF, FMA>(addr, v0, v1, t, rc2, m);
@@ -324,8 +333,8 @@ struct RowsAlloc {
 // W = mask words per lane and target (1: tiles of <= 32 chunks, 2: <= 64, kRowsHugeWords: aliased single-cell tiles);
 // s0 = tile slot of the trip's first target.
 template <int W>
-__device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d, Ctrl* ctrl, uint32_t tile_addr,
-                                           unsigned (&m)[W][4], int s0, int nt, int lane, RowsAlloc& al,
+__device__ __forceinline__ void rows_emit4(long long rows_cap, int* __restrict__ num_neighbors, const RowsDesc& d, Ctrl* ctrl,
+                                           uint32_t tile_addr, unsigned (&m)[W][4], int s0, int nt, int lane, RowsAlloc& al,
                                            int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
     int n[4];
@@ -365,7 +374,7 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
         unsigned long long b = 0ull;
         if (lane == 0) b = atomicAdd(&ctrl->rows_cursor, (unsigned long long)sz);
         b = __shfl_sync(0xffffffffu, b, 0);
-        if ((long long)b + sz > a.L.rows_cap) {
+        if ((long long)b + sz > rows_cap) {
             // temporary buffer exhausted: the host re-runs the query on the two-pass path (nvnl_status.rows_overflow)
             if (lane == 0) ctrl->rows_overflow = 1;
             al.pos = al.end = 0;
@@ -393,8 +402,8 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
                     if (k < nt) rows[start[k] + lane] = key;
             }
         }
-        if (W > 2 || d.aliased != 0) {
-            // (only aliased tiles have more than two mask words; aliased tiles always carry shifts)
+        if (W > 2) {
+            // (aliased tiles — and only they — take the path with more than two mask words; they always carry shifts)
 #pragma unroll
             for (int w = 0; w < W; ++w) rows_gather_word<true, true>(d, tile_addr, m[w], w, lane, p);
         } else if (shifted) {
@@ -416,16 +425,16 @@ __device__ __forceinline__ void rows_emit4(const RowsArgs& a, const RowsDesc& d,
         const int c = lane == 0 ? cnt[0] : (lane == 1 ? cnt[1] : (lane == 2 ? cnt[2] : cnt[3]));
         const int s = lane == 0 ? start[0] : (lane == 1 ? start[1] : (lane == 2 ? start[2] : start[3]));
         if (ok) row_ref[i] = (s << 2) | (hdr == 0 ? 0 : (hdr == 8 ? 1 : 2));
-        a.num_neighbors[i] = c;
+        num_neighbors[i] = c;
     }
 }
 
 // One trip of a consumer warp: four targets (tile slots s0 .. s0 + nt - 1) against the staged tile, then their rows.
 // Four targets share every candidate load; two packed pairs share every FP instruction.
 template <bool HALF, bool FMA, int W>
-__device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds, Ctrl* ctrl, uint32_t tile_addr, int s0,
-                                          int nt, float rc2, int lane, RowsAlloc& al, int* __restrict__ rows,
-                                          int* __restrict__ row_ref) {
+__device__ __forceinline__ void rows_trip(long long rows_cap, int* __restrict__ num_neighbors, const RowsDesc& ds, Ctrl* ctrl,
+                                          uint32_t tile_addr, int s0, int nt, float rc2, int lane, RowsAlloc& al,
+                                          int* __restrict__ rows, int* __restrict__ row_ref) {
     constexpr uint32_t RS = sizeof(Rec<float>);
     RowsTargets tg;
     {
@@ -444,7 +453,7 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
     for (int w = 0; w < W; ++w) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) m[w][k] = 0u;
-        if (w == 0 || (w << 5) < ds.nvc) rows_sweep_word<HALF, FMA>(ds, tile_addr, tg, rc2, lane, w, m[w]);
+        if (w == 0 || (w << 5) < ds.nvc) rows_sweep_word<HALF, FMA, (W > 2)>(ds, tile_addr, tg, rc2, lane, w, m[w]);
     }
     if (!HALF) {
         // (i, i, 0) is not a pair: the targets sit in the zero-shift home segment, whose virtual chunks are its staged
@@ -452,15 +461,50 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int sl = s0 + (k < nt ? k : nt - 1);
-            if (lane == (sl & 31)) {
-                const unsigned bit = 1u << ((sl >> 5) & 31);
+            // (branch-free on purpose: a conditional on the word index makes the compiler index m[][] dynamically,
+            //  which moves the masks to local memory)
+            const unsigned bit = lane == (sl & 31) ? 1u << ((sl >> 5) & 31) : 0u;
 #pragma unroll
-                for (int w = 0; w < W; ++w)
-                    if (W == 1 || (sl >> 10) == w) m[w][k] &= ~bit;
-            }
+            for (int w = 0; w < W; ++w) m[w][k] &= ~(W == 1 ? bit : (bit & (0u - (unsigned)((sl >> 10) == w))));
         }
     }
-    rows_emit4<W>(a, ds, ctrl, tile_addr, m, s0, nt, lane, al, rows, row_ref);
+    rows_emit4<W>(rows_cap, num_neighbors, ds, ctrl, tile_addr, m, s0, nt, lane, al, rows, row_ref);
+}
+
+}  // namespace nvnl
+#include "nvnl_pair.cuh"
+namespace nvnl {
+
+// One trip in PAIR mode: the same masks, then the pair consumer instead of the rows.
+template <bool FMA, int W>
+__device__ __forceinline__ void pair_trip(const RowsArgs& a, const RowsDesc& ds, const double (*S64)[3], uint32_t tile_addr,
+                                          int s0, int nt, float rc2, int lane) {
+    constexpr uint32_t RS = sizeof(Rec<float>);
+    RowsTargets tg;
+    {
+        float x[4], y[4], z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            lds_rec(tile_addr + (uint32_t)(s0 + (k < nt ? k : nt - 1)) * RS, x[k], y[k], z[k], tg.i[k]);
+        const f32x2_t nz = pack2(-0.0f, -0.0f);
+        tg.X01 = add2(pack2(x[0], x[1]), nz); tg.Y01 = add2(pack2(y[0], y[1]), nz); tg.Z01 = add2(pack2(z[0], z[1]), nz);
+        tg.X23 = add2(pack2(x[2], x[3]), nz); tg.Y23 = add2(pack2(y[2], y[3]), nz); tg.Z23 = add2(pack2(z[2], z[3]), nz);
+    }
+    unsigned m[W][4];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[w][k] = 0u;
+        if (w == 0 || (w << 5) < ds.nvc) rows_sweep_word<false, FMA, false>(ds, tile_addr, tg, rc2, lane, w, m[w]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int sl = s0 + (k < nt ? k : nt - 1);
+        const unsigned bit = lane == (sl & 31) ? 1u << ((sl >> 5) & 31) : 0u;
+#pragma unroll
+        for (int w = 0; w < W; ++w) m[w][k] &= ~(W == 1 ? bit : (bit & (0u - (unsigned)((sl >> 10) == w))));
+    }
+    pair_consume4<W>(a, ds, S64, tile_addr, tile_addr + (uint32_t)ds.nvc * (32u * RS), m, s0, nt, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,19 +514,26 @@ __device__ __forceinline__ void rows_trip(const RowsArgs& a, const RowsDesc& ds,
 // copy) into the byte ring.  Warps 0..kRowsCons-1 (consumers): claim four targets of the current tile at a time,
 // sweep, emit rows.  No CTA-wide barrier in the steady state.
 // ------------------------------------------------------------------------------------------------
-template <bool HALF, bool FMA>
-__global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const RowsArgs a) {
+// HUGE = the second launch: parts of single-cell systems whose images need more than kRowsMaxVC chunks (aliased tiles,
+// six mask words per lane and target — a register budget the common kernel should not pay for), popped from the huge
+// list the first launch filled.
+// PAIR = the sweep feeds the pair consumer of nvnl_pair.cuh (charges staged next to the records, fp64 shift vectors per
+// segment, no rows): cells it cannot take are reported like deferred cells and the host falls back to list + consumer.
+template <bool HALF, bool FMA, bool HUGE, bool PAIR = false>
+__global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinBlocks)) k_rows(const RowsArgs a) {
     pdl_enter();
     using T = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RowsSmem& sm = *reinterpret_cast<RowsSmem*>(smem_raw + (size_t)kRowsRingBytes);
+    double (*const segS64)[kRowsMaxSeg][3] =
+        reinterpret_cast<double (*)[kRowsMaxSeg][3]>(smem_raw + (size_t)kRowsRingBytes + sizeof(RowsSmem));   // PAIR only
     const uint32_t ring_addr = smem_u32(smem_raw);
     constexpr uint32_t RS = sizeof(Rec<T>);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(a.ws + a.L.ctrl);
 
-    {
+    if (!HUGE) {
         // re-arm the look-back scan that turns the counts into neighbor_ptr (runs after the count kernels)
         unsigned long long* st1 = reinterpret_cast<unsigned long long*>(a.ws + a.L.scan_status1);
         const long long nst = (a.n + 1) / kScanTile + 2;
@@ -504,14 +555,13 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
     // large shared-memory carve-out, otherwise the two serialise — profiles/r2_zero_overlap.txt.)
     // Workloads whose rows mostly carry shifts (small periodic boxes; Ctrl::shift_heavy, set by k_grid) are not
     // pre-zeroed: the output kernel writes their shifts densely, zeros included, in one pass.
-    unsigned char* const zbase = reinterpret_cast<unsigned char*>(a.prezero);
-    long long zpos = 0, zend = 0, zquota = 0;    // bytes
-    if (a.prezero && ctrl->shift_heavy == 0) {
+    int zpos = 0, zend = 0, zquota = 0;    // in 16-byte units (the buffer holds fewer than 2^31 of them)
+    if (!HUGE && a.prezero && ctrl->shift_heavy == 0) {
         const long long n16 = a.prezero_ints >> 2;
         const long long slice = (n16 + gridDim.x - 1) / gridDim.x;
         long long lo = (long long)blockIdx.x * slice, hi = lo + slice < n16 ? lo + slice : n16;
         if (lo > hi) lo = hi;
-        zpos = lo * 16; zend = hi * 16;
+        zpos = (int)lo; zend = (int)hi;
         if (blockIdx.x == 0 && tid < (int)(a.prezero_ints & 3)) a.prezero[(n16 << 2) + tid] = 0;
     }
     for (int k = tid; k < kRowsZeroBytes / 16; k += kRowsThreads) reinterpret_cast<int4*>(sm.zeros)[k] = make_int4(0, 0, 0, 0);
@@ -534,29 +584,31 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
         int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
         const int total_cells = active ? ctrl->total_cells : 0;
         // zero-fill quota per published tile: the slice spread over the tiles this CTA is expected to produce
-        zquota = ((zend - zpos) / (total_cells / (int)gridDim.x + 1) + kRowsZeroBytes) / kRowsZeroBytes * kRowsZeroBytes;
+        zquota = ((zend - zpos) / (total_cells / (int)gridDim.x + 1) + kRowsZeroBytes / 16) / (kRowsZeroBytes / 16) * (kRowsZeroBytes / 16);
         // descriptor ring + byte ring (FIFO): tiles [oldest, nprod) are live
         int nprod = 0, oldest = 0;
         int head = 0, used = 0;
         int g_next = 0;
-        if (lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);
+        if (!HUGE && lane == 0) g_next = atomicAdd(&ctrl->work_counter[0], 1);   // (the second launch pops the huge list only)
         // cells with many targets (small systems that are one or a few cells) are not swept by one CTA: whoever meets
         // such a cell pushes it to the split list as parts of kRowsSplitPart targets; once the cell queue is drained
         // every CTA pops parts until all cells have been classified and the list is empty
-        int2* split = reinterpret_cast<int2*>(a.ws + a.L.split);
-        const int split_cap = (int)(a.n / 16 + 2);
+#define NVNL_SPLIT_PTR reinterpret_cast<int2*>(a.ws + a.L.split)
+#define NVNL_SPLIT_CAP ((int)(a.n / 16 + 2))
         bool phase2 = false;
         int my_cells = 0;
         // grid of the current system (reloaded only when the system changes)
         int s_cur = -1, cpd0 = 1, cpd1 = 1, cpd2 = 1, R0 = 0, R1 = 0, R2 = 0, pb0 = 0, pb1 = 0, pb2 = 0, coff = 0, c01 = 1;
+        bool one_cell = false;
         float rcp0 = 1.f, rcp01 = 1.f;   // reciprocals for the cell-coordinate division (corrected exactly below)
         bool r111 = false;
-        auto zero_some = [&](long long quota) {   // lane 0: TMA bulk stores of zeros, up to `quota` bytes of the slice
-            long long e = zpos + quota;
-            e = e < zend ? e : zend;
+        auto zero_some = [&](int quota) {   // lane 0: TMA bulk stores of zeros, up to `quota` bytes of the slice
+            int e = zpos + quota;
+            e = (e < zend && e >= zpos) ? e : zend;
+            unsigned char* const zbase = reinterpret_cast<unsigned char*>(a.prezero);
             while (zpos < e) {
-                const long long nb = e - zpos < kRowsZeroBytes ? e - zpos : kRowsZeroBytes;
-                tma_store_1d(zbase + zpos, sm.zeros, (uint32_t)nb);
+                const int nb = e - zpos < kRowsZeroBytes / 16 ? e - zpos : kRowsZeroBytes / 16;
+                tma_store_1d(zbase + (size_t)zpos * 16, sm.zeros, (uint32_t)nb * 16u);
                 zpos += nb;
             }
             tma_store_commit();
@@ -566,14 +618,22 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             //         sort, aligned layout) BEFORE waiting for ring space ----
             bool have = false;
             int g = 0, ntarget = 0, st = 0, cn = 0, key = kKeyEmpty, aoff = 0, total = 0, nseg = 1, nvc = 0;
-            int home_slot = 0, si = 0, seg_len = 0, seg_vcb = 0, seg_nch = 0, grp_cn = 0, seg_ph = 0;
+            int home_slot = 0, si = 0, seg_len = 0, seg_vcb = 0, seg_nch = 0, grp_cn = 0;
             int tgt0 = 0, tgt1 = 0;          // the targets of the cell this work item covers
             unsigned shiftmask = 0u, hm = 1u;
             bool head_lane = false, alias = false;
             T Sx = (T)0, Sy = (T)0, Sz = (T)0;
+            double S64x = 0.0, S64y = 0.0, S64z = 0.0;   // PAIR: the segment's lattice vector in fp64
             for (;;) {
                 bool part = false;           // the item is a part of a cell, popped from the split list
-                if (!phase2) {
+                if (HUGE) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&ctrl->huge_next, 1);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    if (t >= ctrl->n_huge) break;                     // (the list is final: the first launch has completed)
+                    const int2 it = reinterpret_cast<const int2*>(a.ws + a.L.huge)[t];
+                    g = it.x; tgt0 = it.y; part = true;
+                } else if (!phase2) {
                     g = __shfl_sync(0xffffffffu, g_next, 0);
                     if (g >= total_cells) {
                         // cell queue drained: publish how many cells this CTA has classified, then serve the split list
@@ -593,8 +653,8 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                         volatile int* vdone = &ctrl->cells_done;
                         volatile int* vres = &ctrl->split_reserved;
                         for (;;) {
-                            if (t >= split_cap) break;
-                            const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&split[t]);
+                            if (t >= NVNL_SPLIT_CAP) break;
+                            const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&NVNL_SPLIT_PTR[t]);
                             ix = (int)(unsigned)w; iy = (int)(w >> 32);
                             if (ix != 0) break;                       // the part has been pushed
                             if (*vdone >= total_cells) {              // every cell classified: the list is final
@@ -628,6 +688,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     rcp0 = 1.0f / (float)cpd0;
                     rcp01 = 1.0f / (float)c01;
                     r111 = R0 == 1 && R1 == 1 && R2 == 1;   // the common 3 x 3 x 3 stencil
+                    one_cell = c01 * cpd2 == 1;
                 }
                 // cell coordinates: float-reciprocal quotient, corrected to the exact one
                 int cx, cy, cz;
@@ -663,14 +724,16 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     if (lane == 0) base = atomicAdd(&ctrl->split_reserved, nparts);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     for (int k = lane; k < nparts; k += 32)
-                        if (base + k < split_cap)
-                            *reinterpret_cast<volatile unsigned long long*>(&split[base + k]) =
+                        if (base + k < NVNL_SPLIT_CAP)
+                            *reinterpret_cast<volatile unsigned long long*>(&NVNL_SPLIT_PTR[base + k]) =
                                 (unsigned long long)(unsigned)(g + 1) | ((unsigned long long)(unsigned)(k * kRowsSplitPart) << 32);
                     __threadfence();     // (every lane's entries are visible before this CTA reports its cells as classified)
                     __syncwarp();
                     return true;
                 };
                 alias = false;
+                bool ok_item = false;
+                do {     // (a `continue` in this block leaves it with ok_item == false)
                 if (r111 && cx >= 1 && cx <= cpd0 - 2 && cy >= 1 && cy <= cpd1 - 2 && cz >= 1 && cz <= cpd2 - 2) {
                     // ---- interior cell (no wrap, every stencil cell in range): the stencil is nine runs of three
                     //      x-adjacent cells, contiguous in the sorted array — nine lanes, two loads each, nine copies
@@ -684,14 +747,11 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     aoff = incl - cn;
                     total = __shfl_sync(0xffffffffu, incl, 31);
                     nvc = ((total + 63) >> 6) << 1;    // chunk count padded to an even number (two chunks per trip)
-                    if (nvc > kRowsMaxVC) { defer_cell(); continue; }
+                    if (nvc > kRowsMaxVC || (PAIR && nvc * 32 * (int)(RS + 8) > kRowsRingBytes)) { defer_cell(); continue; }
                     seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0; nseg = 1; hm = 1u; head_lane = lane == 0;
-                    shiftmask = 0u; key = 0; grp_cn = cn; seg_ph = 0;
+                    shiftmask = 0u; key = 0; grp_cn = cn;
                     home_slot = __shfl_sync(0xffffffffu, aoff, 4) + (home_start - __shfl_sync(0xffffffffu, st, 4));
-                    if (split_cell()) continue;
-                    if (!part) tgt0 = 0;
-                    tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
-                    have = true;
+                    ok_item = true;
                     break;
                 }
                 const int nx = 2 * R0 + 1, ny = 2 * R1 + 1, nzz = 2 * R2 + 1;
@@ -748,7 +808,14 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 head_lane = lane == 0;
                 // a system that is ONE cell: every image is the same run of records -> stage it once and let the image
                 // segments alias it (virtual chunks = image * chunks-per-image; up to kRowsMaxVCAlias of them)
-                alias = ok && shiftmask != 0u && sp.ncells == 1;
+                // (only when the images do not fit kRowsMaxVC chunks staged one by one; smaller tiles take the regular path)
+                alias = ok && shiftmask != 0u && one_cell;
+                if (alias) {
+                    const unsigned nonempty0 = __ballot_sync(0xffffffffu, cn > 0);
+                    const int c0 = __shfl_sync(0xffffffffu, cn, 0);
+                    if (__popc(nonempty0) * ((c0 + 31) >> 5) <= kRowsMaxVC) alias = false;
+                }
+                if (PAIR && alias) { defer_cell(); continue; }   // (the pair consumer leaves these to the host's fallback)
                 if (alias) {
                     const unsigned nonempty = __ballot_sync(0xffffffffu, cn > 0);
                     const int cn1 = __shfl_sync(0xffffffffu, cn, 0), st1 = __shfl_sync(0xffffffffu, st, 0);   // (zero shift first)
@@ -760,7 +827,6 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     seg_len = cn > 0 ? cn1 : 0;
                     seg_nch = cn > 0 ? nch : 0;
                     seg_vcb = si * nch;
-                    seg_ph = 0;
                     nvc = nseg * nch;
                     total = cn1;                       // records staged
                     aoff = 0;
@@ -776,17 +842,27 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                         shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
                     }
                     if (nvc > kRowsMaxVCAlias || nch * 32 * (int)RS > kRowsRingBytes) { defer_cell(); continue; }
-                    if (split_cell()) continue;
-                    if (!part) tgt0 = 0;
-                    tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
-                    have = true;
+                    if (!HUGE && nvc > kRowsMaxVC) {
+                        // more than two mask words: the cell goes to the second launch, as parts of kRowsSplitPart targets
+                        const int nparts = (ntarget + kRowsSplitPart - 1) / kRowsSplitPart;
+                        int base = 0;
+                        if (lane == 0) {
+                            base = atomicAdd(&ctrl->n_huge, nparts);
+                            ctrl->had_huge = 1;
+                        }
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        int2* huge = reinterpret_cast<int2*>(a.ws + a.L.huge);
+                        for (int k = lane; k < nparts; k += 32) huge[base + k] = make_int2(g, k * kRowsSplitPart);
+                        continue;
+                    }
+                    ok_item = true;
                     break;
                 }
                 if (!shiftmask) {
                     // interior cell: one zero-shift segment, chunk count padded to an even number (two chunks per trip)
                     aoff = off;
                     nvc = ((total + 63) >> 6) << 1;
-                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0; seg_ph = 0;
+                    seg_len = total; seg_vcb = 0; seg_nch = nvc; si = 0;
                 } else {
                     // segments = runs of equal shift among the non-empty images; each starts on a 32-slot boundary
                     const int pk = __shfl_up_sync(0xffffffffu, key, 1);
@@ -803,7 +879,6 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     seg_nch = (seg_len + 31) >> 5;
                     const int vincl = warp_incl_scan(seg_nch, lane);
                     seg_vcb = vincl - seg_nch;
-                    seg_ph = seg_vcb;
                     nvc = __shfl_sync(0xffffffffu, vincl, 31);
                     si = __popc(hm & le) - 1;
                     const int seg_off = __shfl_sync(0xffffffffu, off, hl);
@@ -816,9 +891,14 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
 #pragma unroll
                         for (int k = 0; k < 9; ++k) cm[k] = (T)sp.cellm[k];
                         shift_vector<T, FMA>(cm, csx, csy, csz, Sx, Sy, Sz);
+                        if (PAIR) {
+                            S64x = (double)csx * sp.cellm[0] + (double)csy * sp.cellm[3] + (double)csz * sp.cellm[6];
+                            S64y = (double)csx * sp.cellm[1] + (double)csy * sp.cellm[4] + (double)csz * sp.cellm[7];
+                            S64z = (double)csx * sp.cellm[2] + (double)csy * sp.cellm[5] + (double)csz * sp.cellm[8];
+                        }
                     }
                 }
-                ok = ok && nvc <= kRowsMaxVC && nseg <= kRowsMaxSeg;
+                ok = ok && nvc <= kRowsMaxVC && nseg <= kRowsMaxSeg && !(PAIR && nvc * 32 * (int)(RS + 8) > kRowsRingBytes);
                 if (!ok) { defer_cell(); continue; }
                 const unsigned tagm = __ballot_sync(0xffffffffu, tag != 0);
                 const int home_lane = __ffs(tagm) - 1;
@@ -836,7 +916,10 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                     const int incl_last = __shfl_sync(0xffffffffu, incl, last);
                     grp_cn = cont ? 0 : incl_last - off;
                 }
-                if (split_cell()) continue;
+                ok_item = true;
+                } while (0);
+                if (!ok_item) continue;      // empty, deferred: next work item
+                if (split_cell()) continue;  // pushed as parts
                 if (!part) tgt0 = 0;
                 tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
                 have = true;
@@ -845,7 +928,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             // ---- 2. descriptor slot + ring space (FIFO release), then publish the tables
             //         and issue the copies ----
             const int dslot = nprod % kRowsDesc;
-            const int bytes = have ? (alias ? ((total + 31) >> 5) : nvc) * 32 * (int)RS : 0;
+            const int bytes = have ? (alias ? ((total + 31) >> 5) : nvc) * 32 * (int)(PAIR ? RS + 8 : RS) : 0;   // PAIR: + charges
             int foot, data_off;
             for (;;) {
                 foot = bytes; data_off = head;
@@ -873,9 +956,22 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             const uint32_t tile_addr = ring_addr + (uint32_t)data_off;
             if (head_lane) {
                 ds.seg_vc[si] = seg_vcb;
-                ds.seg_phys[si] = seg_ph;
                 ds.seg_key[si] = shiftmask ? key : 0;
                 ds.segS[si][0] = Sx; ds.segS[si][1] = Sy; ds.segS[si][2] = Sz;
+                if (PAIR) { segS64[dslot][si][0] = S64x; segS64[dslot][si][1] = S64y; segS64[dslot][si][2] = S64z; }
+            }
+            if (PAIR) {
+                // the charges of the staged records, image by image (copied by the lanes: runs of 8-byte values are not
+                // 16-byte aligned, so they cannot ride the bulk copies)
+                const uint32_t q_addr = tile_addr + (uint32_t)nvc * (32u * RS);
+                unsigned live = __ballot_sync(0xffffffffu, cn > 0);
+                while (live) {
+                    const int l = __ffs((int)live) - 1;
+                    live &= live - 1u;
+                    const int s_ = __shfl_sync(0xffffffffu, st, l), c_ = __shfl_sync(0xffffffffu, cn, l);
+                    const int a_ = __shfl_sync(0xffffffffu, aoff, l);
+                    for (int t = lane; t < c_; t += 32) sts_f64(q_addr + (uint32_t)(a_ + t) * 8u, a.q_sorted[s_ + t]);
+                }
             }
             if (lane == 0) {
                 ds.seg_vc[nseg] = nvc;
@@ -925,7 +1021,15 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
         if (lane == 0 && zpos < zend) zero_some(zend - zpos);
         if (lane == 0 && zend > 0) tma_store_wait_all();
         // the last CTA to drain the queue re-arms it for the next launch on this workspace
-        {
+        if (HUGE) {
+            if (lane == 0) {
+                __threadfence();
+                if (atomicAdd(&ctrl->huge_done, 1) == (int)gridDim.x - 1) {
+                    ctrl->huge_next = 0;
+                    ctrl->huge_done = 0;
+                }
+            }
+        } else {
             int dn = 0;
             if (lane == 0) {
                 __threadfence();
@@ -935,7 +1039,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             if (dn == (int)gridDim.x - 1) {
                 // (every other CTA has left its pop loop: the split list can be cleared for the next query)
                 const int used_parts = *reinterpret_cast<volatile int*>(&ctrl->split_reserved);
-                for (int k = lane; k < used_parts && k < split_cap; k += 32) split[k] = make_int2(0, 0);
+                for (int k = lane; k < used_parts && k < NVNL_SPLIT_CAP; k += 32) NVNL_SPLIT_PTR[k] = make_int2(0, 0);
                 __syncwarp();
                 if (lane == 0) {
                     ctrl->work_counter[0] = 0;
@@ -946,6 +1050,8 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
                 }
             }
         }
+#undef NVNL_SPLIT_PTR
+#undef NVNL_SPLIT_CAP
     } else {
         // =========================== consumers ===========================
         int* rows = reinterpret_cast<int*>(a.ws + a.L.rows);
@@ -953,6 +1059,7 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
         RowsAlloc al;
         al.pos = al.end = 0;
         const float rc2 = a.cutoff_sq;
+        const long long rows_cap = a.L.rows_cap;
         for (int ncons = 0;; ++ncons) {
             const int dslot = ncons % kRowsDesc;
             mbar_wait_backoff(reinterpret_cast<uint64_t*>(&sm.full[dslot]), (uint32_t)((ncons / kRowsDesc) & 1));
@@ -960,20 +1067,25 @@ __global__ void __launch_bounds__(kRowsThreads, kRowsMinBlocks) k_rows(const Row
             if (ds.item < 0) break;
             const uint32_t tile_addr = ring_addr + (uint32_t)ds.data_off;
             const int ntarget = ds.ntarget, home_slot = ds.home_slot;
-            const int words = ds.nvc <= 32 ? 1 : (ds.nvc <= 64 ? 2 : kRowsHugeWords);   // mask words per lane and target
+            const int words = ds.nvc <= 32 ? 1 : 2;   // mask words per lane and target (first launch)
             for (;;) {
                 int t0 = 0;
                 if (lane == 0) t0 = atomicAdd(&ds.next_target, 4);
                 t0 = __shfl_sync(0xffffffffu, t0, 0);
                 if (t0 >= ntarget) break;
                 const int nt = ntarget - t0 < 4 ? ntarget - t0 : 4;
-                if (words == 1)
-                    rows_trip<HALF, FMA, 1>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
-                else if (words == 2)
-                    rows_trip<HALF, FMA, 2>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows, row_ref);
+                if (PAIR) {
+                    if (words == 1) pair_trip<FMA, 1>(a, ds, segS64[dslot], tile_addr, home_slot + t0, nt, rc2, lane);
+                    else pair_trip<FMA, 2>(a, ds, segS64[dslot], tile_addr, home_slot + t0, nt, rc2, lane);
+                } else if (HUGE)
+                    rows_trip<HALF, FMA, kRowsHugeWords>(rows_cap, a.num_neighbors, ds, ctrl, tile_addr, home_slot + t0, nt, rc2,
+                                                         lane, al, rows, row_ref);
+                else if (words == 1)
+                    rows_trip<HALF, FMA, 1>(rows_cap, a.num_neighbors, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al,
+                                            rows, row_ref);
                 else
-                    rows_trip<HALF, FMA, kRowsHugeWords>(a, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al, rows,
-                                                         row_ref);
+                    rows_trip<HALF, FMA, 2>(rows_cap, a.num_neighbors, ds, ctrl, tile_addr, home_slot + t0, nt, rc2, lane, al,
+                                            rows, row_ref);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(&sm.empty[dslot]));
@@ -1182,6 +1294,9 @@ __global__ void k_query_reset(unsigned char* __restrict__ ws, WsLayout L, long l
         ctrl->rows_overflow = 0;
         ctrl->split_next = 0;
         ctrl->cells_done = 0;
+        ctrl->n_huge = 0;
+        ctrl->huge_next = 0;
+        ctrl->huge_done = 0;
         // (split_reserved counts entries the last sweep may not have cleared if it was aborted; k_rows clears and resets it)
     }
     (void)n; (void)with_rows;

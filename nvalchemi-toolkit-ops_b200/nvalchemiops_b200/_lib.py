@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libnvalchemi_nl_b200.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 c_void_p, c_int, c_int32, c_int64, c_double, c_size_t = (
@@ -51,6 +51,10 @@ _SIGNATURES = {
                                          c_void_p, c_void_p]),
     "nvnl_moved_beyond": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_double, c_void_p, c_void_p]),
     "nvnl_get_grid": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "nvnl_coulomb_fused": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_double, c_int, c_void_p, c_double, c_double,
+                                   c_void_p, c_void_p, c_void_p]),
+    "nvnl_coulomb_list": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_double, c_double, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "nvnl_pack_shifts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_gathered": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -186,8 +186,8 @@ def _raise_on_error_bits(bits: int):
 
 def status(h: CellListHandle):
     """(total_pairs, max_count, total_cells, error_bits, launch_hint) — synchronizes the stream.
-    launch_hint (bit 0: atoms outside the primary image, bit 1: cells left to the general kernel) lets the fill
-    stage launch only the kernels that have work."""
+    launch_hint (bit 0: atoms outside the primary image, bit 1: cells left to the general kernel, bit 5: single-cell
+    systems that take the second single-sweep launch) lets the next stage launch only the kernels that have work."""
     L = _lib.lib()
     tp, mc, tc, eb, uw, hd, ro = (ctypes.c_int64(0), ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0),
                                   ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0))
@@ -199,7 +199,8 @@ def status(h: CellListHandle):
         )
     h.rows_overflow = bool(ro.value)
     h.wide_stencil = bool(uw.value & 2)
-    return tp.value, mc.value, tc.value, eb.value, (1 if (uw.value & 1) else 0) | (2 if hd.value else 0)
+    return (tp.value, mc.value, tc.value, eb.value,
+            (1 if (uw.value & 1) else 0) | (2 if (hd.value & 1) else 0) | (32 if (hd.value & 2) else 0))
 
 
 def query_matrix(h: CellListHandle, cutoff_sq, neighbor_matrix, neighbor_matrix_shifts, num_neighbors, fill_value,
@@ -340,7 +341,7 @@ def query_coo(h: CellListHandle, cutoff_sq, half_fill=False, max_neighbors=None)
         raise NeighborOverflowError(max_neighbors, max_count)
     if total > 2**31 - 1:
         raise OverflowError(f"{total} pairs do not fit int32 neighbor_ptr/neighbor_list indices")
-    _pair_history.put(key, total, hint & 3)
+    _pair_history.put(key, total, hint & 35)
     fits = (rows and zbuf is not None and 3 * total <= zbuf.numel() and 2 * 3 * total >= zbuf.numel()
             and not (hint & 1) and not (hint & 16))
     hint &= 15
@@ -390,7 +391,7 @@ def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, 
     if rows and prezero is not None and spec_edge is not None:
         fill_rows_speculative(h, ptr, spec_edge, prezero)      # runs while the host waits for the size
     total, max_count, _cells, err, hint = status(h)
-    if rows and launch_hint >= 0 and (hint & ~launch_hint & 3):
+    if rows and launch_hint >= 0 and (hint & ~launch_hint & 35):
         # a variant that was not launched had work: repeat the count with every variant (the speculative outputs, if any,
         # are discarded by the caller because the totals cannot have been right)
         num, ptr = count(h, cutoff_sq, half_fill, rows=True, prezero=None, launch_hint=-1)
