@@ -570,6 +570,34 @@ def main():
         sharded = {"workload": "config 5: 4096 systems x 1000 atoms, periodic, COO, sharded by batch_ptr (strong scaling)", **res}
         del bp, bc, bb, bptr
 
+    # ---- the sweep fused with a pair consumer (N = 1): config-4 box, real-space Ewald, list never written ----
+    fused = None
+    if world == 1 and not args.no_other_configs and args.config == 4:
+        from nvalchemiops_b200.interactions.electrostatics import coulomb_energy_forces, fused_coulomb_energy_forces
+
+        p4, c4, b4 = [x.to(dev) for x in bench_box(args.atoms, seed=4)]
+        q4 = ((torch.rand(args.atoms, generator=torch.Generator().manual_seed(1), dtype=torch.float64) - 0.5) * 2).to(dev)
+
+        def list_pipeline(alpha):
+            nl_, ptr_, sh_ = neighbor_list(p4, CUTOFF, cell=c4, pbc=b4, return_neighbor_list=True)
+            return coulomb_energy_forces(p4, q4, c4, CUTOFF, alpha, neighbor_list=nl_, neighbor_ptr=ptr_, neighbor_shifts=sh_)
+
+        fused = {"workload": f"config-4 box ({args.atoms} atoms) + real-space Coulomb/Ewald energies and forces in fp64 "
+                             "(reference coulomb.py:1540): fused = build + ONE sweep+consumer kernel, list = neighbor_list + consumer"}
+        for alpha in (0.0, 0.3):
+            for _ in range(2):
+                of = fused_coulomb_energy_forces(p4, q4, c4, b4, CUTOFF, alpha, return_path=True)
+                ol = list_pipeline(alpha)
+            ms_f, _ = time_api(lambda: fused_coulomb_energy_forces(p4, q4, c4, b4, CUTOFF, alpha), 8, flush)
+            ms_l, _ = time_api(lambda: list_pipeline(alpha), 8, flush)
+            fused[f"alpha_{alpha}"] = {
+                "fused_ms": ms_f, "list_pipeline_ms": ms_l, "path": of[2], "pairs_per_s_fused": P / (ms_f * 1e-3),
+                "max_rel_diff_energy": float((of[0] - ol[0]).abs().max() / ol[0].abs().max()),
+                "max_rel_diff_forces": float((of[1] - ol[1]).abs().max() / ol[1].abs().max())}
+            del of, ol
+        del p4, c4, b4, q4
+        torch.cuda.empty_cache()
+
     # ---- cpu_baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -598,6 +626,8 @@ def main():
             line["other_configs"] = others
         if sharded is not None:
             line["sharded_batch"] = sharded
+        if fused is not None:
+            line["fused_consumer"] = fused
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -22,35 +22,39 @@ namespace nvnl {
 
 constexpr double kTwoOverSqrtPi = 1.1283791670955126;   // coulomb.py:266
 
-// The reference's erfc (nvalchemiops/math/math.py:52-93, wp_erfc): the Abramowitz & Stegun 7.1.26 polynomial
-// (|error| <= 1.5e-7), evaluated here in fp64 with the reference's operation order — NOT the exact erfc, on purpose:
-// the consumer has to reproduce the reference's numbers.
-__device__ __forceinline__ double ref_erfc(double x) {
-    const double ax = fabs(x);
-    const double t = 1.0 / (1.0 + 0.3275911 * ax);
-    const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
-    const double poly = 0.254829592 * t + -0.284496736 * t2 + 1.421413741 * t3 + -1.453152027 * t4 + 1.061405429 * t5;
-    const double v = poly * exp(-ax * ax);
-    return x >= 0.0 ? v : 2.0 - v;
-}
-
-// one directed entry (i, j, s): d = r_i - r_j - s·cell.  Adds the entry's energy to e and its force on i to (fx, fy, fz).
+// One directed entry (i, j, s): d = r_i - r_j - s·cell.  Adds the entry's energy to e and its force on i to (fx, fy, fz).
+// The reference's formulas (coulomb.py:247-276) with its erfc (nvalchemiops/math/math.py:52-93, wp_erfc: the Abramowitz &
+// Stegun 7.1.26 polynomial, |error| <= 1.5e-7 — NOT the exact erfc, on purpose: the consumer has to reproduce the
+// reference's numbers), arranged for fp64 throughput: ONE reciprocal square root, ONE division and ONE exp per entry
+// (exp(-(alpha r)^2) serves the polynomial and the force term; 1/r and t = 1/(1 + p alpha r) share the division).  The
+// skip test `r >= cutoff` is decided on r^2 away from the knife edge and with the correctly rounded sqrt within 1e-12 of
+// it, so it is the reference's decision bit for bit.
 __device__ __forceinline__ void pair_coulomb(double qiqj, double dx, double dy, double dz, double cutoff, double alpha,
                                              double& e, double& fx, double& fy, double& fz) {
     const double r2 = dx * dx + dy * dy + dz * dz;
-    const double r = sqrt(r2);
-    if (r >= cutoff || r < 1e-10) return;
+    const double c2 = cutoff * cutoff;
+    if (r2 > c2 * (1.0 + 1e-12) || r2 < 1e-20 * (1.0 - 1e-12)) return;
+    if (r2 > c2 * (1.0 - 1e-12) || r2 < 1e-20 * (1.0 + 1e-12)) {
+        const double r_exact = sqrt(r2);
+        if (r_exact >= cutoff || r_exact < 1e-10) return;
+    }
     const double pre = 0.5 * qiqj;
+    double inv_r = rsqrt(r2);
+    inv_r = inv_r * (1.5 - 0.5 * r2 * inv_r * inv_r);        // one Newton step: full fp64 accuracy
+    const double r = r2 * inv_r;
     double fm;
     if (alpha > 0.0) {
         const double ar = alpha * r;
-        const double erfc_t = ref_erfc(ar);
+        const double u = 1.0 + 0.3275911 * ar;
+        const double t = 1.0 / u;
+        const double poly = t * (0.254829592 + t * (-0.284496736 + t * (1.421413741 + t * (-1.453152027 + t * 1.061405429))));
         const double exp_t = exp(-(ar * ar));
-        e += pre * erfc_t / r;
-        fm = pre * (erfc_t / (r * r * r) + kTwoOverSqrtPi * alpha * exp_t / (r * r));
+        const double erfc_t = poly * exp_t;                  // (ar >= 0: the reference's x >= 0 branch)
+        e += pre * erfc_t * inv_r;
+        fm = pre * inv_r * inv_r * (erfc_t * inv_r + kTwoOverSqrtPi * alpha * exp_t);
     } else {
-        e += pre / r;
-        fm = pre / (r * r * r);
+        e += pre * inv_r;
+        fm = pre * inv_r * inv_r * inv_r;
     }
     fx += fm * dx;
     fy += fm * dy;

@@ -27,7 +27,7 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _prep(positions, charges, cell, batch_idx):
+def _prep(positions, charges, cell, batch_idx, need_batch=True):
     _engine._require_cuda(positions, "positions")
     code = _engine._dtype_code(positions.dtype)
     dev = positions.device
@@ -39,7 +39,7 @@ def _prep(positions, charges, cell, batch_idx):
     cell = cell.to(device=dev, dtype=positions.dtype).reshape(-1, 3, 3).contiguous()
     if batch_idx is not None:
         batch_idx = batch_idx.to(device=dev, dtype=torch.int32).contiguous()
-    elif cell.shape[0] > 1:
+    elif cell.shape[0] > 1 and need_batch:
         raise ValueError("batch_idx is required when more than one cell is given")
     return positions, q, cell, batch_idx, code, n, dev
 
@@ -107,7 +107,7 @@ def fused_coulomb_energy_forces(positions, charges, cell, pbc, cutoff, alpha=0.0
     "list" (which path produced the numbers)."""
     from ...neighborlist.neighbor_utils import _prepare_batch_idx_ptr
 
-    pos, q, cell3, _, code, n, dev = _prep(positions, charges, cell, None if batch_idx is None else batch_idx)
+    pos, q, cell3, _, code, n, dev = _prep(positions, charges, cell, batch_idx, need_batch=False)
     ns = cell3.shape[0]
     if batch_idx is not None or batch_ptr is not None:
         batch_idx, batch_ptr = _prepare_batch_idx_ptr(batch_idx, batch_ptr, n, dev)

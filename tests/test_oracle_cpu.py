@@ -153,7 +153,7 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.declared_symbols())
     lib = _lib.lib()
-    assert lib.nvnl_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.nvnl_abi_version() == _lib.ABI_VERSION == 4
     assert lib.nvnl_workspace_bytes(1000, 1, 0) > 1000 * 16
     assert lib.nvnl_workspace_bytes(1000, 4, 1) > lib.nvnl_workspace_bytes(1000, 4, 0)
     # argument validation happens before any CUDA call
@@ -357,3 +357,37 @@ def test_oracle_reproduces_the_pair_counts_the_reference_publishes():
         # (the published naive totals equal the cell-list ones; checked here against the independent brute force)
         pos, cell, pbc = fcc_benchmark_system(n)
         assert ro.brute_force(pos, 5.0, cell, pbc).shape[0] == want, ("brute force", n)
+
+
+def test_coulomb_oracle_closed_forms_and_reference_erfc():
+    """The pair-consumer oracle (coulomb.py:206-292, math.py:52-93 restated): two charges reproduce the closed forms the
+    reference's docstrings state; the damped case equals the formulas evaluated by hand with the A&S erfc, which itself
+    stays within its documented 1.5e-7 of the exact function; forces obey Newton's third law on a full periodic list."""
+    import math
+
+    import coulomb_oracle as co
+
+    q1, q2, r = 1.5, -2.0, 2.0
+    pos = np.array([[0.0, 0.0, 0.0], [r, 0.0, 0.0]])
+    cell = np.eye(3)[None] * 20.0
+    e, f = co.coulomb_energy_forces_list(pos, [q1, q2], cell, 5.0, 0.0, [0, 1], [1, 0], np.zeros((2, 3)))
+    assert np.allclose(e, [q1 * q2 / (2 * r)] * 2, rtol=1e-15)
+    assert np.allclose(f, [[-q1 * q2 / r**2, 0, 0], [q1 * q2 / r**2, 0, 0]], rtol=1e-15)
+    alpha = 0.35
+    e, f = co.coulomb_energy_forces_list(pos, [q1, q2], cell, 5.0, alpha, [0, 1], [1, 0], np.zeros((2, 3)))
+    erfc_as = float(co.wp_erfc(alpha * r))
+    assert abs(erfc_as - math.erfc(alpha * r)) < 1.5e-7
+    assert np.allclose(e, [0.5 * q1 * q2 * erfc_as / r] * 2, rtol=1e-15)
+    fm = q1 * q2 * (erfc_as / r**3 + 2 * alpha / math.sqrt(math.pi) * math.exp(-(alpha * r) ** 2) / r**2)
+    assert np.allclose(f[0], [fm * -r, 0, 0], rtol=1e-13)
+    xs = np.linspace(-3.0, 5.0, 161)
+    assert np.abs(co.wp_erfc(xs) - np.array([math.erfc(x) for x in xs])).max() < 1.5e-7
+    # beyond the cutoff / coincident atoms are skipped (coulomb.py:247)
+    e, f = co.coulomb_energy_forces_list(pos, [q1, q2], cell, 1.9, 0.0, [0, 1], [1, 0], np.zeros((2, 3)))
+    assert not e.any() and not f.any()
+    # periodic system over the neighbor-list oracle: total force vanishes, a shifted image enters through cell^T · s
+    p, c, b = random_system(60, 9.0, torch.float32, seed=2)
+    rec = ro.records_from_matrix(*ro.cell_list(p, 4.0, c, b, max_neighbors=256))
+    qs = np.linspace(-1, 1, 60)
+    e, f = co.coulomb_energy_forces_list(p.numpy(), qs, c.numpy(), 4.0, 0.3, rec[:, 0], rec[:, 1], rec[:, 2:])
+    assert np.abs(f.sum(0)).max() < 1e-12 and (rec[:, 2:] != 0).any()
