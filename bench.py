@@ -558,6 +558,8 @@ def main():
                     agree = bool(lo.item() == hi.item())
                 res[name].update({"checksum": check, "checksum_agrees_on_all_ranks": agree})
             if stats is not None and gather and world > 1:
+                if "phase_ms" in stats:
+                    res[name]["phase_ms_rank0_one_call"] = stats["phase_ms"]
                 res[name].update({"peer_bytes_per_rank": stats["peer_bytes"], "packed_exchange": stats["packed"],
                                   "full_payload_bytes_per_rank": 20 * (tot - tot // world) + 4 * (4096000 - 4096000 // world)})
         if world > 1 and "with_gather" in res and "kernels_only" in res:

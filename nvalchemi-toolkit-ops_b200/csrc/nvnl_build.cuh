@@ -60,8 +60,8 @@ __host__ __device__ inline WsLayout make_layout(long long n, long long s, int re
     // parts of cells with many targets: (cell + 1, first target) — a cell of more than 64 targets is cut into parts of
     // 32, so there are fewer than n / 16 + 1 of them
     L.split = take(sizeof(int2) * (size_t)(n / 16 + 2));
-    // parts (32 targets) of single-cell systems that take the six-mask-word launch: (cell, first target)
-    L.huge = take(sizeof(int2) * (size_t)(n / 32 + s + 2));
+    // parts (20 targets) of single-cell systems that take the six-mask-word launch: (cell, first target)
+    L.huge = take(sizeof(int2) * (size_t)(n / 16 + s + 2));
     L.rows_cap = rows_per_atom * n + rows_slack;
     if (L.rows_cap < 1) L.rows_cap = 1;
     if (L.rows_cap > (1LL << 29) - 1) L.rows_cap = (1LL << 29) - 1;   // row_ref = first entry << 2 | header kind

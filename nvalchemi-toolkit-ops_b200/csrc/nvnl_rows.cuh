@@ -47,6 +47,8 @@ constexpr int kRowsHugeWords = kRowsMaxVCAlias / 32;  // mask words per lane and
 constexpr int kRowsMaxSeg = 32;                       // shift segments per tile (one per image at most)
 constexpr int kRowsSplitAbove = 64;                   // cells with more targets are swept in parts, by several CTAs
 constexpr int kRowsSplitPart = 32;                    // targets per part
+constexpr int kRowsHugePart = 20;                     // ... of a huge (aliased) tile: one trip per consumer warp, the sweep of
+                                                      // 100+ chunks is a long serial chain and there are few such tiles
 constexpr int kRowsBlock = 2048;                      // temp-buffer entries a warp reserves per cursor bump
 constexpr int kRowsSegShift = 27;                     // boundary rows: entry = atom | segment << 27 (atoms < 2^27)
 constexpr float kRowsFar = 3.0e18f;                   // sentinel coordinate: squares stay finite, never within any cutoff
@@ -103,6 +105,17 @@ struct RowsArgs {
 // from the sweeping warps of its scheduler
 template <int SLEEP_NS = 64>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#ifdef NVNL_MBAR_SUSPEND
+    // variant: let the hardware suspend the warp inside try_wait (time-limit hint) instead of polling with naps
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "NVNL_SWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra NVNL_SWAIT_%=;\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(NVNL_MBAR_SUSPEND) : "memory");
+    return;
+#endif
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -844,7 +857,7 @@ __global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinB
                     if (nvc > kRowsMaxVCAlias || nch * 32 * (int)RS > kRowsRingBytes) { defer_cell(); continue; }
                     if (!HUGE && nvc > kRowsMaxVC) {
                         // more than two mask words: the cell goes to the second launch, as parts of kRowsSplitPart targets
-                        const int nparts = (ntarget + kRowsSplitPart - 1) / kRowsSplitPart;
+                        const int nparts = (ntarget + kRowsHugePart - 1) / kRowsHugePart;
                         int base = 0;
                         if (lane == 0) {
                             base = atomicAdd(&ctrl->n_huge, nparts);
@@ -852,7 +865,7 @@ __global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinB
                         }
                         base = __shfl_sync(0xffffffffu, base, 0);
                         int2* huge = reinterpret_cast<int2*>(a.ws + a.L.huge);
-                        for (int k = lane; k < nparts; k += 32) huge[base + k] = make_int2(g, k * kRowsSplitPart);
+                        for (int k = lane; k < nparts; k += 32) huge[base + k] = make_int2(g, k * kRowsHugePart);
                         continue;
                     }
                     ok_item = true;
@@ -921,7 +934,10 @@ __global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinB
                 if (!ok_item) continue;      // empty, deferred: next work item
                 if (split_cell()) continue;  // pushed as parts
                 if (!part) tgt0 = 0;
-                tgt1 = part && tgt0 + kRowsSplitPart < ntarget ? tgt0 + kRowsSplitPart : ntarget;
+                {
+                    const int plen = HUGE ? kRowsHugePart : kRowsSplitPart;
+                    tgt1 = part && tgt0 + plen < ntarget ? tgt0 + plen : ntarget;
+                }
                 have = true;
                 break;
             }

@@ -164,6 +164,16 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = positions.device
     N = positions.shape[0]
+    # phase marks for return_stats (CUDA events on the current stream; read after the call's last kernel)
+    marks = []
+
+    def mark(name):
+        if return_stats and dev.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     parts, atom_ranges, n_total = _partition(batch_ptr, world)
     if n_total != N:
         raise ValueError("batch_ptr[-1] must equal the number of atoms")
@@ -197,6 +207,7 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             return (edge, lp, shifts, {"peer_bytes": 0, "packed": False}) if return_stats else (edge, lp, shifts)
         return edge, lp, shifts, (a0, a1)
 
+    mark("build_sweep_count")
     # ---- 1. one small all-gather: every rank learns every size and raises the same errors at the same point ----
     mine = torch.tensor([total, max_count, err, 1 if packable else 0], dtype=torch.int64, device=dev)
     everyone = torch.empty(4 * world, dtype=torch.int64, device=dev)
@@ -220,6 +231,7 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     for c in counts:
         offs.append(offs[-1] + c)
 
+    mark("size_exchange")
     # ---- 2. every rank writes its own range of the final arrays ----
     edge = torch.empty((2, P), dtype=torch.int32, device=dev)
     shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
@@ -234,6 +246,7 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
         if o1 > o0:
             _pack_shifts(shifts[o0:o1], packed[o0:o1])
 
+    mark("alloc_fill_own_pack")
     # ---- 3. variable-size gather, in place ----
     arrays = [[edge[1, offs[g]:offs[g + 1]] for g in range(world)],
               [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]]
@@ -244,13 +257,18 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
         arrays.append([shifts[offs[g]:offs[g + 1]] for g in range(world)])
     _gather_slices(arrays, rank, group)
 
+    mark("nccl_gather")
     # ---- 4. neighbor_ptr, then the source atoms and shifts of the foreign ranges ----
     neighbor_ptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
     torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
     if packed_ok:
         _expand(neighbor_ptr, N, a0, a1, packed, edge, shifts)
+    mark("ptr_scan_expand")
     if return_stats:
         per_pair = 5 if packed_ok else 20
-        return edge, neighbor_ptr, shifts, {"peer_bytes": per_pair * (P - counts[rank]) + 4 * (N - n_loc),
-                                            "packed": packed_ok}
+        stats = {"peer_bytes": per_pair * (P - counts[rank]) + 4 * (N - n_loc), "packed": packed_ok}
+        if marks:
+            torch.cuda.synchronize(dev)
+            stats["phase_ms"] = {marks[k + 1][0]: marks[k][1].elapsed_time(marks[k + 1][1]) for k in range(len(marks) - 1)}
+        return edge, neighbor_ptr, shifts, stats
     return edge, neighbor_ptr, shifts
