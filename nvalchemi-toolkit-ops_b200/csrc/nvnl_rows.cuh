@@ -1110,7 +1110,10 @@ __global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinB
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_rows_out: the final arrays in atom-index order.  One warp per 32 consecutive atoms: every lane issues ONE TMA bulk
+// k_rows_out: the final arrays in atom-index order.  (A two-stage software pipeline per warp — bulk copies of batch k + 1 in
+// flight while batch k is written, row references loaded one group ahead — was measured and changed nothing: 0.297 vs
+// 0.292 ms, profiles/r2_variants_c.txt; the kernel sits at what DRAM gives this read/write mix.)
+// One warp per 32 consecutive atoms: every lane issues ONE TMA bulk
 // copy that brings its atom's temporary row into the warp's shared-memory staging buffer (as many rows per batch as
 // fit), then the warp writes out_i (= i), out_j and, for rows of cells at a periodic boundary, the shifts unpacked from
 // the image keys in front of the row — all strictly sequential in the large.
@@ -1135,8 +1138,8 @@ __device__ __forceinline__ void warp_fill(int* __restrict__ dst, int n, int valu
 }
 
 struct RowsOutSmem {
-    alignas(128) int buf[kOutWarps][kOutCap];   // per warp: two stages of kOutCap / 2 entries
-    unsigned long long bar[kOutWarps][2];
+    alignas(128) int buf[kOutWarps][kOutCap];
+    unsigned long long bar[kOutWarps];
 };
 
 // writes one row (already in shared or global memory at `row`, header of `hdr` keys in front of it): the general case,
@@ -1221,127 +1224,81 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
     const int* __restrict__ rows = reinterpret_cast<const int*>(ws + L.rows);
     const int* __restrict__ row_ref = reinterpret_cast<const int*>(ws + L.row_ref);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Two-stage software pipeline per warp: the staging buffer is two halves with one mbarrier each; the bulk copies of
-    // batch k + 1 are in flight while batch k is written out, and the row references / pointers of the NEXT group of 32
-    // atoms are loaded one group ahead — the kernel is bound by the latency of these dependent reads, not by issue.
-    constexpr int CAP = kOutCap / 2;
-    uint64_t* const bar0 = reinterpret_cast<uint64_t*>(&sm.bar[warp][0]);   // stage st: bar0 + st
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.bar[warp]);
     if (lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 1, 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
     }
     __syncwarp();
-    int* const buf0 = sm.buf[warp];
-    uint32_t parity = 0u;                                                    // bit st = phase parity of stage st
-    const long long stride = (long long)gridDim.x * kOutWarps * 32;
-    long long base = ((long long)blockIdx.x * kOutWarps + warp) * 32;
-    if (base >= n) return;
-    auto load_meta = [&](long long b, int& ref, int& p, int& cnt) {
-        const long long il = b + lane;
-        ref = il < n ? row_ref[il] : -1;
-        p = neighbor_ptr[il < n ? il : n];
-        cnt = neighbor_ptr[il + 1 < n ? il + 1 : n] - p;
-    };
-    int ref, p, cnt, ref2 = -1, p2 = 0, cnt2 = 0;
-    load_meta(base, ref, p, cnt);
-    long long nbase = base + stride;
-    if (nbase < n) load_meta(nbase, ref2, p2, cnt2);
-    int s = 0;
-    // a planned batch: atoms [bs, be) of the group at bbase; per lane: row metadata, output position, row reference
-    struct Batch { long long bbase; int bs, be, tot, direct, meta, p, ref; };
-    // plans the next batch at the cursor (base, s), issues its bulk copies into stage `st`, advances the cursor
-    auto plan_issue = [&](Batch& b, int st) -> bool {
-        for (;;) {
-            if (base >= n) return false;
-            const int na = n - base < 32 ? (int)(n - base) : 32;
-            if (s >= na) {
-                base = nbase; ref = ref2; p = p2; cnt = cnt2; s = 0;
-                nbase += stride;
-                if (base < n && nbase < n) load_meta(nbase, ref2, p2, cnt2);
-                continue;
-            }
-            const int flag = ref & 3;
-            const int hdr = ref < 0 ? 0 : (flag == 0 ? 0 : (flag == 1 ? 8 : 32));
-            const int clen = (ref < 0 || cnt == 0) ? 0 : hdr + ((cnt + 3) & ~3);      // entries to copy
+    int* buf = sm.buf[warp];
+    uint32_t parity = 0;
+    const long long nwarps = (long long)gridDim.x * kOutWarps;
+    for (long long base = ((long long)blockIdx.x * kOutWarps + warp) * 32; base < n; base += nwarps * 32) {
+        const long long il = base + lane;
+        const int ref = il < n ? row_ref[il] : -1;
+        const int p = neighbor_ptr[il < n ? il : n];
+        const int cnt = neighbor_ptr[il + 1 < n ? il + 1 : n] - p;
+        const int na = n - base < 32 ? (int)(n - base) : 32;
+        const int flag = ref & 3;
+        const int hdr = ref < 0 ? 0 : (flag == 0 ? 0 : (flag == 1 ? 8 : 32));
+        const int clen = (ref < 0 || cnt == 0) ? 0 : hdr + ((cnt + 3) & ~3);      // entries to copy
+        const int* src = rows + (ref >> 2);
+        int s = 0;
+        while (s < na) {
             const int v = lane >= s ? clen : 0;
             const int incl = warp_incl_scan(v, lane);
-            const unsigned fit = __ballot_sync(0xffffffffu, lane >= s && lane < na && incl <= CAP);
-            const int e = s + __popc(fit);        // lanes [s, e) fit one batch (incl is monotone: the fitting lanes are a prefix)
-            b.bbase = base; b.bs = s; b.p = p; b.ref = ref;
+            const unsigned fit = __ballot_sync(0xffffffffu, lane >= s && lane < na && incl <= kOutCap);
+            // lanes [s, e) fit one batch (incl is monotone: the fitting lanes are a prefix)
+            const int e = s + __popc(fit);
             if (e == s) {
-                // a single row longer than the staging buffer: written straight from global memory when its turn comes
-                b.be = s + 1; b.tot = 0; b.direct = 1; b.meta = cnt | ((ref & 3) << 16);
-                s = s + 1;
-                return true;
+                // a single row longer than the staging buffer: straight from global memory
+                const int ref_t = __shfl_sync(0xffffffffu, ref, s), p_t = __shfl_sync(0xffffffffu, p, s);
+                const int cnt_t = __shfl_sync(0xffffffffu, cnt, s), hdr_t = __shfl_sync(0xffffffffu, hdr, s);
+                if (ref_t >= 0 && cnt_t > 0)
+                    rows_out_row(rows + (ref_t >> 2) + hdr_t, hdr_t, cnt_t, (int)(base + s) + index_offset, index_offset,
+                                 shifts_zeroed, out_i + (size_t)p_t, out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
+                ++s;
+                continue;
             }
-            b.be = e; b.direct = 0;
-            b.tot = __shfl_sync(0xffffffffu, incl, e - 1);
-            // per-row metadata in one word: row length (16 bits) | header kind (2 bits) | offset in the staging buffer
-            b.meta = (ref < 0 ? 0 : cnt) | ((ref & 3) << 16) | ((incl - v) << 18);
-            if (b.tot > 0) {
-                fence_proxy_async_smem();   // (the stage was read by generic loads two batches ago)
-                if (lane == 0) mbar_arrive_expect_tx(bar0 + st, (uint32_t)b.tot * 4u);
+            const int tot = __shfl_sync(0xffffffffu, incl, e - 1);
+            if (tot > 0) {
+                fence_proxy_async_smem();
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)tot * 4u);
                 __syncwarp();
-                if (lane >= s && lane < e && v > 0)
-                    tma_load_1d(buf0 + st * CAP + (incl - v), rows + (ref >> 2), (uint32_t)v * 4u, bar0 + st);
-            }
-            s = e;
-            return true;
-        }
-    };
-    auto process = [&](const Batch& b, int st) {
-        if (b.direct) {
-            const int t = b.bs;
-            const int ref_t = __shfl_sync(0xffffffffu, b.ref, t), p_t = __shfl_sync(0xffffffffu, b.p, t);
-            const int m_t = __shfl_sync(0xffffffffu, b.meta, t);
-            const int cnt_t = m_t & 0xffff, kind_t = (m_t >> 16) & 3;
-            const int hdr_t = kind_t == 0 ? 0 : (kind_t == 1 ? 8 : 32);
-            if (ref_t >= 0 && cnt_t > 0)
-                rows_out_row(rows + (ref_t >> 2) + hdr_t, hdr_t, cnt_t, (int)(b.bbase + t) + index_offset, index_offset,
-                             shifts_zeroed, out_i + (size_t)p_t, out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
-            return;
-        }
-        if (b.tot <= 0) return;
-        mbar_wait(bar0 + st, (parity >> st) & 1u);
-        parity ^= 1u << st;
-        const int* buf = buf0 + st * CAP;
-        const uint32_t buf_addr = smem_u32(buf) + (uint32_t)lane * 4u;
+                if (lane >= s && lane < e && v > 0) tma_load_1d(buf + (incl - v), src, (uint32_t)v * 4u, bar);
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                // per-row metadata in one word: row length (16 bits) | header kind (2 bits) | offset in the staging buffer
+                const int meta = cnt | ((ref & 3) << 16) | ((incl - v) << 18);
+                const uint32_t buf_addr = smem_u32(buf) + (uint32_t)lane * 4u;
 #pragma unroll 1
-        for (int t = b.bs; t < b.be; ++t) {
-            const int m_t = __shfl_sync(0xffffffffu, b.meta, t), p_t = __shfl_sync(0xffffffffu, b.p, t);
-            const int cnt_t = m_t & 0xffff, kind_t = (m_t >> 16) & 3, off_t = (int)((unsigned)m_t >> 18);
-            if (cnt_t == 0) continue;
-            const int iv = (int)(b.bbase + t) + index_offset;
-            if (kind_t == 0 && cnt_t <= 96 && shifts_zeroed) {
-                // the common case, unrolled: interior row, shifts already zero
-                int* __restrict__ oj = out_j + (size_t)p_t + lane;
-                int* __restrict__ oi = out_i + (size_t)p_t + lane;
-                const uint32_t ra = buf_addr + (uint32_t)off_t * 4u;
+                for (int t = s; t < e; ++t) {
+                    const int m_t = __shfl_sync(0xffffffffu, meta, t), p_t = __shfl_sync(0xffffffffu, p, t);
+                    const int cnt_t = m_t & 0xffff, kind_t = (m_t >> 16) & 3, off_t = (int)((unsigned)m_t >> 18);
+                    if (cnt_t == 0 || __shfl_sync(0xffffffffu, ref, t) < 0) continue;
+                    const int iv = (int)(base + t) + index_offset;
+                    if (kind_t == 0 && cnt_t <= 96 && shifts_zeroed) {
+                        // the common case, unrolled: interior row, shifts already zero
+                        int* __restrict__ oj = out_j + (size_t)p_t + lane;
+                        int* __restrict__ oi = out_i + (size_t)p_t + lane;
+                        const uint32_t ra = buf_addr + (uint32_t)off_t * 4u;
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    if (lane + 32 * u < cnt_t) {
-                        oj[32 * u] = lds_b32(ra + 128u * u) + index_offset;
-                        oi[32 * u] = iv;
+                        for (int u = 0; u < 3; ++u) {
+                            if (lane + 32 * u < cnt_t) {
+                                oj[32 * u] = lds_b32(ra + 128u * u) + index_offset;
+                                oi[32 * u] = iv;
+                            }
+                        }
+                    } else {
+                        const int hdr_t = kind_t == 0 ? 0 : (kind_t == 1 ? 8 : 32);
+                        rows_out_row(buf + off_t + hdr_t, hdr_t, cnt_t, iv, index_offset, shifts_zeroed, out_i + (size_t)p_t,
+                                     out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
                     }
                 }
-            } else {
-                const int hdr_t = kind_t == 0 ? 0 : (kind_t == 1 ? 8 : 32);
-                rows_out_row(buf + off_t + hdr_t, hdr_t, cnt_t, iv, index_offset, shifts_zeroed, out_i + (size_t)p_t,
-                             out_j + (size_t)p_t, out_shifts + 3 * (size_t)p_t, lane);
+                __syncwarp();   // every lane is done with the buffer before the next batch lands in it
             }
+            s = e;
         }
-        __syncwarp();   // every lane is done with the stage before the batch after next lands in it
-    };
-    Batch cur, nxt;
-    int st = 0;
-    if (!plan_issue(cur, st)) return;
-    for (;;) {
-        const bool more = plan_issue(nxt, st ^ 1);
-        process(cur, st);
-        if (!more) break;
-        cur = nxt;
-        st ^= 1;
     }
 }
 
