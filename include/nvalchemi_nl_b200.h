@@ -233,6 +233,14 @@ int nvnl_pack_shifts(const int32_t* shifts, int64_t n_pairs, uint8_t* packed, in
 int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t atom_lo, int64_t atom_hi,
                          const uint8_t* packed_shifts, int32_t* out_i, int32_t* shifts, void* stream);
 
+/* Re-assembly after a PADDED all-gather (one ncclAllGather per array, in place): rank g's targets / packed shifts sit at
+ * gathered_dst[g * pmax + k] / gathered_packed[g * pmax + k], k = pair index inside the rank's range
+ * [pair_bounds[g], pair_bounds[g+1]); atoms of rank g are [atom_bounds[g], atom_bounds[g+1]) (world + 1 HOST int64 each,
+ * world <= 16).  Writes out_j (row 1 of edge_index) for every pair and out_i / shifts for the pairs of the other ranks. */
+int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
+                       const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
+                       int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream);
+
 /* Size of the temporary row buffer nvnl_count_rows may use: entries_per_atom * n_atoms + slack_entries int32 entries
  * (defaults 160 and 148*4*8*2048; negative = default).  Changes nvnl_workspace_bytes(): set it before sizing a
  * workspace and keep it fixed while that workspace is in use.  Process-wide. */

@@ -170,12 +170,15 @@ int launch_rows_out(const unsigned char* ws, const WsLayout& L, long long n, con
         blocks_per_sm = b > 0 ? b : 1;
         bps[current_device()].store(blocks_per_sm, std::memory_order_relaxed);
     }
-    long long grid = (n + kOutWarps * 32 - 1) / (kOutWarps * 32);
+    // small inputs: 8 atoms per warp pass instead of 32 (the per-warp chain row references -> bulk copies -> rows is
+    // latency, and there are too few warps to hide it)
+    const int group = n < 262144 ? 8 : 32;
+    long long grid = (n + kOutWarps * group - 1) / (kOutWarps * group);
     const long long cap = (long long)sm_count() * blocks_per_sm * 4;   // a few waves: the tail is short
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     launch_pdl(kern, (unsigned)grid, kOutWarps * 32, smem, st, ws, L, n, neighbor_ptr, out_i, out_j, out_shifts, index_offset,
-                                                      shifts_zeroed, spec_cap);
+                                                      shifts_zeroed, spec_cap, group);
     NVNL_CHECK_LAUNCH("k_rows_out");
     return 0;
 }
@@ -229,7 +232,8 @@ int build_t(const T* pos, long long n, const T* cell, const uint8_t* pbc, const 
     }
     {
         const int need_counts = (batch_ptr == nullptr && ns > 1) ? 1 : 0;
-        long long blocks = (n + 2047) / 2048;
+        const long long chunk = ns > 1 ? 512 : 2048;
+        long long blocks = (n + chunk - 1) / chunk;
         if (blocks > (long long)sms * 4) blocks = (long long)sms * 4;
         if (blocks < 1) blocks = 1;
         launch_pdl(k_bbox<T>, (unsigned)blocks, kSmallBlock, 0, st, ws, L, n, ns, pos, batch_idx, need_counts);
@@ -454,6 +458,63 @@ __global__ void __launch_bounds__(256) k_expand_gathered(const int* __restrict__
             for (int e = lane; e < 3 * cnt; e += 32) {
                 const int k = e / 3, c = e - 3 * k;
                 sh[e] = (int)((pk[k] >> (2 * c)) & 3) - 1;
+            }
+        }
+    }
+}
+
+// Re-assembly after the padded all-gather of the packed exchange: rank g's targets / packed shifts sit at
+// gathered_dst[g * pmax + k] / gathered_packed[g * pmax + k] (k = pair index inside the rank's range).  Writes out_j for
+// every pair, and out_i / shifts for the pairs of the OTHER ranks (the rank's own were written by its fill kernels).
+struct ExpandRanks {
+    int world, rank;
+    long long atom_lo[17];    // atoms of rank g: [atom_lo[g], atom_lo[g + 1])
+    long long pair_lo[17];    // pairs of rank g: [pair_lo[g], pair_lo[g + 1])
+};
+__global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ neighbor_ptr, long long n_atoms, ExpandRanks R,
+                                                       long long pmax, const int* __restrict__ gathered_dst,
+                                                       const unsigned char* __restrict__ gathered_packed,
+                                                       int* __restrict__ out_i, int* __restrict__ out_j, int* __restrict__ shifts) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_atoms;
+         base += nwarps * 32) {
+        const long long il = base + lane;
+        const int p_l = neighbor_ptr[il < n_atoms ? il : n_atoms];
+        const int e_l = neighbor_ptr[il + 1 < n_atoms ? il + 1 : n_atoms];
+        const int na = n_atoms - base < 32 ? (int)(n_atoms - base) : 32;
+        int g = 0;
+        while (g + 1 < R.world && base >= R.atom_lo[g + 1]) ++g;          // rank of the group's first atom
+        // element e = lane + 32 u of a group of 32 pairs' shifts (96 ints) belongs to pair e / 3, component e % 3
+        int q[3], c2[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int e = lane + 32 * u;
+            q[u] = e / 3;
+            c2[u] = 2 * (e - 3 * q[u]);
+        }
+        for (int t = 0; t < na; ++t) {
+            const long long i = base + t;
+            while (g + 1 < R.world && i >= R.atom_lo[g + 1]) ++g;
+            const int p = __shfl_sync(0xffffffffu, p_l, t), cnt = __shfl_sync(0xffffffffu, e_l, t) - p;
+            const long long src = (long long)g * pmax + ((long long)p - R.pair_lo[g]);
+            const int* __restrict__ dj = gathered_dst + src;
+            const unsigned char* __restrict__ pk = gathered_packed + src;
+            const bool foreign = g != R.rank;
+            for (int k0 = 0; k0 < cnt; k0 += 32) {
+                const int k = k0 + lane;
+                const bool valid = k < cnt;
+                if (valid) out_j[(size_t)p + k] = dj[k];
+                if (!foreign) continue;
+                if (valid) out_i[(size_t)p + k] = (int)i;
+                const int pkv = valid ? (int)pk[k] : 0;
+                int* __restrict__ sh = shifts + 3 * ((size_t)p + k0);
+                const int nel = 3 * (cnt - k0);
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int pq = __shfl_sync(0xffffffffu, pkv, q[u]);
+                    if (lane + 32 * u < nel) sh[lane + 32 * u] = ((pq >> c2[u]) & 3) - 1;
+                }
             }
         }
     }
@@ -871,6 +932,31 @@ int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t a
     if (blocks > cap) blocks = cap;
     k_expand_gathered<<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, atom_lo, atom_hi, packed_shifts, out_i, shifts);
     NVNL_CHECK_LAUNCH("k_expand_gathered");
+    return 0;
+}
+
+int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
+                       const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
+                       int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || !atom_bounds || !pair_bounds || pmax < 0)
+        return fail(-1, "nvnl_expand_padded: bad rank layout (1 <= world <= 16)");
+    if (n_atoms <= 0) return 0;
+    if (!neighbor_ptr || !gathered_dst || !gathered_packed || !out_i || !out_j || !shifts)
+        return fail(-1, "nvnl_expand_padded: null pointer");
+    ExpandRanks R;
+    R.world = world; R.rank = rank;
+    for (int g = 0; g <= 16; ++g) {
+        R.atom_lo[g] = atom_bounds[g <= world ? g : world];
+        R.pair_lo[g] = pair_bounds[g <= world ? g : world];
+    }
+    if (R.atom_lo[0] != 0 || R.atom_lo[world] != n_atoms) return fail(-1, "nvnl_expand_padded: atom bounds do not cover the atoms");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long blocks = (n_atoms + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_expand_padded<<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, R, pmax, gathered_dst, gathered_packed, out_i, out_j,
+                                                      shifts);
+    NVNL_CHECK_LAUNCH("k_expand_padded");
     return 0;
 }
 

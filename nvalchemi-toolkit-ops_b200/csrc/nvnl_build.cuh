@@ -167,7 +167,7 @@ __global__ void k_bbox(unsigned char* __restrict__ ws, WsLayout L, long long n, 
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(ws + L.ctrl);
     __shared__ long long s_red[6][kSmallBlock / 32];
     __shared__ int s_cnt;
-    const long long chunk = 2048;
+    const long long chunk = num_systems > 1 ? 512 : 2048;   // (batches: more, shorter blocks — the atomics of one system serialise)
     for (long long base = (long long)blockIdx.x * chunk; base < n; base += (long long)gridDim.x * chunk) {
         const long long end = base + chunk < n ? base + chunk : n;
         const int s_first = batch_idx ? batch_idx[base] : 0;

@@ -1208,7 +1208,8 @@ template <bool SPEC>
 __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char* __restrict__ ws, WsLayout L, long long n,
                                                              const int* __restrict__ neighbor_ptr, int* __restrict__ out_i,
                                                              int* __restrict__ out_j_arg, int* __restrict__ out_shifts,
-                                                             int index_offset, int shifts_zeroed, long long spec_cap) {
+                                                             int index_offset, int shifts_zeroed, long long spec_cap, int group) {
+    // group = atoms a warp takes per pass (32, or 8 for small inputs: more, shorter dependent chains per warp)
     pdl_enter();
     extern __shared__ __align__(128) unsigned char out_smem_raw[];
     RowsOutSmem& sm = *reinterpret_cast<RowsOutSmem*>(out_smem_raw);
@@ -1233,12 +1234,13 @@ __global__ void __launch_bounds__(kOutWarps * 32) k_rows_out(const unsigned char
     int* buf = sm.buf[warp];
     uint32_t parity = 0;
     const long long nwarps = (long long)gridDim.x * kOutWarps;
-    for (long long base = ((long long)blockIdx.x * kOutWarps + warp) * 32; base < n; base += nwarps * 32) {
+    for (long long base = ((long long)blockIdx.x * kOutWarps + warp) * group; base < n; base += nwarps * group) {
         const long long il = base + lane;
-        const int ref = il < n ? row_ref[il] : -1;
-        const int p = neighbor_ptr[il < n ? il : n];
-        const int cnt = neighbor_ptr[il + 1 < n ? il + 1 : n] - p;
-        const int na = n - base < 32 ? (int)(n - base) : 32;
+        const bool mine = lane < group && il < n;
+        const int ref = mine ? row_ref[il] : -1;
+        const int p = neighbor_ptr[mine ? il : (base < n ? base : n)];
+        const int cnt = mine ? neighbor_ptr[il + 1] - p : 0;
+        const int na = n - base < group ? (int)(n - base) : group;
         const int flag = ref & 3;
         const int hdr = ref < 0 ? 0 : (flag == 0 ? 0 : (flag == 1 ? 8 : 32));
         const int clen = (ref < 0 || cnt == 0) ? 0 : hdr + ((cnt + 3) & ~3);      // entries to copy

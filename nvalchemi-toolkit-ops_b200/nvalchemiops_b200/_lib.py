@@ -56,6 +56,8 @@ _SIGNATURES = {
     "nvnl_coulomb_list": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_double, c_double, c_void_p,
                                   c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "nvnl_pack_shifts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nvnl_expand_padded": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_gathered": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -128,6 +128,33 @@ def _expand(neighbor_ptr, n_atoms, a0, a1, packed, edge, shifts):
         shifts[lo:hi] = keep_s
 
 
+def _expand_padded(neighbor_ptr, n_atoms, world, rank, atom_ranges, offs, pmax, t_dst, t_packed, edge, shifts):
+    """edge[1] for every pair, edge[0] / shifts for the other ranks' pairs, from the padded gathered staging buffers."""
+    if edge.is_cuda:
+        from .. import _lib
+
+        ab = (ctypes.c_int64 * (world + 1))(*([a for a, _ in atom_ranges] + [atom_ranges[-1][1]]))
+        pb = (ctypes.c_int64 * (world + 1))(*offs)
+        with torch.cuda.device(edge.device):
+            _lib.check(_lib.lib().nvnl_expand_padded(ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, world, rank, ab, pb, pmax,
+                                                     ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_packed.data_ptr()),
+                                                     ctypes.c_void_p(edge[0].data_ptr()), ctypes.c_void_p(edge[1].data_ptr()),
+                                                     ctypes.c_void_p(shifts.data_ptr()),
+                                                     ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)),
+                       "nvnl_expand_padded")
+        return
+    counts = torch.diff(neighbor_ptr).long()
+    src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), counts)
+    for g in range(world):
+        lo, hi = offs[g], offs[g + 1]
+        edge[1, lo:hi] = t_dst[g * pmax: g * pmax + (hi - lo)]
+        if g == rank:
+            continue
+        pk = t_packed[g * pmax: g * pmax + (hi - lo)].to(torch.int32)
+        edge[0, lo:hi] = src[lo:hi]
+        shifts[lo:hi] = torch.stack([(pk & 3) - 1, ((pk >> 2) & 3) - 1, ((pk >> 4) & 3) - 1], dim=1).to(torch.int32)
+
+
 def _gather_slices(arrays_by_rank, rank, group):
     """Variable-size all-gather IN PLACE: ``arrays_by_rank[k][g]`` is the contiguous view of array k that rank g owns
     (already filled on rank g); afterwards every view is filled on every rank.
@@ -233,36 +260,56 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
 
     mark("size_exchange")
     # ---- 2. every rank writes its own range of the final arrays ----
-    edge = torch.empty((2, P), dtype=torch.int32, device=dev)
+    # Packed exchange (the usual case): the targets (row 1 of edge_index) and the packed shifts travel through staging
+    # buffers of world x Pmax entries, each rank writing ITS slot directly (the fill kernel's row 1 lands there), so that
+    # the exchange is ONE in-place ncclAllGather per array (grouped broadcasts into uneven views run at a third of its
+    # bandwidth); nvnl_expand_padded then writes edge_index row 1 everywhere and row 0 / shifts of the other ranks.
     shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
     num_all = torch.empty((N,), dtype=torch.int32, device=dev)
     o0, o1 = offs[rank], offs[rank + 1]
-    if shard is not None:
-        shard.fill(edge.view(-1)[o0:], shifts[o0:o1], P)
-        num_all[a0:a1] = num
-    packed = None
+    pmax = max(counts)
     if packed_ok:
-        packed = torch.empty((P,), dtype=torch.uint8, device=dev)
-        if o1 > o0:
-            _pack_shifts(shifts[o0:o1], packed[o0:o1])
+        ebuf = torch.empty(2 * P + world * pmax, dtype=torch.int32, device=dev)
+        edge = ebuf[:2 * P].view(2, P)
+        t_dst = ebuf[2 * P:]
+        t_packed = torch.empty(world * pmax, dtype=torch.uint8, device=dev)
+        if shard is not None:
+            # row 0 at the rank's offset of the final array, row 1 in the rank's slot of the staging buffer
+            shard.fill(ebuf[o0:], shifts[o0:o1], (2 * P + rank * pmax) - o0)
+            num_all[a0:a1] = num
+            if o1 > o0:
+                _pack_shifts(shifts[o0:o1], t_packed[rank * pmax: rank * pmax + (o1 - o0)])
+    else:
+        edge = torch.empty((2, P), dtype=torch.int32, device=dev)
+        if shard is not None:
+            shard.fill(edge.view(-1)[o0:], shifts[o0:o1], P)
+            num_all[a0:a1] = num
 
     mark("alloc_fill_own_pack")
-    # ---- 3. variable-size gather, in place ----
-    arrays = [[edge[1, offs[g]:offs[g + 1]] for g in range(world)],
-              [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]]
+    # ---- 3. gather ----
+    counts_views = [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]
     if packed_ok:
-        arrays.append([packed[offs[g]:offs[g + 1]] for g in range(world)])
+        _gather_slices([counts_views], rank, group)
+        if pmax > 0:
+            if dev.type == "cuda":
+                dist.all_gather_into_tensor(t_dst, t_dst[rank * pmax:(rank + 1) * pmax], group=group)
+                dist.all_gather_into_tensor(t_packed, t_packed[rank * pmax:(rank + 1) * pmax], group=group)
+            else:   # gloo tests of the plumbing
+                dist.all_gather([t_dst[g * pmax:(g + 1) * pmax] for g in range(world)], t_dst[rank * pmax:(rank + 1) * pmax].clone(),
+                                group=group)
+                dist.all_gather([t_packed[g * pmax:(g + 1) * pmax] for g in range(world)],
+                                t_packed[rank * pmax:(rank + 1) * pmax].clone(), group=group)
     else:
-        arrays.append([edge[0, offs[g]:offs[g + 1]] for g in range(world)])
-        arrays.append([shifts[offs[g]:offs[g + 1]] for g in range(world)])
-    _gather_slices(arrays, rank, group)
+        _gather_slices([[edge[1, offs[g]:offs[g + 1]] for g in range(world)], counts_views,
+                        [edge[0, offs[g]:offs[g + 1]] for g in range(world)],
+                        [shifts[offs[g]:offs[g + 1]] for g in range(world)]], rank, group)
 
     mark("nccl_gather")
-    # ---- 4. neighbor_ptr, then the source atoms and shifts of the foreign ranges ----
+    # ---- 4. neighbor_ptr, then the targets everywhere and the source atoms / shifts of the foreign ranges ----
     neighbor_ptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
     torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
     if packed_ok:
-        _expand(neighbor_ptr, N, a0, a1, packed, edge, shifts)
+        _expand_padded(neighbor_ptr, N, world, rank, atom_ranges, offs, pmax, t_dst, t_packed, edge, shifts)
     mark("ptr_scan_expand")
     if return_stats:
         per_pair = 5 if packed_ok else 20

@@ -385,6 +385,30 @@ def test_sharded_ranges_fill_pack_and_expand_on_one_gpu():
                                                ctypes.c_void_p(e2.data_ptr()), ctypes.c_void_p(s2.data_ptr()), st), "expand")
     torch.cuda.synchronize()
     assert torch.equal(e2, edge) and torch.equal(s2, shifts)
+    # the padded exchange (one in-place ncclAllGather per array): every rank's targets / packed shifts sit in its slot of
+    # staging buffers of world x Pmax entries; nvnl_expand_padded writes row 1 everywhere and row 0 / shifts of the peers
+    pmax = max(counts)
+    offs = [0, counts[0], P]
+    t_dst = torch.full((world * pmax,), -5, dtype=torch.int32, device=DEV)
+    t_pk = torch.zeros((world * pmax,), dtype=torch.uint8, device=DEV)
+    for g in range(world):
+        t_dst[g * pmax: g * pmax + counts[g]] = edge[1, offs[g]:offs[g + 1]]
+        t_pk[g * pmax: g * pmax + counts[g]] = packed[offs[g]:offs[g + 1]]
+    ab = (ctypes.c_int64 * 3)(0, locals_[0][5], N)
+    pb = (ctypes.c_int64 * 3)(*offs)
+    for rank in range(world):
+        e3, s3 = edge.clone(), shifts.clone()
+        e3[1] = -9                                   # row 1 comes from the staging buffer on every rank
+        lo, hi = offs[rank], offs[rank + 1]
+        keep = torch.zeros(P, dtype=torch.bool, device=DEV); keep[lo:hi] = True
+        e3[0, ~keep] = -9
+        s3[~keep] = -9
+        _lib.check(_lib.lib().nvnl_expand_padded(ctypes.c_void_p(nptr.data_ptr()), N, world, rank, ab, pb, pmax,
+                                                 ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_pk.data_ptr()),
+                                                 ctypes.c_void_p(e3[0].data_ptr()), ctypes.c_void_p(e3[1].data_ptr()),
+                                                 ctypes.c_void_p(s3.data_ptr()), st), "expand_padded")
+        torch.cuda.synchronize()
+        assert torch.equal(e3, edge) and torch.equal(s3, shifts), rank
     # a shift outside {-1, 0, 1} is reported by the pack kernel
     s3 = shifts[:100].clone(); s3[17, 1] = 2
     bad.zero_()

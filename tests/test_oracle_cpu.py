@@ -391,3 +391,23 @@ def test_coulomb_oracle_closed_forms_and_reference_erfc():
     qs = np.linspace(-1, 1, 60)
     e, f = co.coulomb_energy_forces_list(p.numpy(), qs, c.numpy(), 4.0, 0.3, rec[:, 0], rec[:, 1], rec[:, 2:])
     assert np.abs(f.sum(0)).max() < 1e-12 and (rec[:, 2:] != 0).any()
+
+
+def test_pair_consumer_host_checks_need_no_gpu():
+    """Argument checks of the consumer API mirror the reference's (coulomb.py:1607-1621) and run before any CUDA call; CPU
+    tensors are rejected (no fallback)."""
+    from nvalchemiops_b200.interactions import electrostatics as es
+
+    pos, cell, pbc = random_system(8, 5.0, torch.float32, seed=1)
+    q = torch.ones(8, dtype=torch.float64)
+    nl = torch.zeros((2, 3), dtype=torch.int32)
+    sh = torch.zeros((3, 3), dtype=torch.int32)
+    with pytest.raises(ValueError, match="Must provide either"):
+        es.coulomb_energy_forces(pos, q, cell, 3.0)
+    with pytest.raises(ValueError, match="Cannot provide both"):
+        es.coulomb_energy_forces(pos, q, cell, 3.0, neighbor_list=nl, neighbor_shifts=sh, neighbor_matrix=nl, neighbor_matrix_shifts=sh)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        es.coulomb_energy_forces(pos, q, cell, 3.0, neighbor_list=nl, neighbor_ptr=torch.zeros(9, dtype=torch.int32), neighbor_shifts=sh)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        es.fused_coulomb_energy_forces(pos, q, cell, pbc, 3.0)
+    assert set(es.__all__) == {"coulomb_energy", "coulomb_forces", "coulomb_energy_forces", "fused_coulomb_energy_forces"}
