@@ -923,6 +923,42 @@ def test_coo_paths_single_cell_systems_and_many_target_cells(coo_path):
         assert np.array_equal(ro.records_from_coo(e.cpu(), sft.cpu()), want), coo_path
 
 
+def test_matrix_path_is_cuda_graph_capturable():
+    """The padded-matrix path has no host sync: build + query with pre-allocated outputs can be captured in a CUDA graph
+    (the kernels are launched with the programmatic-dependent-launch attribute, also under capture) and replayed on new
+    positions in the same buffers."""
+    n, M = 4000, 160
+    pos_a, cell, pbc = random_system(n, 30.0, torch.float32, seed=3)
+    pos_b, _, _ = random_system(n, 30.0, torch.float32, seed=4)
+    d_pos, d_cell, d_pbc = pos_a.to(DEV), cell.to(DEV), pbc.to(DEV)
+    nm = torch.empty((n, M), dtype=torch.int32, device=DEV)
+    sh = torch.empty((n, M, 3), dtype=torch.int32, device=DEV)
+    num = torch.empty((n,), dtype=torch.int32, device=DEV)
+
+    def call():
+        return _nl().cell_list(d_pos, 6.0, d_cell, d_pbc, max_neighbors=M, neighbor_matrix=nm, neighbor_matrix_shifts=sh,
+                               num_neighbors=num)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        call()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = call()
+    assert out[0] is nm and out[1] is num and out[2] is sh
+    for pos in (pos_b, pos_a):
+        d_pos.copy_(pos.to(DEV))
+        nm.fill_(-3); num.fill_(-3); sh.fill_(-3)
+        g.replay()
+        torch.cuda.synchronize()
+        want = ro.records_from_matrix(*ro.cell_list(pos, 6.0, cell, pbc, max_neighbors=M, nthreads=8))
+        assert np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+        _check_matrix_padding(nm, num, sh, n)
+
+
 def test_coo_paths_batch_and_sharded_blocks(coo_path):
     """Batched mixed-PBC systems through the public API, and the rank-sharded fill (index_offset, block layout)."""
     from nvalchemiops_b200.neighborlist import _engine
