@@ -501,19 +501,31 @@ __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ n
             const int* __restrict__ dj = gathered_dst + src;
             const unsigned char* __restrict__ pk = gathered_packed + src;
             const bool foreign = g != R.rank;
-            for (int k0 = 0; k0 < cnt; k0 += 32) {
-                const int k = k0 + lane;
-                const bool valid = k < cnt;
-                if (valid) out_j[(size_t)p + k] = dj[k];
-                if (!foreign) continue;
-                if (valid) out_i[(size_t)p + k] = (int)i;
-                const int pkv = valid ? (int)pk[k] : 0;
-                int* __restrict__ sh = shifts + 3 * ((size_t)p + k0);
-                const int nel = 3 * (cnt - k0);
+            // four chunks of 32 pairs per pass: all loads of a pass are issued before its stores (memory-level parallelism;
+            // a row has ~90 pairs, so one pass usually covers it)
+            for (int k0 = 0; k0 < cnt; k0 += 128) {
+                int dv[4], pv[4];
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int pq = __shfl_sync(0xffffffffu, pkv, q[u]);
-                    if (lane + 32 * u < nel) sh[lane + 32 * u] = ((pq >> c2[u]) & 3) - 1;
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 32 * u + lane;
+                    dv[u] = k < cnt ? dj[k] : 0;
+                    pv[u] = (foreign && k < cnt) ? (int)pk[k] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kb = k0 + 32 * u;
+                    if (kb >= cnt) break;
+                    const int k = kb + lane;
+                    if (k < cnt) out_j[(size_t)p + k] = dv[u];
+                    if (!foreign) continue;
+                    if (k < cnt) out_i[(size_t)p + k] = (int)i;
+                    int* __restrict__ sh = shifts + 3 * ((size_t)p + kb);
+                    const int nel = 3 * (cnt - kb);
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        const int pq = __shfl_sync(0xffffffffu, pv[u], q[w]);
+                        if (lane + 32 * w < nel) sh[lane + 32 * w] = ((pq >> c2[w]) & 3) - 1;
+                    }
                 }
             }
         }
