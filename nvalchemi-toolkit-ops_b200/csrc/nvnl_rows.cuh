@@ -597,7 +597,13 @@ __global__ void __launch_bounds__(kRowsThreads, HUGE ? 3 : (PAIR ? 3 : kRowsMinB
         int* row_ref = reinterpret_cast<int*>(a.ws + a.L.row_ref);
         const int total_cells = active ? ctrl->total_cells : 0;
         // zero-fill quota per published tile: the slice spread over the tiles this CTA is expected to produce
-        zquota = ((zend - zpos) / (total_cells / (int)gridDim.x + 1) + kRowsZeroBytes / 16) / (kRowsZeroBytes / 16) * (kRowsZeroBytes / 16);
+        // (pacing knob for experiments: quota x 0.7 / 1.5 / 2 were all slower than the even pace, profiles/r2_variants_d.txt)
+#ifndef NVNL_ZQUOTA_NUM
+#define NVNL_ZQUOTA_NUM 1
+#define NVNL_ZQUOTA_DEN 1
+#endif
+        zquota = (int)(((long long)(zend - zpos) * NVNL_ZQUOTA_NUM / NVNL_ZQUOTA_DEN / (total_cells / (int)gridDim.x + 1) + kRowsZeroBytes / 16) /
+                       (kRowsZeroBytes / 16) * (kRowsZeroBytes / 16));
         // descriptor ring + byte ring (FIFO): tiles [oldest, nprod) are live
         int nprod = 0, oldest = 0;
         int head = 0, used = 0;
