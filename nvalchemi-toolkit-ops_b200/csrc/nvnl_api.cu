@@ -62,7 +62,12 @@ std::atomic<long long> g_rows_per_atom{kRowsPerAtom};
 std::atomic<long long> g_rows_slack{kRowsSlackEntries};
 
 WsLayout mk_layout(long long n, long long s, int rec) {
-    return make_layout(n, s, rec, g_rows_per_atom.load(), g_rows_slack.load());
+    // the slack of the temporary row buffer is one 2048-entry reservation block per consumer warp that can get work: no
+    // more warps than trips (every trip has at least one target), so small inputs do not pay the 39 MB of a full machine
+    long long slack = g_rows_slack.load();
+    const long long by_atoms = (n + 64) * 2048;
+    if (slack > by_atoms) slack = by_atoms;
+    return make_layout(n, s, rec, g_rows_per_atom.load(), slack);
 }
 
 int rec_bytes(int dtype) { return dtype == NVNL_F64 ? (int)sizeof(Rec<double>) : (int)sizeof(Rec<float>); }
