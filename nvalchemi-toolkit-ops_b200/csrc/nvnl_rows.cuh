@@ -17,9 +17,16 @@
 // shift SEGMENT starts on a 32-slot boundary and its tail is padded with far-away sentinel records, so a chunk never
 // straddles two shifts (warp-uniform shift vector, no per-lane selection) and no chunk needs a validity mask.
 //
-// Cells the lean kernel cannot take (> 32 images, > 64 chunks) go to the general kernel; unwrapped inputs and fp64 use
-// the two-pass path.  Replaces (different algorithm, same result): cell_list.py:372-556 + neighbor_utils.py:106-147,
-// 362-441.
+// Work distribution beyond "one cell = one tile": a cell with more than 64 targets (small systems that are one or a few
+// cells) is pushed to a device-side split list as parts of 32 targets and swept by whichever CTAs drain the cell queue
+// first; a single-cell periodic system whose 27 images do not fit 64 chunks is staged ONCE with the image segments
+// aliasing the same records (six mask words per lane and target) — that variant is the second instantiation
+// k_rows<HUGE>, launched only for workloads that have such systems, so the common kernel keeps its register budget.
+// k_rows<PAIR> (nvnl_pair.cuh) feeds a pair consumer instead of writing rows: the neighbor list is never materialised.
+//
+// Cells the lean kernel cannot take (> 32 images, > 64 chunks that cannot be aliased) go to the general kernel; unwrapped
+// inputs and fp64 use the two-pass path.  Replaces (different algorithm, same result): cell_list.py:372-556 +
+// neighbor_utils.py:106-147, 362-441.
 #pragma once
 #include "nvnl_fast.cuh"
 
