@@ -87,6 +87,30 @@ def _prepare_batch_idx_ptr(batch_idx, batch_ptr, num_atoms: int, device):
     return batch_idx, batch_ptr
 
 
+def compute_naive_num_shifts(cell: torch.Tensor, cutoff: float, pbc: torch.Tensor):
+    """``(shift_range [S,3] int32, shift_offset [S+1] int32, total_shifts int)`` — how many periodic images the
+    reference's naive kernels enumerate per system (neighbor_utils.py:151-211, 233-293): per periodic dimension
+    ``s_d = ceil(cutoff * |row d of inverse(cell)^T|)`` (= cutoff / face distance), 0 in open dimensions, and the
+    half-space count ``s_0 (2 s_1 + 1)(2 s_2 + 1) + s_1 (2 s_2 + 1) + s_2 + 1``.  The B200 engine derives its images
+    from the cell grid and does not need these; the function exists for callers that pre-compute them
+    (``naive_neighbor_list(..., shift_range_per_dimension=, shift_offset=, total_shifts=)``).  Tensor arithmetic on
+    ``cell.device`` in ``cell.dtype``; the one ``.item()`` is the reference's."""
+    c = cell.reshape(-1, 3, 3)
+    a0, a1, a2 = c[:, 0], c[:, 1], c[:, 2]
+    # rows of inverse(cell)^T are the reciprocal vectors (a_j x a_k) / det
+    r0, r1, r2 = torch.linalg.cross(a1, a2), torch.linalg.cross(a2, a0), torch.linalg.cross(a0, a1)
+    det = (a0 * r0).sum(dim=1)
+    inv_len = torch.stack([r0.norm(dim=1), r1.norm(dim=1), r2.norm(dim=1)], dim=1) / det.abs()[:, None]
+    periodic = pbc.reshape(-1, 3).to(device=c.device, dtype=torch.bool)
+    inv_len = torch.where(periodic, inv_len, torch.zeros_like(inv_len))
+    s = torch.ceil(inv_len * torch.tensor(cutoff, dtype=c.dtype, device=c.device)).to(torch.int32)
+    k1, k2 = 2 * s[:, 1] + 1, 2 * s[:, 2] + 1
+    num_shifts = s[:, 0] * k1 * k2 + s[:, 1] * k2 + s[:, 2] + 1
+    shift_offset = torch.zeros((c.shape[0] + 1,), dtype=torch.int32, device=c.device)
+    shift_offset[1:] = torch.cumsum(num_shifts, dim=0)
+    return s, shift_offset, int(shift_offset[-1].item())
+
+
 def allocate_cell_list(total_atoms: int, max_total_cells: int, neighbor_search_radius: torch.Tensor, device):
     """The seven-tensor cell-list cache, zero-filled int32, in the reference's order: ``cells_per_dimension`` ([3], or
     [S,3] when ``neighbor_search_radius`` is [S,3]), ``neighbor_search_radius`` (passed through),

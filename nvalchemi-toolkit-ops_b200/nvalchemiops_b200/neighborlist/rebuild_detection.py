@@ -36,9 +36,24 @@ def neighbor_list_needs_rebuild(reference_positions: torch.Tensor, current_posit
     return _engine.moved_beyond(reference_positions, current_positions, skin_distance_threshold).to(torch.bool)
 
 
-def check_cell_list_rebuild_needed(current_positions, atom_to_cell_mapping, cells_per_dimension, cell, pbc) -> bool:
-    """Python-bool convenience wrapper (reference :505-576)."""
-    return bool(cell_list_needs_rebuild(current_positions, atom_to_cell_mapping, cells_per_dimension, cell, pbc).item())
+def check_cell_list_rebuild_needed(
+    cells_per_dimension: torch.Tensor,
+    neighbor_search_radius: torch.Tensor,
+    atom_periodic_shifts: torch.Tensor,
+    atom_to_cell_mapping: torch.Tensor,
+    atoms_per_cell_count: torch.Tensor,
+    cell_atom_start_indices: torch.Tensor,
+    cell_atom_list: torch.Tensor,
+    current_positions: torch.Tensor,
+    current_cell: torch.Tensor,
+    current_pbc: torch.Tensor,
+    cutoff: float,
+) -> bool:
+    """Python-bool convenience wrapper with the reference's argument list (:505-576): the seven cache tensors of
+    ``build_cell_list`` in their usual order, then the current positions / cell / pbc and the (unused) cutoff.  Only
+    ``atom_to_cell_mapping`` and ``cells_per_dimension`` enter the check, as in the reference."""
+    return bool(cell_list_needs_rebuild(current_positions, atom_to_cell_mapping, cells_per_dimension, current_cell,
+                                        current_pbc).item())
 
 
 def check_neighbor_list_rebuild_needed(reference_positions, current_positions, skin_distance_threshold) -> bool:

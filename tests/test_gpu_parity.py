@@ -664,22 +664,22 @@ def test_rebuild_detection():
     cache2 = _alloc_cache(2000, 4096)
     nl.build_cell_list(inside.to(DEV), 5.0, cell_d, pbc_d, *cache2)
     small = inside.clone(); small[7, 0] += 0.3 * w                                      # stays in its cell
-    assert nl.check_cell_list_rebuild_needed(small.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is False
+    assert nl.check_cell_list_rebuild_needed(*cache2, small.to(DEV), cell_d, pbc_d, 5.0) is False
     big = inside.clone(); big[7, 0] += 0.6 * w                                          # crosses into the next cell
-    assert nl.check_cell_list_rebuild_needed(big.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is True
+    assert nl.check_cell_list_rebuild_needed(*cache2, big.to(DEV), cell_d, pbc_d, 5.0) is True
     wrap = inside.clone(); wrap[7, 0] += 30.0                                           # a full period: same cell
-    assert nl.check_cell_list_rebuild_needed(wrap.to(DEV), cache2[3], cache2[0], cell_d, pbc_d) is False
+    assert nl.check_cell_list_rebuild_needed(*cache2, wrap.to(DEV), cell_d, pbc_d, 5.0) is False
     # the exported mapping agrees with the geometry
     cells = torch.floor(pos / w).long().clamp(0, 4)
     assert torch.equal(cache[3].cpu().long(), cells)
     # stateless: cloned tensors (no hidden handle), a non-periodic dimension, and a batch
-    assert nl.check_cell_list_rebuild_needed(big.to(DEV), cache2[3].clone(), cache2[0].clone(), cell_d, pbc_d) is True
+    assert nl.check_cell_list_rebuild_needed(*[t.clone() for t in cache2], big.to(DEV), cell_d, pbc_d, 5.0) is True
     pbc_open = torch.tensor([True, False, True])
     cache3 = _alloc_cache(2000, 4096)
     nl.build_cell_list(inside.to(DEV), 5.0, cell_d, pbc_open.to(DEV), *cache3)
     up = inside.clone(); up[7, 1] += 0.6 * w
-    assert nl.check_cell_list_rebuild_needed(inside.to(DEV), cache3[3], cache3[0], cell_d, pbc_open.to(DEV)) is False
-    assert nl.check_cell_list_rebuild_needed(up.to(DEV), cache3[3], cache3[0], cell_d, pbc_open.to(DEV)) is True
+    assert nl.check_cell_list_rebuild_needed(*cache3, inside.to(DEV), cell_d, pbc_open.to(DEV), 5.0) is False
+    assert nl.check_cell_list_rebuild_needed(*cache3, up.to(DEV), cell_d, pbc_open.to(DEV), 5.0) is True
     bpos, bcell, bpbc, bidx, bptr = bench_batch(4, 150, 250, seed=3, mixed_pbc=True)
     bcache = _alloc_cache(bpos.shape[0], 4096, ns=4)
     nl.batch_build_cell_list(bpos.to(DEV), 3.0, bcell.to(DEV), bpbc.to(DEV), bidx.to(DEV), *bcache)
@@ -708,6 +708,69 @@ def test_dual_cutoff_routes():
     assert len(out) == 6 and out[0].shape[0] == 2 and out[3].shape[0] == 2
     assert np.array_equal(ro.records_from_coo(out[3].cpu(), out[5].cpu()),
                           ro.records_from_matrix(*ro.cell_list(pos, 5.0, cell, pbc, max_neighbors=256)))
+
+
+def test_public_naive_entry_points():
+    """The reference's naive functions as public names (naive.py:400, batch_naive.py:480, naive_dual_cutoff.py:544,
+    batch_naive_dual_cutoff.py:592): reference signatures, return arity, in-place buffers, cutoff <= 0, default sizes —
+    all answered by the cell-list engine with the same neighbor sets."""
+    nl = _nl()
+    pos, cell, pbc = random_system(300, 11.0, torch.float32, seed=31)
+    pd, cd, bd = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    want = ro.records_from_matrix(*ro.cell_list(pos, 2.5, cell, pbc, max_neighbors=64))
+    # keyword order of the reference's docstring example: pbc before cell
+    nm, num, sh = nl.naive_neighbor_list(pd, 2.5, pbc=bd, cell=cd, max_neighbors=64)
+    assert nm.shape == (300, 64) and np.array_equal(_records_gpu_matrix(nm, num, sh), want)
+    _check_matrix_padding(nm, num, sh, 300)
+    # pre-allocated buffers are filled in place and returned as the same objects; pre-computed shift ranges are accepted
+    rng, off, tot = nl.compute_naive_num_shifts(cd, 2.5, bd)
+    assert rng.device.type == "cuda" and rng.cpu().tolist() == [[1, 1, 1]] and tot == 14
+    b_nm = torch.full((300, 48), -7, dtype=torch.int32, device=DEV)
+    b_sh = torch.full((300, 48, 3), 9, dtype=torch.int32, device=DEV)
+    b_num = torch.full((300,), 5, dtype=torch.int32, device=DEV)
+    out = nl.naive_neighbor_list(pd, 2.5, cd, bd, fill_value=-1, neighbor_matrix=b_nm, neighbor_matrix_shifts=b_sh,
+                                 num_neighbors=b_num, shift_range_per_dimension=rng, shift_offset=off, total_shifts=tot)
+    assert out[0] is b_nm and out[1] is b_num and out[2] is b_sh
+    assert np.array_equal(ro.records_from_matrix(b_nm.cpu(), b_num.cpu(), b_sh.cpu()), want)
+    _check_matrix_padding(b_nm, b_num, b_sh, -1)
+    e, ptr, s = nl.naive_neighbor_list(pd, 2.5, cd, bd, max_neighbors=64, return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want) and ptr[-1].item() == want.shape[0]
+    with pytest.raises(nl.NeighborOverflowError):
+        nl.naive_neighbor_list(pd, 2.5, cd, bd, max_neighbors=2, return_neighbor_list=True)
+    # cutoff <= 0, matrix mode: the (N, max_neighbors) buffers the reference allocates, all padding
+    nm0, num0, sh0 = nl.naive_neighbor_list(pd, 0.0, cd, bd, max_neighbors=8)
+    assert nm0.shape == (300, 8) and (nm0 == 300).all() and num0.sum().item() == 0 and sh0.shape == (300, 8, 3)
+    nm0, num0 = nl.naive_neighbor_list(pd, -1.0, max_neighbors=8)
+    assert nm0.shape == (300, 8) and num0.shape == (300,)
+    # batch: one of batch_idx / batch_ptr is enough; pairs never cross systems; 2-tuple without PBC
+    bpos, bcell, bpbc, bidx, bptr = bench_batch(5, 60, 90, seed=9, mixed_pbc=True)
+    wantb = ro.records_from_matrix(*ro.batch_cell_list(bpos, 5.0, bcell, bpbc, bidx, max_neighbors=256))
+    for kw in ({"batch_idx": bidx.to(DEV)}, {"batch_ptr": bptr.to(DEV)}, {"batch_idx": bidx.to(DEV), "batch_ptr": bptr.to(DEV)}):
+        nmb, numb, shb = nl.batch_naive_neighbor_list(bpos.to(DEV), 5.0, pbc=bpbc.to(DEV), cell=bcell.to(DEV),
+                                                      max_neighbors=256, max_atoms_per_system=90, **kw)
+        assert np.array_equal(_records_gpu_matrix(nmb, numb, shb), wantb)
+    open_cell = torch.eye(3).reshape(1, 3, 3).repeat(5, 1, 1)
+    want_open = ro.records_from_matrix(*ro.batch_cell_list(bpos, 5.0, open_cell, torch.zeros(5, 3, dtype=torch.bool), bidx,
+                                                            max_neighbors=256))
+    outb = nl.batch_naive_neighbor_list(bpos.to(DEV), 5.0, bidx.to(DEV), max_neighbors=256, return_neighbor_list=True)
+    assert len(outb) == 2 and np.array_equal(ro.records_from_coo(outb[0].cpu()), want_open)
+    assert nl.neighbor_list(bpos.to(DEV), 5.0, batch_ptr=bptr.to(DEV), method="batch_naive", max_neighbors=256)[0].shape == (bpos.shape[0], 256)
+    # dual cutoff: both matrices are sized from cutoff2 when no size is given (naive_dual_cutoff.py:761-772)
+    out = nl.naive_neighbor_list_dual_cutoff(pd, 2.5, 4.0, pbc=bd, cell=cd)
+    M2 = nl.estimate_max_neighbors(4.0)
+    assert len(out) == 6 and out[0].shape == (300, M2) and out[3].shape == (300, M2)
+    assert np.array_equal(_records_gpu_matrix(out[0], out[1], out[2]), want)
+    assert np.array_equal(_records_gpu_matrix(out[3], out[4], out[5]),
+                          ro.records_from_matrix(*ro.cell_list(pos, 4.0, cell, pbc, max_neighbors=M2)))
+    out = nl.naive_neighbor_list_dual_cutoff(pd, 0.0, 2.5, pbc=bd, cell=cd, max_neighbors1=16, max_neighbors2=64)
+    assert out[0].shape == (300, 16) and out[1].sum().item() == 0 and (out[0] == 300).all()
+    assert np.array_equal(_records_gpu_matrix(out[3], out[4], out[5]), want)
+    outb = nl.batch_naive_neighbor_list_dual_cutoff(bpos.to(DEV), 2.5, 5.0, batch_ptr=bptr.to(DEV), pbc=bpbc.to(DEV),
+                                                    cell=bcell.to(DEV), max_neighbors1=128, max_neighbors2=256,
+                                                    return_neighbor_list=True)
+    assert len(outb) == 6 and np.array_equal(ro.records_from_coo(outb[3].cpu(), outb[5].cpu()), wantb)
+    assert np.array_equal(ro.records_from_coo(outb[0].cpu(), outb[2].cpu()),
+                          ro.records_from_matrix(*ro.batch_cell_list(bpos, 2.5, bcell, bpbc, bidx, max_neighbors=128)))
 
 
 @pytest.mark.parametrize("pbc_flag", [[True, True, True], [True, True, False]])

@@ -411,3 +411,83 @@ def test_pair_consumer_host_checks_need_no_gpu():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         es.fused_coulomb_energy_forces(pos, q, cell, pbc, 3.0)
     assert set(es.__all__) == {"coulomb_energy", "coulomb_forces", "coulomb_energy_forces", "fused_coulomb_energy_forces"}
+
+
+def test_public_api_matches_the_reference_signatures():
+    """Every name of the reference's ``nvalchemiops.neighborlist.__all__`` exists here with the reference's parameter
+    names, order, kinds and defaults (tests/golden/reference_signatures.json, generated from the reference sources by
+    tests/golden/make_reference_signatures.py).  Allowed difference: extra trailing parameters that default to None
+    (``batch_cell_list(..., batch_ptr=None)``, ``cell_list_needs_rebuild(..., batch_idx=None)``)."""
+    import inspect
+    import json
+
+    import nvalchemiops_b200.neighborlist as nl
+
+    with open(os.path.join(ROOT, "tests", "golden", "reference_signatures.json")) as f:
+        want = json.load(f)["functions"]
+    assert len(want) == 18
+    for name, spec in want.items():
+        assert name in nl.__all__ and hasattr(nl, name), f"{name} is not exported"
+        params = list(inspect.signature(getattr(nl, name)).parameters.values())
+        ref = spec["params"]
+        assert len(params) >= len(ref), f"{name}: parameters missing"
+        for p, (rname, rdefault, rkind) in zip(params, ref):
+            assert p.name == rname, f"{name}: parameter {p.name} where the reference has {rname}"
+            assert p.kind.name.lower() == rkind, f"{name}.{rname}: kind {p.kind.name}"
+            if rdefault is None:
+                assert p.default is inspect.Parameter.empty, f"{name}.{rname} has a default here"
+            else:
+                assert p.default is not inspect.Parameter.empty and repr(p.default) == rdefault, \
+                    f"{name}.{rname}: default {p.default!r} vs reference {rdefault}"
+        for p in params[len(ref):]:
+            assert p.default is None, f"{name}: extra parameter {p.name} must be optional"
+
+
+def test_compute_naive_num_shifts_restates_the_reference_kernel():
+    """neighbor_utils.py:194-211: s_d = ceil(cutoff / face distance) in periodic dims, 0 in open ones;
+    num_shifts = s0 (2 s1 + 1)(2 s2 + 1) + s1 (2 s2 + 1) + s2 + 1; offsets = exclusive scan (test_naive.py:415-423
+    uses a 3 A cubic cell with cutoff 1.5: one image per direction -> 14 half-space shifts)."""
+    from nvalchemiops_b200.neighborlist import compute_naive_num_shifts
+
+    cell = (torch.eye(3) * 3.0).reshape(1, 3, 3)
+    rng, off, total = compute_naive_num_shifts(cell, 1.5, torch.tensor([[True, True, True]]))
+    assert rng.dtype == torch.int32 and rng.tolist() == [[1, 1, 1]] and off.tolist() == [0, 14] and total == 14
+    assert isinstance(total, int) and off.dtype == torch.int32
+    rng, off, total = compute_naive_num_shifts(cell, 1.5, torch.tensor([[True, False, True]]))
+    assert rng.tolist() == [[1, 0, 1]] and total == 1 * 1 * 3 + 0 + 1 + 1
+    # a batch: cubic 10 A with rc 12 (two images), an open system, a triclinic cell checked against numpy
+    tri = torch.tensor([[8.0, 0.0, 0.0], [2.0, 7.0, 0.0], [1.0, 1.5, 9.0]], dtype=torch.float64)
+    cells = torch.stack([torch.eye(3, dtype=torch.float64) * 10.0, torch.eye(3, dtype=torch.float64) * 10.0, tri])
+    pbc = torch.tensor([[True, True, True], [False, False, False], [True, True, False]])
+    rng, off, total = compute_naive_num_shifts(cells, 12.0, pbc)
+    inv_t = np.linalg.inv(tri.numpy()).T
+    s_tri = [int(np.ceil(np.linalg.norm(inv_t[d]) * 12.0)) if pbc[2, d] else 0 for d in range(3)]
+    assert rng.tolist() == [[2, 2, 2], [0, 0, 0], s_tri]
+    count = lambda s: s[0] * (2 * s[1] + 1) * (2 * s[2] + 1) + s[1] * (2 * s[2] + 1) + s[2] + 1   # noqa: E731
+    assert off.tolist() == [0, 63, 64, 64 + count(s_tri)] and total == off[-1].item()
+
+
+def test_naive_entry_points_host_logic():
+    """What the naive entry points decide before any kernel runs (naive.py:560-662, batch_naive.py:653-707,
+    naive_dual_cutoff.py:751-772): argument errors, no CPU fallback, and the reference's tuples for cutoff <= 0."""
+    from nvalchemiops_b200.neighborlist import (batch_naive_neighbor_list, batch_naive_neighbor_list_dual_cutoff,
+                                                naive_neighbor_list, naive_neighbor_list_dual_cutoff)
+
+    pos, cell, pbc = random_system(12, 5.0)
+    for fn, args in ((naive_neighbor_list, (pos, 2.0)), (naive_neighbor_list_dual_cutoff, (pos, 1.0, 2.0)),
+                     (batch_naive_neighbor_list, (pos, 2.0, torch.zeros(12, dtype=torch.int32))),
+                     (batch_naive_neighbor_list_dual_cutoff, (pos, 1.0, 2.0, torch.zeros(12, dtype=torch.int32)))):
+        with pytest.raises(ValueError, match="pbc must also be provided"):
+            fn(*args, cell=cell)
+        with pytest.raises(ValueError, match="cell must also be provided"):
+            fn(*args, pbc=pbc)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn(*args)
+    with pytest.raises(ValueError, match="Either batch_idx or batch_ptr"):
+        batch_naive_neighbor_list(pos, 2.0)
+    # cutoff <= 0 with return_neighbor_list: the reference's 3- / 4-tuples with the extra zero [N] tensor
+    out = naive_neighbor_list(pos, 0.0, return_neighbor_list=True)
+    assert [tuple(t.shape) for t in out] == [(2, 0), (12,), (13,)]
+    out = naive_neighbor_list(pos, -1.0, cell=cell, pbc=pbc, return_neighbor_list=True)
+    assert [tuple(t.shape) for t in out] == [(2, 0), (12,), (13,), (0, 3)]
+    assert all(t.dtype == torch.int32 for t in out)
