@@ -773,6 +773,56 @@ def test_public_naive_entry_points():
                           ro.records_from_matrix(*ro.batch_cell_list(bpos, 2.5, bcell, bpbc, bidx, max_neighbors=128)))
 
 
+def test_dispatcher_scenarios_of_the_reference_suite():
+    """The dispatcher-level scenarios of test/neighborlist/test_neighborlist.py, restated: auto-selection with and without
+    a batch (:43-292), kwargs forwarding and pre-allocated tensors (:735-899), empty / single-atom inputs through the naive
+    route (:905-943), wrapper == direct call (:328-357, 418-463)."""
+    nl = _nl()
+    pos, cell, pbc = random_system(50, 10.0, torch.float32, seed=42)
+    pd, cd, bd = pos.to(DEV), cell.to(DEV), pbc.to(DEV)
+    for kw, width in (({"method": "naive", "max_neighbors": 20}, 20), ({"method": "cell_list", "max_neighbors": 30}, 30),
+                      ({"max_neighbors": 25}, 25)):
+        out = nl.neighbor_list(pd, 5.0, cell=cd, pbc=bd, **kw)
+        assert len(out) == 3 and out[0].shape == (50, width) and out[0].dtype == torch.int32 and out[0].device == pd.device
+    nm1, _, _, nm2, _, _ = nl.neighbor_list(pd, 2.5, cell=cd, pbc=bd, cutoff2=3.5, method="naive_dual_cutoff",
+                                            max_neighbors1=15, max_neighbors2=25)
+    assert nm1.shape[1] == 15 and nm2.shape[1] == 25
+    bufs = (torch.full((50, 20), 50, dtype=torch.int32, device=DEV), torch.zeros(50, dtype=torch.int32, device=DEV),
+            torch.zeros((50, 20, 3), dtype=torch.int32, device=DEV))
+    out = nl.neighbor_list(pd, 5.0, cell=cd, pbc=bd, method="naive", neighbor_matrix=bufs[0], num_neighbors=bufs[1],
+                           neighbor_matrix_shifts=bufs[2])
+    assert out[0] is bufs[0] and out[1] is bufs[1] and out[2] is bufs[2]
+    with pytest.raises(TypeError):
+        nl.neighbor_list(pd, 2.0, method="naive", invalid_parameter_name=123)
+    # wrapper == direct call, both output formats
+    a = nl.neighbor_list(pd, 3.0, cell=cd, pbc=bd, method="cell_list", max_neighbors=64)
+    b = nl.cell_list(pd, 3.0, cd, bd, max_neighbors=64)
+    assert np.array_equal(_records_gpu_matrix(*a), _records_gpu_matrix(*b))
+    a = nl.neighbor_list(pd, 3.0, cell=cd, pbc=bd, method="naive", max_neighbors=64, return_neighbor_list=True)
+    assert np.array_equal(ro.records_from_coo(a[0].cpu(), a[2].cpu()), _records_gpu_matrix(*b))
+    # empty and single-atom systems through the naive route: 2-tuples, no pairs
+    e, ptr = nl.neighbor_list(torch.empty(0, 3, device=DEV), 2.0, method="naive", return_neighbor_list=True)
+    assert e.shape == (2, 0) and ptr.tolist() == [0]
+    e, ptr = nl.neighbor_list(torch.randn(1, 3, device=DEV), 2.0, method="naive", return_neighbor_list=True)
+    assert e.shape == (2, 0) and ptr.tolist() == [0, 0]
+    # auto-selection with a batch: batch_naive below 5000 atoms (2-tuple without PBC), batch_naive_dual_cutoff with cutoff2
+    bpos, bcell, bpbc, bidx, bptr = bench_batch(3, 40, 60, seed=11, mixed_pbc=False)
+    out = nl.neighbor_list(bpos.to(DEV), 3.0, batch_idx=bidx.to(DEV), max_neighbors=64)
+    assert len(out) == 2 and out[0].shape == (bpos.shape[0], 64)
+    i = torch.arange(bpos.shape[0]).repeat_interleave(out[1].cpu().long())
+    j = out[0].cpu()[out[0].cpu() < bpos.shape[0]].long()
+    assert (bidx[i] == bidx[j]).all(), "pairs must not cross systems"
+    out = nl.neighbor_list(bpos.to(DEV), 2.0, cell=bcell.to(DEV), pbc=bpbc.to(DEV), batch_ptr=bptr.to(DEV), cutoff2=3.0,
+                           max_neighbors1=64, max_neighbors2=64)
+    assert len(out) == 6
+    want = ro.records_from_matrix(*ro.batch_cell_list(bpos, 3.0, bcell, bpbc, bidx, max_neighbors=64))
+    assert np.array_equal(_records_gpu_matrix(out[3], out[4], out[5]), want)
+    # >= 5000 atoms with a batch: batch_cell_list is selected (3-tuple even without a cell)
+    big, _, _, gidx, gptr = bench_batch(4, 1300, 1300, seed=12, mixed_pbc=False)
+    out = nl.neighbor_list(big.to(DEV), 3.0, batch_ptr=gptr.to(DEV), max_neighbors=64)
+    assert len(out) == 3 and out[0].shape == (5200, 64)
+
+
 @pytest.mark.parametrize("pbc_flag", [[True, True, True], [True, True, False]])
 def test_unwrapped_coordinates_medium_box(pbc_flag):
     """MD-style unwrapped coordinates (atoms up to two lattice vectors outside the box) on a box large enough for the
