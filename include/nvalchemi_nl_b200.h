@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NVNL_ABI_VERSION 4
+#define NVNL_ABI_VERSION 5
 #define NVNL_F32 0
 #define NVNL_F64 1
 
@@ -240,6 +240,14 @@ int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t a
 int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
                        const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
                        int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream);
+
+/* The same for a CHUNKED exchange (the all-gather of chunk k overlaps the fill of chunk k + 1 and the expansion of chunk
+ * k - 1): one call per chunk.  Rank g's atoms of this chunk are [atom_begin[g], atom_end[g]) — ascending, disjoint; the atoms
+ * in between belong to other chunks and are left alone — and its pairs start at pair_begin[g] (= neighbor_ptr[atom_begin[g]]);
+ * gathered_dst / gathered_packed are this chunk's world x pmax staging buffers (world HOST int64 each, world <= 16). */
+int nvnl_expand_padded_ranges(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_begin,
+                              const int64_t* atom_end, const int64_t* pair_begin, int64_t pmax, const int32_t* gathered_dst,
+                              const uint8_t* gathered_packed, int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream);
 
 /* Size of the temporary row buffer nvnl_count_rows may use: entries_per_atom * n_atoms + slack_entries int32 entries
  * (defaults 160 and 148*4*8*2048; negative = default).  Changes nvnl_workspace_bytes(): set it before sizing a

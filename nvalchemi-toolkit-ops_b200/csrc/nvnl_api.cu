@@ -471,10 +471,13 @@ __global__ void __launch_bounds__(256) k_expand_gathered(const int* __restrict__
 // Re-assembly after the padded all-gather of the packed exchange: rank g's targets / packed shifts sit at
 // gathered_dst[g * pmax + k] / gathered_packed[g * pmax + k] (k = pair index inside the rank's range).  Writes out_j for
 // every pair, and out_i / shifts for the pairs of the OTHER ranks (the rank's own were written by its fill kernels).
+// (Chunked exchange: one launch per chunk; a rank's atoms of that chunk are [atom_lo[g], atom_hi[g]), the atoms between
+// atom_hi[g] and atom_lo[g + 1] belong to other chunks and are skipped.)
 struct ExpandRanks {
     int world, rank;
-    long long atom_lo[17];    // atoms of rank g: [atom_lo[g], atom_lo[g + 1])
-    long long pair_lo[17];    // pairs of rank g: [pair_lo[g], pair_lo[g + 1])
+    long long atom_lo[17];    // atoms of rank g: [atom_lo[g], atom_hi[g]); atom_lo ascending, atom_lo[world] = end of the last range
+    long long atom_hi[17];
+    long long pair_lo[17];    // first pair of rank g's range (= neighbor_ptr[atom_lo[g]])
 };
 __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ neighbor_ptr, long long n_atoms, ExpandRanks R,
                                                        long long pmax, const int* __restrict__ gathered_dst,
@@ -490,6 +493,8 @@ __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ n
         const int na = n_atoms - base < 32 ? (int)(n_atoms - base) : 32;
         int g = 0;
         while (g + 1 < R.world && base >= R.atom_lo[g + 1]) ++g;          // rank of the group's first atom
+        // the whole group lies between two ranks' ranges of this chunk (or outside all of them): nothing to do
+        if (base + 32 <= R.atom_lo[0] || (base >= R.atom_hi[g] && (g + 1 >= R.world || base + 32 <= R.atom_lo[g + 1]))) continue;
         // element e = lane + 32 u of a group of 32 pairs' shifts (96 ints) belongs to pair e / 3, component e % 3
         int q[3], c2[3];
 #pragma unroll
@@ -501,6 +506,7 @@ __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ n
         for (int t = 0; t < na; ++t) {
             const long long i = base + t;
             while (g + 1 < R.world && i >= R.atom_lo[g + 1]) ++g;
+            if (i < R.atom_lo[g] || i >= R.atom_hi[g]) continue;           // an atom of another chunk (warp-uniform)
             const int p = __shfl_sync(0xffffffffu, p_l, t), cnt = __shfl_sync(0xffffffffu, e_l, t) - p;
             const long long src = (long long)g * pmax + ((long long)p - R.pair_lo[g]);
             const int* __restrict__ dj = gathered_dst + src;
@@ -952,21 +958,15 @@ int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t a
     return 0;
 }
 
-int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
-                       const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
-                       int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream) {
-    if (world < 1 || world > 16 || rank < 0 || rank >= world || !atom_bounds || !pair_bounds || pmax < 0)
-        return fail(-1, "nvnl_expand_padded: bad rank layout (1 <= world <= 16)");
+static int expand_padded_launch(const char* who, const int32_t* neighbor_ptr, int64_t n_atoms, const ExpandRanks& R, int64_t pmax,
+                                const int32_t* gathered_dst, const uint8_t* gathered_packed, int32_t* out_i, int32_t* out_j,
+                                int32_t* shifts, void* stream) {
     if (n_atoms <= 0) return 0;
-    if (!neighbor_ptr || !gathered_dst || !gathered_packed || !out_i || !out_j || !shifts)
-        return fail(-1, "nvnl_expand_padded: null pointer");
-    ExpandRanks R;
-    R.world = world; R.rank = rank;
-    for (int g = 0; g <= 16; ++g) {
-        R.atom_lo[g] = atom_bounds[g <= world ? g : world];
-        R.pair_lo[g] = pair_bounds[g <= world ? g : world];
+    if (!neighbor_ptr || !gathered_dst || !gathered_packed || !out_i || !out_j || !shifts) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "%s: null pointer", who);
+        return fail(-1, msg);
     }
-    if (R.atom_lo[0] != 0 || R.atom_lo[world] != n_atoms) return fail(-1, "nvnl_expand_padded: atom bounds do not cover the atoms");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long blocks = (n_atoms + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -975,6 +975,44 @@ int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t wor
                                                       shifts);
     NVNL_CHECK_LAUNCH("k_expand_padded");
     return 0;
+}
+
+int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
+                       const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
+                       int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || !atom_bounds || !pair_bounds || pmax < 0)
+        return fail(-1, "nvnl_expand_padded: bad rank layout (1 <= world <= 16)");
+    if (n_atoms <= 0) return 0;
+    ExpandRanks R;
+    R.world = world; R.rank = rank;
+    for (int g = 0; g <= 16; ++g) {
+        R.atom_lo[g] = atom_bounds[g <= world ? g : world];
+        R.atom_hi[g] = atom_bounds[g + 1 <= world ? g + 1 : world];
+        R.pair_lo[g] = pair_bounds[g <= world ? g : world];
+    }
+    if (R.atom_lo[0] != 0 || R.atom_lo[world] != n_atoms) return fail(-1, "nvnl_expand_padded: atom bounds do not cover the atoms");
+    return expand_padded_launch("nvnl_expand_padded", neighbor_ptr, n_atoms, R, pmax, gathered_dst, gathered_packed, out_i, out_j,
+                                shifts, stream);
+}
+
+int nvnl_expand_padded_ranges(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_begin,
+                              const int64_t* atom_end, const int64_t* pair_begin, int64_t pmax, const int32_t* gathered_dst,
+                              const uint8_t* gathered_packed, int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || !atom_begin || !atom_end || !pair_begin || pmax < 0)
+        return fail(-1, "nvnl_expand_padded_ranges: bad rank layout (1 <= world <= 16)");
+    if (n_atoms <= 0) return 0;
+    ExpandRanks R;
+    R.world = world; R.rank = rank;
+    long long prev = 0;
+    for (int g = 0; g < world; ++g) {
+        if (atom_begin[g] < prev || atom_end[g] < atom_begin[g] || atom_end[g] > n_atoms || pair_begin[g] < 0)
+            return fail(-1, "nvnl_expand_padded_ranges: atom ranges must be ascending, disjoint and inside [0, n_atoms)");
+        R.atom_lo[g] = atom_begin[g]; R.atom_hi[g] = atom_end[g]; R.pair_lo[g] = pair_begin[g];
+        prev = atom_end[g];
+    }
+    for (int g = world; g <= 16; ++g) { R.atom_lo[g] = prev; R.atom_hi[g] = prev; R.pair_lo[g] = 0; }
+    return expand_padded_launch("nvnl_expand_padded_ranges", neighbor_ptr, n_atoms, R, pmax, gathered_dst, gathered_packed, out_i,
+                                out_j, shifts, stream);
 }
 
 }  // extern "C"

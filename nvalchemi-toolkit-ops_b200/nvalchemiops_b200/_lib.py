@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libnvalchemi_nl_b200.so"))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 c_void_p, c_int, c_int32, c_int64, c_double, c_size_t = (
@@ -58,6 +58,8 @@ _SIGNATURES = {
     "nvnl_pack_shifts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_padded": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "nvnl_expand_padded_ranges": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_gathered": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

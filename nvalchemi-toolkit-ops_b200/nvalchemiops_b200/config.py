@@ -32,3 +32,8 @@ speculative_fill: bool = True
 # cells is truncated, a singular cell yields an empty list — the COO path raises ValueError for all three.  True = one
 # host sync per matrix query to raise the same errors.
 check_inputs: bool = False
+
+# Multi-GPU sharded batches (neighborlist/distributed.py): every rank splits its own systems into this many chunks and the
+# exchange of chunk k (NCCL all-gather on a communication stream) runs under the output kernels of chunk k + 1 and the
+# re-assembly of chunk k - 1.  1 = one exchange after all kernels (no overlap).
+exchange_chunks: int = 2

@@ -7,18 +7,19 @@ one node, every rank builds the COO list of its own systems with GLOBAL atom ind
 Semantics: identical to running the whole batch on one GPU, up to the order of entries inside a source atom's row
 (which the reference leaves unspecified).
 
-Data flow (no padded blocks, no re-assembly pass over the payload):
-  1. local build + sweep (counts);  ONE small all-gather of (pairs, atoms, max count, error bits, flags) per rank — every
-     rank then knows every offset and raises the same errors at the same point;
-  2. every rank writes its OWN range straight into the final global arrays (``nvnl_fill_rows`` with the global row
-     stride) and packs its shifts into one byte per pair (``nvnl_pack_shifts``);
-  3. variable-size gather = one NCCL broadcast per rank and array, IN PLACE on slices of the final arrays, grouped into
-     one NCCL group: per pair only the target atom (4 B) and the packed shift (1 B) travel, per atom ``num_neighbors``
-     — 5 B/pair instead of 20;
-  4. ``neighbor_ptr`` = scan of the gathered counts; ``nvnl_expand_gathered`` writes the source atoms and int32 shifts of
-     the foreign ranges from it.
+Data flow (5 B per pair on the wire, no re-assembly pass over the payload, exchange overlapped with the kernels):
+  1. every rank splits its own systems into ``config.exchange_chunks`` chunks; local build + sweep (counts) of every chunk;
+     ONE small all-gather of (pairs, max count, error bits, flags) per rank and chunk — every rank then knows every offset
+     and raises the same errors at the same point; ``num_neighbors`` is gathered and scanned into ``neighbor_ptr``;
+  2. chunk by chunk every rank writes its OWN range straight into the final global arrays (``nvnl_fill_rows`` with the
+     global row stride, the targets landing in the rank's slot of the chunk's staging buffer) and packs its shifts into one
+     byte per pair (``nvnl_pack_shifts``);
+  3. the exchange of a chunk is ONE in-place ``ncclAllGather`` per array (targets 4 B/pair, packed shifts 1 B/pair) on a
+     communication stream: it runs while the next chunk is being written and the previous one re-assembled;
+  4. ``nvnl_expand_padded_ranges`` (one launch per chunk) writes the targets everywhere and the source atoms / int32
+     shifts of the foreign ranges.
 If some shift does not fit the packed byte (unwrapped coordinates, boxes smaller than the cutoff) the source atoms and
-int32 shifts are broadcast instead (20 B/pair, still in place).
+int32 shifts are broadcast instead (20 B/pair, in place, not chunked).
 """
 from __future__ import annotations
 
@@ -53,19 +54,37 @@ def partition_systems(batch_ptr_host, world_size: int):
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
-def _partition(batch_ptr, world):
-    """Partition of ``batch_ptr`` (device tensor) over ``world`` ranks, cached per tensor identity + version so that
-    repeated calls on the same batch pay no device->host copy."""
-    key = (batch_ptr.data_ptr(), batch_ptr._version, batch_ptr.shape[0], world, str(batch_ptr.device))
+def _partition(batch_ptr, world, chunks=1):
+    """Partition of ``batch_ptr`` (device tensor) over ``world`` ranks and of every rank's systems into ``chunks`` chunks,
+    cached per tensor identity + version so that repeated calls on the same batch pay no device->host copy.
+    Returns (system ranges, atom ranges, atoms, per-rank chunk system ranges, per-rank chunk atom ranges)."""
+    key = (batch_ptr.data_ptr(), batch_ptr._version, batch_ptr.shape[0], world, chunks, str(batch_ptr.device))
     hit = _partition_cache.get(key)
     if hit is None:
         ptr_host = batch_ptr.detach().cpu().tolist()
         parts = partition_systems(ptr_host, world)
-        hit = (parts, [(ptr_host[a], ptr_host[b]) for a, b in parts], ptr_host[-1])
+        sub = []
+        for a, b in parts:
+            local = partition_systems([ptr_host[s] - ptr_host[a] for s in range(a, b + 1)], chunks)
+            sub.append([(a + x, a + y) for x, y in local])
+        hit = (parts, [(ptr_host[a], ptr_host[b]) for a, b in parts], ptr_host[-1], sub,
+               [[(ptr_host[x], ptr_host[y]) for x, y in row] for row in sub])
         if len(_partition_cache) > 64:
             _partition_cache.clear()
         _partition_cache[key] = hit
     return hit
+
+
+_comm_streams: dict = {}
+
+
+def _comm_stream(dev):
+    """One side stream per device for the chunk exchanges (created once: stream creation is not free)."""
+    key = (dev.type, dev.index)
+    st = _comm_streams.get(key)
+    if st is None:
+        st = _comm_streams[key] = torch.cuda.Stream(device=dev)
+    return st
 
 
 class _CudaShard:
@@ -155,6 +174,31 @@ def _expand_padded(neighbor_ptr, n_atoms, world, rank, atom_ranges, offs, pmax, 
         shifts[lo:hi] = torch.stack([(pk & 3) - 1, ((pk >> 2) & 3) - 1, ((pk >> 4) & 3) - 1], dim=1).to(torch.int32)
 
 
+def _expand_chunk(neighbor_ptr, n_atoms, world, rank, begins, ends, pair_begins, counts, pmax, t_dst, t_packed, edge, shifts):
+    """One chunk of the exchange: ``t_dst`` / ``t_packed`` are the chunk's world x pmax staging buffers; rank g's atoms of
+    the chunk are [begins[g], ends[g]) and its ``counts[g]`` pairs start at ``pair_begins[g]``."""
+    if edge.is_cuda:
+        from .. import _lib
+
+        arr = ctypes.c_int64 * world
+        with torch.cuda.device(edge.device):
+            _lib.check(_lib.lib().nvnl_expand_padded_ranges(
+                ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, world, rank, arr(*begins), arr(*ends), arr(*pair_begins), pmax,
+                ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_packed.data_ptr()), ctypes.c_void_p(edge[0].data_ptr()),
+                ctypes.c_void_p(edge[1].data_ptr()), ctypes.c_void_p(shifts.data_ptr()),
+                ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)), "nvnl_expand_padded_ranges")
+        return
+    src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), torch.diff(neighbor_ptr).long())
+    for g in range(world):
+        lo, hi = pair_begins[g], pair_begins[g] + counts[g]
+        edge[1, lo:hi] = t_dst[g * pmax: g * pmax + (hi - lo)]
+        if g == rank:
+            continue
+        pk = t_packed[g * pmax: g * pmax + (hi - lo)].to(torch.int32)
+        edge[0, lo:hi] = src[lo:hi]
+        shifts[lo:hi] = torch.stack([(pk & 3) - 1, ((pk >> 2) & 3) - 1, ((pk >> 4) & 3) - 1], dim=1).to(torch.int32)
+
+
 def _gather_slices(arrays_by_rank, rank, group):
     """Variable-size all-gather IN PLACE: ``arrays_by_rank[k][g]`` is the contiguous view of array k that rank g owns
     (already filled on rank g); afterwards every view is filled on every rank.
@@ -175,7 +219,7 @@ def _gather_slices(arrays_by_rank, rank, group):
 
 
 def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fill=False, max_neighbors=None,
-                                group=None, gather=True, _local_shard=None, return_stats=False):
+                                group=None, gather=True, _local_shard=None, return_stats=False, chunks=None):
     """COO neighbor list of a batch, sharded over the ranks of ``group`` (default: WORLD).
 
     Every rank passes the SAME global tensors (on its own device): ``positions`` [N,3], ``cell`` [S,3,3],
@@ -183,14 +227,19 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     ``(neighbor_list [2,P] int32, neighbor_ptr [N+1] int32, shifts [P,3] int32)`` with global atom indices.
     With ``gather=False`` the collective is skipped and the rank's own shard is returned as
     ``(neighbor_list, neighbor_ptr_local, shifts, (atom_lo, atom_hi))`` — the "kernels only" figure of the bench.
-    ``return_stats=True`` appends a dict (bytes received from peers, packed or not).
+    ``return_stats=True`` appends a dict (bytes received from peers, packed or not, phase times).
+    ``chunks`` (default ``config.exchange_chunks``): chunks per rank of the overlapped exchange.
 
     ``_local_shard`` is a test hook (CPU/gloo tests inject an oracle-backed shard); the product path leaves it None.
     """
+    from .. import config
+    from ._engine import _raise_on_error_bits
+
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = positions.device
     N = positions.shape[0]
+    K = max(1, int(config.exchange_chunks if chunks is None else chunks)) if (gather and world > 1) else 1
     # phase marks for return_stats (CUDA events on the current stream; read after the call's last kernel)
     marks = []
 
@@ -201,26 +250,27 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             marks.append((name, ev))
 
     mark("start")
-    parts, atom_ranges, n_total = _partition(batch_ptr, world)
+    parts, atom_ranges, n_total, sub_sys, sub_atoms = _partition(batch_ptr, world, K)
     if n_total != N:
         raise ValueError("batch_ptr[-1] must equal the number of atoms")
-    s0, s1 = parts[rank]
     a0, a1 = atom_ranges[rank]
     n_loc = a1 - a0
     make = _local_shard or _CudaShard
-    if n_loc > 0:
-        lptr = (batch_ptr[s0:s1 + 1] - a0).to(torch.int32)
-        lidx = torch.repeat_interleave(torch.arange(s1 - s0, dtype=torch.int32, device=dev),
-                                       (lptr[1:] - lptr[:-1]).long())
-        shard = make(positions[a0:a1], cutoff, cell[s0:s1], pbc[s0:s1], lidx, lptr, half_fill, a0)
-        total, max_count, err, packable, num = shard.total, shard.max_count, shard.err, shard.packable, shard.num
-    else:
-        shard, total, max_count, err, packable = None, 0, 0, 0, True
-        num = torch.zeros(0, dtype=torch.int32, device=dev)
+    shards = []
+    for k in range(K):
+        (s0, s1), (c0, c1) = sub_sys[rank][k], sub_atoms[rank][k]
+        if c1 > c0:
+            lptr = (batch_ptr[s0:s1 + 1] - c0).to(torch.int32)
+            lidx = torch.repeat_interleave(torch.arange(s1 - s0, dtype=torch.int32, device=dev),
+                                           (lptr[1:] - lptr[:-1]).long())
+            shards.append(make(positions[c0:c1], cutoff, cell[s0:s1], pbc[s0:s1], lidx, lptr, half_fill, c0))
+        else:
+            shards.append(None)
 
     if not gather or world == 1:
-        from ._engine import _raise_on_error_bits
-
+        shard = shards[0]
+        total, max_count, err = (shard.total, shard.max_count, shard.err) if shard is not None else (0, 0, 0)
+        num = shard.num if shard is not None else torch.zeros(0, dtype=torch.int32, device=dev)
         _raise_on_error_bits(err)
         if max_neighbors is not None and max_count > max_neighbors:
             raise NeighborOverflowError(max_neighbors, max_count)
@@ -236,13 +286,14 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
 
     mark("build_sweep_count")
     # ---- 1. one small all-gather: every rank learns every size and raises the same errors at the same point ----
-    mine = torch.tensor([total, max_count, err, 1 if packable else 0], dtype=torch.int64, device=dev)
-    everyone = torch.empty(4 * world, dtype=torch.int64, device=dev)
+    mine = []
+    for sh in shards:
+        mine += [sh.total, sh.max_count, sh.err, 1 if sh.packable else 0] if sh is not None else [0, 0, 0, 1]
+    mine = torch.tensor(mine, dtype=torch.int64, device=dev)
+    everyone = torch.empty(4 * K * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(everyone, mine, group=group)
     everyone = everyone.cpu().tolist()
-    counts = everyone[0::4]
-    from ._engine import _raise_on_error_bits
-
+    counts = [[everyone[4 * (g * K + k)] for k in range(K)] for g in range(world)]     # pairs of (rank, chunk)
     err_all = 0
     for e in everyone[2::4]:
         err_all |= int(e)
@@ -250,72 +301,115 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     worst = max(everyone[1::4])
     if max_neighbors is not None and worst > max_neighbors:
         raise NeighborOverflowError(max_neighbors, worst)
-    P = sum(counts)
+    packed_ok = all(everyone[3::4])
+    offs, P = [], 0                                    # first pair of (rank, chunk): global atom order = (rank, chunk) order
+    for g in range(world):
+        row = []
+        for k in range(K):
+            row.append(P)
+            P += counts[g][k]
+        offs.append(row)
     if P > 2**31 - 1:
         raise OverflowError(f"{P} pairs do not fit int32 indices")
-    packed_ok = all(everyone[3::4])
-    offs = [0]
-    for c in counts:
-        offs.append(offs[-1] + c)
+    rank_lo = [offs[g][0] for g in range(world)] + [P]         # pairs of rank g: [rank_lo[g], rank_lo[g + 1])
+    pmax = max(max(row) for row in counts)
 
     mark("size_exchange")
-    # ---- 2. every rank writes its own range of the final arrays ----
-    # Packed exchange (the usual case): the targets (row 1 of edge_index) and the packed shifts travel through staging
-    # buffers of world x Pmax entries, each rank writing ITS slot directly (the fill kernel's row 1 lands there), so that
-    # the exchange is ONE in-place ncclAllGather per array (grouped broadcasts into uneven views run at a third of its
-    # bandwidth); nvnl_expand_padded then writes edge_index row 1 everywhere and row 0 / shifts of the other ranks.
     shifts = torch.empty((P, 3), dtype=torch.int32, device=dev)
     num_all = torch.empty((N,), dtype=torch.int32, device=dev)
-    o0, o1 = offs[rank], offs[rank + 1]
-    pmax = max(counts)
+    for k, sh in enumerate(shards):
+        if sh is not None:
+            num_all[sub_atoms[rank][k][0]:sub_atoms[rank][k][1]] = sh.num
+    counts_views = [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]
+    neighbor_ptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+    stats = {}
+
     if packed_ok:
-        ebuf = torch.empty(2 * P + world * pmax, dtype=torch.int32, device=dev)
+        # neighbor_ptr first (the per-atom counts are all the re-assembly needs besides the payload)
+        _gather_slices([counts_views], rank, group)
+        torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
+        mark("counts_gather_scan")
+        # ---- 2./3. chunk by chunk: own range into the final arrays (targets into the chunk's staging slot, shifts packed),
+        #      then ONE in-place all-gather per array on the communication stream ----
+        ebuf = torch.empty(2 * P + K * world * pmax, dtype=torch.int32, device=dev)
         edge = ebuf[:2 * P].view(2, P)
         t_dst = ebuf[2 * P:]
-        t_packed = torch.empty(world * pmax, dtype=torch.uint8, device=dev)
-        if shard is not None:
-            # row 0 at the rank's offset of the final array, row 1 in the rank's slot of the staging buffer
-            shard.fill(ebuf[o0:], shifts[o0:o1], (2 * P + rank * pmax) - o0)
-            num_all[a0:a1] = num
-            if o1 > o0:
-                _pack_shifts(shifts[o0:o1], t_packed[rank * pmax: rank * pmax + (o1 - o0)])
-    else:
-        edge = torch.empty((2, P), dtype=torch.int32, device=dev)
-        if shard is not None:
-            shard.fill(edge.view(-1)[o0:], shifts[o0:o1], P)
-            num_all[a0:a1] = num
-
-    mark("alloc_fill_own_pack")
-    # ---- 3. gather ----
-    counts_views = [num_all[atom_ranges[g][0]:atom_ranges[g][1]] for g in range(world)]
-    if packed_ok:
-        _gather_slices([counts_views], rank, group)
-        if pmax > 0:
-            if dev.type == "cuda":
-                dist.all_gather_into_tensor(t_dst, t_dst[rank * pmax:(rank + 1) * pmax], group=group)
-                dist.all_gather_into_tensor(t_packed, t_packed[rank * pmax:(rank + 1) * pmax], group=group)
+        t_packed = torch.empty(K * world * pmax, dtype=torch.uint8, device=dev)
+        on_gpu = dev.type == "cuda"
+        cur = torch.cuda.current_stream(dev) if on_gpu else None
+        comm = _comm_stream(dev) if on_gpu and K > 1 else cur
+        done, comm_marks = [], []
+        for k, sh in enumerate(shards):
+            base = k * world * pmax                     # the chunk's staging buffers: [base, base + world * pmax)
+            slot = base + rank * pmax
+            o0, cnt = offs[rank][k], counts[rank][k]
+            if sh is not None:
+                # row 0 at the chunk's offset of the final array, row 1 in the rank's slot of the chunk's staging buffer
+                sh.fill(ebuf[o0:], shifts[o0:o0 + cnt], (2 * P + slot) - o0)
+                if cnt > 0:
+                    _pack_shifts(shifts[o0:o0 + cnt], t_packed[slot:slot + cnt])
+            if pmax == 0:
+                continue
+            if on_gpu:
+                if comm is not cur:
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    comm.wait_event(ready)
+                with torch.cuda.stream(comm):
+                    if return_stats:
+                        b = torch.cuda.Event(enable_timing=True)
+                        b.record(comm)
+                    dist.all_gather_into_tensor(t_dst[base:base + world * pmax], t_dst[slot:slot + pmax], group=group)
+                    dist.all_gather_into_tensor(t_packed[base:base + world * pmax], t_packed[slot:slot + pmax], group=group)
+                    ev = torch.cuda.Event(enable_timing=return_stats)
+                    ev.record(comm)
+                    if return_stats:
+                        comm_marks.append((b, ev))
+                done.append(ev)
             else:   # gloo tests of the plumbing
-                dist.all_gather([t_dst[g * pmax:(g + 1) * pmax] for g in range(world)], t_dst[rank * pmax:(rank + 1) * pmax].clone(),
-                                group=group)
-                dist.all_gather([t_packed[g * pmax:(g + 1) * pmax] for g in range(world)],
-                                t_packed[rank * pmax:(rank + 1) * pmax].clone(), group=group)
+                dist.all_gather([t_dst[base + g * pmax: base + (g + 1) * pmax] for g in range(world)],
+                                t_dst[slot:slot + pmax].clone(), group=group)
+                dist.all_gather([t_packed[base + g * pmax: base + (g + 1) * pmax] for g in range(world)],
+                                t_packed[slot:slot + pmax].clone(), group=group)
+        mark("alloc_fill_own_pack")
+        # ---- 4. per chunk, as its exchange completes: the targets everywhere, source atoms / shifts of the foreign ranges ----
+        for k in range(K):
+            if pmax == 0:
+                break
+            if on_gpu and comm is not cur:
+                cur.wait_event(done[k])
+            base = k * world * pmax
+            _expand_chunk(neighbor_ptr, N, world, rank, [sub_atoms[g][k][0] for g in range(world)],
+                          [sub_atoms[g][k][1] for g in range(world)], [offs[g][k] for g in range(world)],
+                          [counts[g][k] for g in range(world)], pmax, t_dst[base:base + world * pmax],
+                          t_packed[base:base + world * pmax], edge, shifts)
+        mark("exchange_wait_expand")
+        if comm_marks:
+            stats["_comm_marks"] = comm_marks
     else:
-        _gather_slices([[edge[1, offs[g]:offs[g + 1]] for g in range(world)], counts_views,
-                        [edge[0, offs[g]:offs[g + 1]] for g in range(world)],
-                        [shifts[offs[g]:offs[g + 1]] for g in range(world)]], rank, group)
-
-    mark("nccl_gather")
-    # ---- 4. neighbor_ptr, then the targets everywhere and the source atoms / shifts of the foreign ranges ----
-    neighbor_ptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
-    torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
-    if packed_ok:
-        _expand_padded(neighbor_ptr, N, world, rank, atom_ranges, offs, pmax, t_dst, t_packed, edge, shifts)
-    mark("ptr_scan_expand")
+        # ---- fallback: int32 shifts and source atoms travel too (20 B/pair), in place, one exchange ----
+        edge = torch.empty((2, P), dtype=torch.int32, device=dev)
+        for k, sh in enumerate(shards):
+            if sh is not None:
+                o0, cnt = offs[rank][k], counts[rank][k]
+                sh.fill(edge.view(-1)[o0:], shifts[o0:o0 + cnt], P)
+        mark("alloc_fill_own")
+        _gather_slices([[edge[1, rank_lo[g]:rank_lo[g + 1]] for g in range(world)], counts_views,
+                        [edge[0, rank_lo[g]:rank_lo[g + 1]] for g in range(world)],
+                        [shifts[rank_lo[g]:rank_lo[g + 1]] for g in range(world)]], rank, group)
+        mark("nccl_gather")
+        torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
+        mark("ptr_scan")
     if return_stats:
         per_pair = 5 if packed_ok else 20
-        stats = {"peer_bytes": per_pair * (P - counts[rank]) + 4 * (N - n_loc), "packed": packed_ok}
+        own_pairs = rank_lo[rank + 1] - rank_lo[rank]
+        comm_marks = stats.pop("_comm_marks", [])
+        stats.update({"peer_bytes": per_pair * (P - own_pairs) + 4 * (N - n_loc), "packed": packed_ok, "chunks": K})
         if marks:
             torch.cuda.synchronize(dev)
             stats["phase_ms"] = {marks[k + 1][0]: marks[k][1].elapsed_time(marks[k + 1][1]) for k in range(len(marks) - 1)}
+            if comm_marks:
+                # the exchanges run on the communication stream, under the kernels of the neighbouring chunks
+                stats["phase_ms"]["nccl_chunks_on_comm_stream"] = [b.elapsed_time(e) for b, e in comm_marks]
         return edge, neighbor_ptr, shifts, stats
     return edge, neighbor_ptr, shifts

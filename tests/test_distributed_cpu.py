@@ -50,6 +50,14 @@ def _worker(rank, world, port, out_dir):
     pos, cell, pbc, bidx, bptr = bench_batch(9, 60, 140, seed=5, mixed_pbc=True)
     e, ptr, s = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_shard=_OracleShard)
     torch.save({"e": e, "ptr": ptr, "s": s}, os.path.join(out_dir, f"r{rank}.pt"))
+    # the chunked exchange (config.exchange_chunks = 2 above): any number of chunks per rank gives the same arrays,
+    # also when some chunks of some ranks are empty (9 systems over 3 ranks x 4 chunks)
+    import reference_oracle as ro
+    for chunks in (1, 3, 4):
+        e2, ptr2, s2 = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_shard=_OracleShard, chunks=chunks)
+        assert torch.equal(ptr2, ptr), chunks
+        assert np.array_equal(ro.records_from_coo(e2, s2), ro.records_from_coo(e, s)), chunks
+        assert bool((e2[0, 1:] >= e2[0, :-1]).all()), chunks
     shard = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, gather=False, _local_shard=_OracleShard)
     torch.save({"e": shard[0], "range": shard[3]}, os.path.join(out_dir, f"s{rank}.pt"))
     dist.barrier()
@@ -80,6 +88,22 @@ def test_sharded_batch_matches_single_process(tmp_path, world):
     covered.sort()
     assert covered[0][0] == 0 and covered[-1][1] == pos.shape[0]
     assert all(covered[k][1] == covered[k + 1][0] for k in range(world - 1))
+
+
+def test_chunk_partition_covers_every_rank_range():
+    """_partition: every rank's systems split into contiguous chunks that cover exactly the rank's range."""
+    from nvalchemiops_b200.neighborlist.distributed import _partition
+
+    bptr = torch.tensor([0, 7, 19, 19, 40, 41, 90, 120, 121, 200], dtype=torch.int32)
+    for world in (1, 2, 3, 5):
+        for chunks in (1, 2, 4):
+            parts, atoms, n, sub, sub_atoms = _partition(bptr, world, chunks)
+            assert n == 200 and len(sub) == world and all(len(row) == chunks for row in sub)
+            for g in range(world):
+                assert sub[g][0][0] == parts[g][0] and sub[g][-1][1] == parts[g][1]
+                assert all(sub[g][k][1] == sub[g][k + 1][0] for k in range(chunks - 1))
+                assert sub_atoms[g][0][0] == atoms[g][0] and sub_atoms[g][-1][1] == atoms[g][1]
+                assert all(a <= b for a, b in sub_atoms[g])
 
 
 def test_partition_balances_atoms():

@@ -409,6 +409,41 @@ def test_sharded_ranges_fill_pack_and_expand_on_one_gpu():
                                                  ctypes.c_void_p(s3.data_ptr()), st), "expand_padded")
         torch.cuda.synchronize()
         assert torch.equal(e3, edge) and torch.equal(s3, shifts), rank
+    # the chunked exchange: every rank's atoms split into chunks (here at arbitrary atoms, one chunk empty), one staging
+    # buffer set and one nvnl_expand_padded_ranges launch per chunk; atoms of other chunks must be left alone
+    mid = locals_[0][5]
+    chunk_atoms = [[(0, 37), (mid, mid + 1001)], [(37, mid - 5), (mid + 1001, mid + 1001)], [(mid - 5, mid), (mid + 1001, N)]]
+    nptr_h = nptr.cpu().tolist()
+    arr = ctypes.c_int64 * world
+    for rank in range(world):
+        e3, s3 = edge.clone(), shifts.clone()
+        e3[1] = -9
+        lo, hi = offs[rank], offs[rank + 1]
+        keep = torch.zeros(P, dtype=torch.bool, device=DEV); keep[lo:hi] = True
+        e3[0, ~keep] = -9
+        s3[~keep] = -9
+        for ranges in chunk_atoms:
+            cnts = [nptr_h[b] - nptr_h[a] for a, b in ranges]
+            pm = max(cnts)
+            if pm == 0:
+                continue
+            c_dst = torch.full((world * pm,), -5, dtype=torch.int32, device=DEV)
+            c_pk = torch.zeros((world * pm,), dtype=torch.uint8, device=DEV)
+            for g, (a, b) in enumerate(ranges):
+                c_dst[g * pm: g * pm + cnts[g]] = edge[1, nptr_h[a]:nptr_h[b]]
+                c_pk[g * pm: g * pm + cnts[g]] = packed[nptr_h[a]:nptr_h[b]]
+            _lib.check(_lib.lib().nvnl_expand_padded_ranges(
+                ctypes.c_void_p(nptr.data_ptr()), N, world, rank, arr(*[a for a, _ in ranges]), arr(*[b for _, b in ranges]),
+                arr(*[nptr_h[a] for a, _ in ranges]), pm, ctypes.c_void_p(c_dst.data_ptr()), ctypes.c_void_p(c_pk.data_ptr()),
+                ctypes.c_void_p(e3[0].data_ptr()), ctypes.c_void_p(e3[1].data_ptr()), ctypes.c_void_p(s3.data_ptr()), st),
+                "expand_padded_ranges")
+            torch.cuda.synchronize()
+        assert torch.equal(e3, edge) and torch.equal(s3, shifts), rank
+    bad_ranges = arr(10, 5)
+    assert _lib.lib().nvnl_expand_padded_ranges(ctypes.c_void_p(nptr.data_ptr()), N, world, 0, bad_ranges, arr(20, 30), arr(0, 0), 1,
+                                                ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_pk.data_ptr()),
+                                                ctypes.c_void_p(e3[0].data_ptr()), ctypes.c_void_p(e3[1].data_ptr()),
+                                                ctypes.c_void_p(s3.data_ptr()), st) != 0
     # a shift outside {-1, 0, 1} is reported by the pack kernel
     s3 = shifts[:100].clone(); s3[17, 1] = 2
     bad.zero_()
