@@ -385,11 +385,24 @@ def count_and_size(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, 
     buffer overflowed, in which case the count is repeated on the two-pass path).  ``launch_hint`` >= 0 (from an earlier
     query with this signature) skips the kernel variants that had no work then; if the device reports work for a
     skipped variant the count is repeated with everything launched."""
+    pending = count_launch(h, cutoff_sq, half_fill, prezero, spec_edge, launch_hint)
+    return count_finish(h, cutoff_sq, half_fill, pending)
+
+
+def count_launch(h: CellListHandle, cutoff_sq, half_fill=False, prezero=None, spec_edge=None, launch_hint=-1):
+    """First half of ``count_and_size``: the launches, no host sync (several independent cell lists can be queued before
+    the first ``count_finish`` waits)."""
     rows = use_rows(h)
     num, ptr = count(h, cutoff_sq, half_fill, rows=rows, prezero=prezero if rows else None,
                      launch_hint=launch_hint if rows else -1)
     if rows and prezero is not None and spec_edge is not None:
         fill_rows_speculative(h, ptr, spec_edge, prezero)      # runs while the host waits for the size
+    return num, ptr, rows, launch_hint
+
+
+def count_finish(h: CellListHandle, cutoff_sq, half_fill, pending):
+    """Second half of ``count_and_size``: the host sync for the sizes and the (rare) repeated counts."""
+    num, ptr, rows, launch_hint = pending
     total, max_count, _cells, err, hint = status(h)
     if rows and launch_hint >= 0 and (hint & ~launch_hint & 35):
         # a variant that was not launched had work: repeat the count with every variant (the speculative outputs, if any,

@@ -88,7 +88,8 @@ def _comm_stream(dev):
 
 
 class _CudaShard:
-    """A rank's own systems on the CUDA path: build + count now, fill into caller-provided (global) arrays later."""
+    """Some of a rank's own systems on the CUDA path: build + count queued now, sizes read by ``finish()`` (the chunks of a
+    rank are all queued before the first host sync), fill into caller-provided (global) arrays later."""
 
     def __init__(self, positions, cutoff, cell, pbc, batch_idx, batch_ptr, half_fill, index_offset):
         from . import _engine
@@ -97,8 +98,12 @@ class _CudaShard:
         self.h = _engine.build(positions, cutoff, cell, pbc, batch_idx=batch_idx, batch_ptr=batch_ptr)
         self.csq = _engine.cutoff_sq_in_dtype(cutoff, positions.dtype)
         self.half_fill, self.index_offset = half_fill, index_offset
-        self.num, self.ptr, self.total, self.max_count, self.err, self.hint, self.rows = _engine.count_and_size(
-            self.h, self.csq, half_fill)
+        self._pending = _engine.count_launch(self.h, self.csq, half_fill)
+
+    def finish(self):
+        self.num, self.ptr, self.total, self.max_count, self.err, self.hint, self.rows = self._e.count_finish(
+            self.h, self.csq, self.half_fill, self._pending)
+        self._pending = None
         # shifts fit one byte when no atom lies outside the primary image and no stencil is wider than one cell
         self.packable = not (self.hint & 1) and not self.h.wide_stencil
 
@@ -266,6 +271,9 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             shards.append(make(positions[c0:c1], cutoff, cell[s0:s1], pbc[s0:s1], lidx, lptr, half_fill, c0))
         else:
             shards.append(None)
+    for sh in shards:                                  # the host syncs, after every chunk has been queued
+        if sh is not None and hasattr(sh, "finish"):
+            sh.finish()
 
     if not gather or world == 1:
         shard = shards[0]
