@@ -224,7 +224,8 @@ def _gather_slices(arrays_by_rank, rank, group):
 
 
 def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fill=False, max_neighbors=None,
-                                group=None, gather=True, _local_shard=None, return_stats=False, chunks=None):
+                                group=None, gather=True, _local_shard=None, return_stats=False, chunks=None,
+                                _exchange_when_alone=False):
     """COO neighbor list of a batch, sharded over the ranks of ``group`` (default: WORLD).
 
     Every rank passes the SAME global tensors (on its own device): ``positions`` [N,3], ``cell`` [S,3,3],
@@ -236,6 +237,8 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     ``chunks`` (default ``config.exchange_chunks``): chunks per rank of the overlapped exchange.
 
     ``_local_shard`` is a test hook (CPU/gloo tests inject an oracle-backed shard); the product path leaves it None.
+    ``_exchange_when_alone`` is a test hook too: a world of ONE rank still goes through the chunked exchange (staging
+    slots, communication stream, re-assembly), so that this plumbing is covered on a single GPU.
     """
     from .. import config
     from ._engine import _raise_on_error_bits
@@ -244,7 +247,8 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = positions.device
     N = positions.shape[0]
-    K = max(1, int(config.exchange_chunks if chunks is None else chunks)) if (gather and world > 1) else 1
+    exchange = gather and (world > 1 or (_exchange_when_alone and dist.is_initialized()))
+    K = max(1, int(config.exchange_chunks if chunks is None else chunks)) if exchange else 1
     # phase marks for return_stats (CUDA events on the current stream; read after the call's last kernel)
     marks = []
 
@@ -275,7 +279,7 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
         if sh is not None and hasattr(sh, "finish"):
             sh.finish()
 
-    if not gather or world == 1:
+    if not exchange:
         shard = shards[0]
         total, max_count, err = (shard.total, shard.max_count, shard.err) if shard is not None else (0, 0, 0)
         num = shard.num if shard is not None else torch.zeros(0, dtype=torch.int32, device=dev)

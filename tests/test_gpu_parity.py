@@ -452,6 +452,40 @@ def test_sharded_ranges_fill_pack_and_expand_on_one_gpu():
     assert int(bad.item()) == 1
 
 
+def test_chunked_exchange_pipeline_on_one_gpu(tmp_path):
+    """The sharded path's exchange machinery on ONE GPU (a one-rank NCCL group): every chunk of the rank's systems is
+    written into the final arrays with its targets in the chunk's staging slot, exchanged on the communication stream and
+    re-assembled by nvnl_expand_padded_ranges — the result must equal the plain batched neighbor list for any number of
+    chunks.  (Foreign ranges need peers: tests/test_distributed_gpu.py on >= 2 GPUs, and the emulation test above.)"""
+    import torch.distributed as dist
+
+    from nvalchemiops_b200.neighborlist.distributed import sharded_batch_neighbor_list
+
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this process")
+    pos, cell, pbc, bidx, bptr = bench_batch(13, 200, 600, seed=21, mixed_pbc=True)
+    pos, cell, pbc, bidx, bptr = pos.to(DEV), cell.to(DEV), pbc.to(DEV), bidx.to(DEV), bptr.to(DEV)
+    e1, p1, s1 = _nl().neighbor_list(pos, 6.0, cell=cell, pbc=pbc, batch_idx=bidx, batch_ptr=bptr, return_neighbor_list=True,
+                                     method="batch_cell_list")
+    want = ro.records_from_coo(e1.cpu(), s1.cpu())
+    dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        for chunks in (1, 2, 3, 16):          # 16 > systems: some chunks are empty
+            e, p, s, stats = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, return_stats=True, chunks=chunks,
+                                                         _exchange_when_alone=True)
+            assert stats["packed"] and stats["chunks"] == chunks and stats["peer_bytes"] == 0
+            assert torch.equal(p, p1), chunks
+            assert bool((e[0, 1:] >= e[0, :-1]).all()), chunks
+            assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), chunks
+        # the world-of-one short cut (what bench.py's N = 1 leg calls) gives the same list
+        e, p, s = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr)
+        assert torch.equal(p, p1) and np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want)
+        with pytest.raises(_nl().NeighborOverflowError):
+            sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, max_neighbors=1, _exchange_when_alone=True)
+    finally:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------
 # split build / query workflow and rebuild detection (SURVEY.md §8f; reference cell_list.py:1037-1192,
 # rebuild_detection.py, docs/userguide/components/neighborlist.md:421-500)
