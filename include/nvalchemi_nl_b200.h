@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NVNL_ABI_VERSION 5
+#define NVNL_ABI_VERSION 6
 #define NVNL_F32 0
 #define NVNL_F64 1
 
@@ -228,6 +228,10 @@ int nvnl_moved_beyond(const void* reference_positions, const void* current_posit
  *   set when a component lies outside {-1, 0, 1} (unwrapped inputs, boxes smaller than the cutoff: the caller then
  *   gathers the int32 shifts instead). */
 int nvnl_pack_shifts(const int32_t* shifts, int64_t n_pairs, uint8_t* packed, int32_t* bad_flag, void* stream);
+/* One-word form of the exchange (atom indices below 2^26): targets[p] |= packed byte << 26, in place on the rank's own
+ * staging slot — 4 B per pair and ONE array travel.  *bad_flag is also set when a target index does not fit 26 bits.
+ * nvnl_expand_padded / nvnl_expand_padded_ranges take such an array as gathered_dst with gathered_packed = NULL. */
+int nvnl_pack_shifts_word(const int32_t* shifts, int64_t n_pairs, int32_t* targets, int32_t* bad_flag, void* stream);
 /* out_i (row 0 of edge_index) and shifts [P,3] of every atom outside [atom_lo, atom_hi) from the global
  * neighbor_ptr [n_atoms+1] and the gathered packed shifts [P]. */
 int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t atom_lo, int64_t atom_hi,
@@ -236,7 +240,8 @@ int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t a
 /* Re-assembly after a PADDED all-gather (one ncclAllGather per array, in place): rank g's targets / packed shifts sit at
  * gathered_dst[g * pmax + k] / gathered_packed[g * pmax + k], k = pair index inside the rank's range
  * [pair_bounds[g], pair_bounds[g+1]); atoms of rank g are [atom_bounds[g], atom_bounds[g+1]) (world + 1 HOST int64 each,
- * world <= 16).  Writes out_j (row 1 of edge_index) for every pair and out_i / shifts for the pairs of the other ranks. */
+ * world <= 16).  Writes out_j (row 1 of edge_index) for every pair and out_i / shifts for the pairs of the other ranks.
+ * gathered_packed = NULL: one-word exchange, gathered_dst[.] = target | packed shift << 26 (nvnl_pack_shifts_word). */
 int nvnl_expand_padded(const int32_t* neighbor_ptr, int64_t n_atoms, int32_t world, int32_t rank, const int64_t* atom_bounds,
                        const int64_t* pair_bounds, int64_t pmax, const int32_t* gathered_dst, const uint8_t* gathered_packed,
                        int32_t* out_i, int32_t* out_j, int32_t* shifts, void* stream);

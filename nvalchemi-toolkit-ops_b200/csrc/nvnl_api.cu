@@ -438,6 +438,24 @@ __global__ void k_pack_shifts(const int* __restrict__ shifts, long long n_pairs,
     if (err && bad) atomicOr(bad, 1);
 }
 
+// One-word form of the exchange (atom indices below 2^26): the packed shift rides in bits 26..31 of the pair's target
+// word, so a rank sends 4 B per pair and ONE array.  *bad is set when a component is outside {-1,0,1} or a target >= 2^26.
+constexpr int kWordShift = 26;
+constexpr unsigned kWordMask = (1u << kWordShift) - 1u;
+__global__ void k_pack_shifts_word(const int* __restrict__ shifts, long long n_pairs, int* __restrict__ targets, int* __restrict__ bad) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    int err = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += nthreads) {
+        const int sx = shifts[3 * p] + 1, sy = shifts[3 * p + 1] + 1, sz = shifts[3 * p + 2] + 1;
+        err |= (sx | sy | sz) & ~3;
+        err |= (sx == 3) | (sy == 3) | (sz == 3);
+        const unsigned t = (unsigned)targets[p];
+        err |= (t & ~kWordMask) != 0u;
+        targets[p] = (int)((t & kWordMask) | ((unsigned)((sx & 3) | ((sy & 3) << 2) | ((sz & 3) << 4)) << kWordShift));
+    }
+    if (err && bad) atomicOr(bad, 1);
+}
+
 // out_i / shifts of every atom OUTSIDE [atom_lo, atom_hi) from neighbor_ptr and the gathered packed shifts (the rank's
 // own range was written by its fill kernels).  One warp per 32 atoms, rows written sequentially.
 __global__ void __launch_bounds__(256) k_expand_gathered(const int* __restrict__ neighbor_ptr, long long n_atoms,
@@ -479,6 +497,8 @@ struct ExpandRanks {
     long long atom_hi[17];
     long long pair_lo[17];    // first pair of rank g's range (= neighbor_ptr[atom_lo[g]])
 };
+// WORD: gathered_dst holds target | packed shift << 26 and gathered_packed is not read.
+template <bool WORD>
 __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ neighbor_ptr, long long n_atoms, ExpandRanks R,
                                                        long long pmax, const int* __restrict__ gathered_dst,
                                                        const unsigned char* __restrict__ gathered_packed,
@@ -520,7 +540,12 @@ __global__ void __launch_bounds__(256) k_expand_padded(const int* __restrict__ n
                 for (int u = 0; u < 4; ++u) {
                     const int k = k0 + 32 * u + lane;
                     dv[u] = k < cnt ? dj[k] : 0;
-                    pv[u] = (foreign && k < cnt) ? (int)pk[k] : 0;
+                    if (WORD) {
+                        pv[u] = (int)((unsigned)dv[u] >> kWordShift);
+                        dv[u] = (int)((unsigned)dv[u] & kWordMask);
+                    } else {
+                        pv[u] = (foreign && k < cnt) ? (int)pk[k] : 0;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -944,6 +969,19 @@ int nvnl_pack_shifts(const int32_t* shifts, int64_t n_pairs, uint8_t* packed, in
     return 0;
 }
 
+int nvnl_pack_shifts_word(const int32_t* shifts, int64_t n_pairs, int32_t* targets, int32_t* bad_flag, void* stream) {
+    if (n_pairs < 0) return fail(-1, "nvnl_pack_shifts_word: negative pair count");
+    if (n_pairs == 0) return 0;
+    if (!shifts || !targets) return fail(-1, "nvnl_pack_shifts_word: null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long blocks = (n_pairs + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pack_shifts_word<<<(unsigned)blocks, 256, 0, st>>>(shifts, n_pairs, targets, bad_flag);
+    NVNL_CHECK_LAUNCH("k_pack_shifts_word");
+    return 0;
+}
+
 int nvnl_expand_gathered(const int32_t* neighbor_ptr, int64_t n_atoms, int64_t atom_lo, int64_t atom_hi,
                          const uint8_t* packed_shifts, int32_t* out_i, int32_t* shifts, void* stream) {
     if (n_atoms < 0 || atom_lo < 0 || atom_hi < atom_lo || atom_hi > n_atoms) return fail(-1, "nvnl_expand_gathered: bad atom range");
@@ -962,7 +1000,7 @@ static int expand_padded_launch(const char* who, const int32_t* neighbor_ptr, in
                                 const int32_t* gathered_dst, const uint8_t* gathered_packed, int32_t* out_i, int32_t* out_j,
                                 int32_t* shifts, void* stream) {
     if (n_atoms <= 0) return 0;
-    if (!neighbor_ptr || !gathered_dst || !gathered_packed || !out_i || !out_j || !shifts) {
+    if (!neighbor_ptr || !gathered_dst || !out_i || !out_j || !shifts) {
         char msg[96];
         snprintf(msg, sizeof(msg), "%s: null pointer", who);
         return fail(-1, msg);
@@ -971,8 +1009,12 @@ static int expand_padded_launch(const char* who, const int32_t* neighbor_ptr, in
     long long blocks = (n_atoms + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_expand_padded<<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, R, pmax, gathered_dst, gathered_packed, out_i, out_j,
-                                                      shifts);
+    if (gathered_packed)
+        k_expand_padded<false><<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, R, pmax, gathered_dst, gathered_packed,
+                                                                 out_i, out_j, shifts);
+    else   // one-word exchange: the packed shifts ride in the top bits of gathered_dst
+        k_expand_padded<true><<<(unsigned)blocks, 256, 0, st>>>(neighbor_ptr, n_atoms, R, pmax, gathered_dst, nullptr, out_i, out_j,
+                                                                shifts);
     NVNL_CHECK_LAUNCH("k_expand_padded");
     return 0;
 }

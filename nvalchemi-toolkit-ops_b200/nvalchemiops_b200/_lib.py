@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "csrc", "libnvalchemi_nl_b200.so"))
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 c_void_p, c_int, c_int32, c_int64, c_double, c_size_t = (
@@ -56,6 +56,7 @@ _SIGNATURES = {
     "nvnl_coulomb_list": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_double, c_double, c_void_p,
                                   c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "nvnl_pack_shifts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nvnl_pack_shifts_word": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_padded": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "nvnl_expand_padded_ranges": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,

@@ -37,3 +37,7 @@ check_inputs: bool = False
 # exchange of chunk k (NCCL all-gather on a communication stream) runs under the output kernels of chunk k + 1 and the
 # re-assembly of chunk k - 1.  1 = one exchange after all kernels (no overlap).
 exchange_chunks: int = 2
+
+# ... and with atom indices below 2^26 the packed shift rides in the top six bits of the pair's target word: 4 B per pair
+# and one all-gather per chunk instead of 5 B and two.  False = separate byte array (any number of atoms).
+exchange_word: bool = True

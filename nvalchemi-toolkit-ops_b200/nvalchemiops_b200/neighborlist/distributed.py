@@ -7,14 +7,15 @@ one node, every rank builds the COO list of its own systems with GLOBAL atom ind
 Semantics: identical to running the whole batch on one GPU, up to the order of entries inside a source atom's row
 (which the reference leaves unspecified).
 
-Data flow (5 B per pair on the wire, no re-assembly pass over the payload, exchange overlapped with the kernels):
+Data flow (4 B per pair on the wire, no re-assembly pass over the payload, exchange overlapped with the kernels):
   1. every rank splits its own systems into ``config.exchange_chunks`` chunks; local build + sweep (counts) of every chunk;
      ONE small all-gather of (pairs, max count, error bits, flags) per rank and chunk — every rank then knows every offset
      and raises the same errors at the same point; ``num_neighbors`` is gathered and scanned into ``neighbor_ptr``;
   2. chunk by chunk every rank writes its OWN range straight into the final global arrays (``nvnl_fill_rows`` with the
      global row stride, the targets landing in the rank's slot of the chunk's staging buffer) and packs its shifts into one
      byte per pair (``nvnl_pack_shifts``);
-  3. the exchange of a chunk is ONE in-place ``ncclAllGather`` per array (targets 4 B/pair, packed shifts 1 B/pair) on a
+  3. the exchange of a chunk is ONE in-place ``ncclAllGather`` of one word per pair (target atom in bits 0..25, packed shift
+     in bits 26..31; with 2^26 atoms or more: targets 4 B/pair + a byte array of packed shifts, two all-gathers) on a
      communication stream: it runs while the next chunk is being written and the previous one re-assembled;
   4. ``nvnl_expand_padded_ranges`` (one launch per chunk) writes the targets everywhere and the source atoms / int32
      shifts of the foreign ranges.
@@ -129,6 +130,26 @@ def _pack_shifts(shifts_own, packed_own):
         packed_own.copy_(s[:, 0] | (s[:, 1] << 2) | (s[:, 2] << 4))
 
 
+_WORD_SHIFT = 26          # one-word exchange: target atom in bits 0..25, packed shift in bits 26..31
+_WORD_MASK = (1 << _WORD_SHIFT) - 1
+
+
+def _pack_shifts_word(shifts_own, targets_own):
+    """targets_own[p] |= packed shift << 26, in place on the rank's slot of the staging buffer."""
+    if shifts_own.is_cuda:
+        from .. import _lib
+
+        with torch.cuda.device(shifts_own.device):
+            _lib.check(_lib.lib().nvnl_pack_shifts_word(ctypes.c_void_p(shifts_own.data_ptr()), shifts_own.shape[0],
+                                                        ctypes.c_void_p(targets_own.data_ptr()), None,
+                                                        ctypes.c_void_p(torch.cuda.current_stream(shifts_own.device).cuda_stream)),
+                       "nvnl_pack_shifts_word")
+    else:  # gloo tests of the plumbing
+        s = (shifts_own + 1).to(torch.int64)
+        w = targets_own.to(torch.int64) | ((s[:, 0] | (s[:, 1] << 2) | (s[:, 2] << 4)) << _WORD_SHIFT)
+        targets_own.copy_(torch.where(w >= 2**31, w - 2**32, w).to(torch.int32))      # the same 32 bits as an int32
+
+
 def _expand(neighbor_ptr, n_atoms, a0, a1, packed, edge, shifts):
     if edge.is_cuda:
         from .. import _lib
@@ -189,17 +210,24 @@ def _expand_chunk(neighbor_ptr, n_atoms, world, rank, begins, ends, pair_begins,
         with torch.cuda.device(edge.device):
             _lib.check(_lib.lib().nvnl_expand_padded_ranges(
                 ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, world, rank, arr(*begins), arr(*ends), arr(*pair_begins), pmax,
-                ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_packed.data_ptr()), ctypes.c_void_p(edge[0].data_ptr()),
+                ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_packed.data_ptr()) if t_packed is not None else None,
+                ctypes.c_void_p(edge[0].data_ptr()),
                 ctypes.c_void_p(edge[1].data_ptr()), ctypes.c_void_p(shifts.data_ptr()),
                 ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)), "nvnl_expand_padded_ranges")
         return
     src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), torch.diff(neighbor_ptr).long())
     for g in range(world):
         lo, hi = pair_begins[g], pair_begins[g] + counts[g]
-        edge[1, lo:hi] = t_dst[g * pmax: g * pmax + (hi - lo)]
+        got = t_dst[g * pmax: g * pmax + (hi - lo)]
+        if t_packed is None:                                   # one-word exchange
+            w = got.to(torch.int64) & 0xFFFFFFFF
+            edge[1, lo:hi] = (w & _WORD_MASK).to(torch.int32)
+            pk = (w >> _WORD_SHIFT).to(torch.int32)
+        else:
+            edge[1, lo:hi] = got
+            pk = t_packed[g * pmax: g * pmax + (hi - lo)].to(torch.int32)
         if g == rank:
             continue
-        pk = t_packed[g * pmax: g * pmax + (hi - lo)].to(torch.int32)
         edge[0, lo:hi] = src[lo:hi]
         shifts[lo:hi] = torch.stack([(pk & 3) - 1, ((pk >> 2) & 3) - 1, ((pk >> 4) & 3) - 1], dim=1).to(torch.int32)
 
@@ -346,7 +374,8 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
         ebuf = torch.empty(2 * P + K * world * pmax, dtype=torch.int32, device=dev)
         edge = ebuf[:2 * P].view(2, P)
         t_dst = ebuf[2 * P:]
-        t_packed = torch.empty(K * world * pmax, dtype=torch.uint8, device=dev)
+        word = bool(config.exchange_word) and N <= _WORD_MASK       # every atom index fits 26 bits: 4 B per pair, one array
+        t_packed = None if word else torch.empty(K * world * pmax, dtype=torch.uint8, device=dev)
         on_gpu = dev.type == "cuda"
         cur = torch.cuda.current_stream(dev) if on_gpu else None
         comm = _comm_stream(dev) if on_gpu and K > 1 else cur
@@ -358,7 +387,9 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             if sh is not None:
                 # row 0 at the chunk's offset of the final array, row 1 in the rank's slot of the chunk's staging buffer
                 sh.fill(ebuf[o0:], shifts[o0:o0 + cnt], (2 * P + slot) - o0)
-                if cnt > 0:
+                if cnt > 0 and word:
+                    _pack_shifts_word(shifts[o0:o0 + cnt], t_dst[slot:slot + cnt])
+                elif cnt > 0:
                     _pack_shifts(shifts[o0:o0 + cnt], t_packed[slot:slot + cnt])
             if pmax == 0:
                 continue
@@ -372,7 +403,8 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
                         b = torch.cuda.Event(enable_timing=True)
                         b.record(comm)
                     dist.all_gather_into_tensor(t_dst[base:base + world * pmax], t_dst[slot:slot + pmax], group=group)
-                    dist.all_gather_into_tensor(t_packed[base:base + world * pmax], t_packed[slot:slot + pmax], group=group)
+                    if not word:
+                        dist.all_gather_into_tensor(t_packed[base:base + world * pmax], t_packed[slot:slot + pmax], group=group)
                     ev = torch.cuda.Event(enable_timing=return_stats)
                     ev.record(comm)
                     if return_stats:
@@ -381,8 +413,9 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             else:   # gloo tests of the plumbing
                 dist.all_gather([t_dst[base + g * pmax: base + (g + 1) * pmax] for g in range(world)],
                                 t_dst[slot:slot + pmax].clone(), group=group)
-                dist.all_gather([t_packed[base + g * pmax: base + (g + 1) * pmax] for g in range(world)],
-                                t_packed[slot:slot + pmax].clone(), group=group)
+                if not word:
+                    dist.all_gather([t_packed[base + g * pmax: base + (g + 1) * pmax] for g in range(world)],
+                                    t_packed[slot:slot + pmax].clone(), group=group)
         mark("alloc_fill_own_pack")
         # ---- 4. per chunk, as its exchange completes: the targets everywhere, source atoms / shifts of the foreign ranges ----
         for k in range(K):
@@ -394,8 +427,9 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
             _expand_chunk(neighbor_ptr, N, world, rank, [sub_atoms[g][k][0] for g in range(world)],
                           [sub_atoms[g][k][1] for g in range(world)], [offs[g][k] for g in range(world)],
                           [counts[g][k] for g in range(world)], pmax, t_dst[base:base + world * pmax],
-                          t_packed[base:base + world * pmax], edge, shifts)
+                          None if word else t_packed[base:base + world * pmax], edge, shifts)
         mark("exchange_wait_expand")
+        stats["bytes_per_pair"] = 4 if word else 5
         if comm_marks:
             stats["_comm_marks"] = comm_marks
     else:
@@ -413,7 +447,7 @@ def sharded_batch_neighbor_list(positions, cutoff, cell, pbc, batch_ptr, half_fi
         torch.cumsum(num_all, 0, out=neighbor_ptr[1:])
         mark("ptr_scan")
     if return_stats:
-        per_pair = 5 if packed_ok else 20
+        per_pair = stats.get("bytes_per_pair", 20)
         own_pairs = rank_lo[rank + 1] - rank_lo[rank]
         comm_marks = stats.pop("_comm_marks", [])
         stats.update({"peer_bytes": per_pair * (P - own_pairs) + 4 * (N - n_loc), "packed": packed_ok, "chunks": K})

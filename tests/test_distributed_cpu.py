@@ -53,11 +53,17 @@ def _worker(rank, world, port, out_dir):
     # the chunked exchange (config.exchange_chunks = 2 above): any number of chunks per rank gives the same arrays,
     # also when some chunks of some ranks are empty (9 systems over 3 ranks x 4 chunks)
     import reference_oracle as ro
-    for chunks in (1, 3, 4):
-        e2, ptr2, s2 = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_shard=_OracleShard, chunks=chunks)
+    from nvalchemiops_b200 import config
+    for chunks, word in ((1, True), (3, True), (4, True), (2, False), (3, False)):
+        # word: target atom and packed shift in ONE int32 per pair (4 B); otherwise targets + a byte array (5 B)
+        config.exchange_word = word
+        e2, ptr2, s2, st = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, _local_shard=_OracleShard, chunks=chunks,
+                                                       return_stats=True)
+        assert st["packed"] and st["chunks"] == chunks and st["bytes_per_pair"] == (4 if word else 5)
         assert torch.equal(ptr2, ptr), chunks
         assert np.array_equal(ro.records_from_coo(e2, s2), ro.records_from_coo(e, s)), chunks
         assert bool((e2[0, 1:] >= e2[0, :-1]).all()), chunks
+    config.exchange_word = True
     shard = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, gather=False, _local_shard=_OracleShard)
     torch.save({"e": shard[0], "range": shard[3]}, os.path.join(out_dir, f"s{rank}.pt"))
     dist.barrier()

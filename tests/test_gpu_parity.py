@@ -439,6 +439,42 @@ def test_sharded_ranges_fill_pack_and_expand_on_one_gpu():
                 "expand_padded_ranges")
             torch.cuda.synchronize()
         assert torch.equal(e3, edge) and torch.equal(s3, shifts), rank
+    # one-word exchange: nvnl_pack_shifts_word ORs the packed shift into bits 26..31 of the targets in place; the
+    # expansion takes the words as gathered_dst with gathered_packed = NULL
+    words = edge[1].clone()
+    bad.zero_()
+    _lib.check(_lib.lib().nvnl_pack_shifts_word(ctypes.c_void_p(shifts.data_ptr()), P, ctypes.c_void_p(words.data_ptr()),
+                                                ctypes.c_void_p(bad.data_ptr()), st), "pack_word")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+    assert torch.equal(words & ((1 << 26) - 1), edge[1])
+    assert torch.equal(((words.long() & 0xFFFFFFFF) >> 26).to(torch.uint8), packed)
+    for rank in range(world):
+        e3, s3 = edge.clone(), shifts.clone()
+        e3[1] = -9
+        keep = torch.zeros(P, dtype=torch.bool, device=DEV); keep[offs[rank]:offs[rank + 1]] = True
+        e3[0, ~keep] = -9
+        s3[~keep] = -9
+        for ranges in chunk_atoms:
+            cnts = [nptr_h[b] - nptr_h[a] for a, b in ranges]
+            pm = max(cnts)
+            if pm == 0:
+                continue
+            c_dst = torch.full((world * pm,), -5, dtype=torch.int32, device=DEV)
+            for g, (a, b) in enumerate(ranges):
+                c_dst[g * pm: g * pm + cnts[g]] = words[nptr_h[a]:nptr_h[b]]
+            _lib.check(_lib.lib().nvnl_expand_padded_ranges(
+                ctypes.c_void_p(nptr.data_ptr()), N, world, rank, arr(*[a for a, _ in ranges]), arr(*[b for _, b in ranges]),
+                arr(*[nptr_h[a] for a, _ in ranges]), pm, ctypes.c_void_p(c_dst.data_ptr()), None,
+                ctypes.c_void_p(e3[0].data_ptr()), ctypes.c_void_p(e3[1].data_ptr()), ctypes.c_void_p(s3.data_ptr()), st),
+                "expand_padded_ranges (word)")
+            torch.cuda.synchronize()
+        assert torch.equal(e3, edge) and torch.equal(s3, shifts), rank
+    big = torch.tensor([5, 1 << 26], dtype=torch.int32, device=DEV)       # a target that does not fit 26 bits is reported
+    bad.zero_()
+    _lib.check(_lib.lib().nvnl_pack_shifts_word(ctypes.c_void_p(shifts.data_ptr()), 2, ctypes.c_void_p(big.data_ptr()),
+                                                ctypes.c_void_p(bad.data_ptr()), st), "pack_word")
+    assert int(bad.item()) == 1
     bad_ranges = arr(10, 5)
     assert _lib.lib().nvnl_expand_padded_ranges(ctypes.c_void_p(nptr.data_ptr()), N, world, 0, bad_ranges, arr(20, 30), arr(0, 0), 1,
                                                 ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_pk.data_ptr()),
@@ -470,10 +506,14 @@ def test_chunked_exchange_pipeline_on_one_gpu(tmp_path):
     want = ro.records_from_coo(e1.cpu(), s1.cpu())
     dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1, device_id=torch.device(DEV))
     try:
-        for chunks in (1, 2, 3, 16):          # 16 > systems: some chunks are empty
+        from nvalchemiops_b200 import config
+        for chunks, word in ((1, True), (2, True), (3, True), (16, True), (2, False), (3, False)):   # 16 > systems: empty chunks
+            config.exchange_word = word       # one int32 per pair (target | shift << 26) or targets + a byte array
             e, p, s, stats = sharded_batch_neighbor_list(pos, 6.0, cell, pbc, bptr, return_stats=True, chunks=chunks,
                                                          _exchange_when_alone=True)
+            config.exchange_word = True
             assert stats["packed"] and stats["chunks"] == chunks and stats["peer_bytes"] == 0
+            assert stats["bytes_per_pair"] == (4 if word else 5)
             assert torch.equal(p, p1), chunks
             assert bool((e[0, 1:] >= e[0, :-1]).all()), chunks
             assert np.array_equal(ro.records_from_coo(e.cpu(), s.cpu()), want), chunks

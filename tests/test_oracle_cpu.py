@@ -153,7 +153,7 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(L, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.declared_symbols())
     lib = _lib.lib()
-    assert lib.nvnl_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.nvnl_abi_version() == _lib.ABI_VERSION == 6
     assert lib.nvnl_workspace_bytes(1000, 1, 0) > 1000 * 16
     assert lib.nvnl_workspace_bytes(1000, 4, 1) > lib.nvnl_workspace_bytes(1000, 4, 0)
     # argument validation happens before any CUDA call
