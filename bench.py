@@ -561,14 +561,17 @@ def main():
                 if "phase_ms" in stats:
                     res[name]["phase_ms_rank0_one_call"] = stats["phase_ms"]
                 res[name].update({"peer_bytes_per_rank": stats["peer_bytes"], "packed_exchange": stats["packed"],
+                                  "exchange_chunks_per_rank": stats.get("chunks"), "wire_bytes_per_pair": stats.get("bytes_per_pair", 20),
                                   "full_payload_bytes_per_rank": 20 * (tot - tot // world) + 4 * (4096000 - 4096000 // world)})
         if world > 1 and "with_gather" in res and "kernels_only" in res:
             t_gather = max(res["with_gather"]["ms_per_step"] - res["kernels_only"]["ms_per_step"], 1e-6)
             res["with_gather"]["gather_ms"] = t_gather
             res["with_gather"]["nvlink_frac"] = res["with_gather"].get("peer_bytes_per_rank", 0) / (t_gather * 1e-3) / 1e9 / NVLINK_GBS_PER_DIR
             res["with_gather"]["nvlink_note"] = ("bytes a rank receives from its peers / (with_gather - kernels_only time) / 900 GB/s per "
-                                                 "direction; the exchange is 5 B/pair (target atom + packed shift) instead of 20 B/pair, "
-                                                 "so the same result needs 4x fewer NVLink bytes than full_payload_bytes_per_rank")
+                                                 "direction; the exchange is wire_bytes_per_pair (target atom + packed shift) instead of 20 B/pair, "
+                                                 "so the same result needs 4-5x fewer NVLink bytes than full_payload_bytes_per_rank; it runs in "
+                                                 "exchange_chunks_per_rank chunks on a communication stream under the kernels of the "
+                                                 "neighbouring chunks (phase_ms_rank0_one_call.nccl_chunks_on_comm_stream)")
         sharded = {"workload": "config 5: 4096 systems x 1000 atoms, periodic, COO, sharded by batch_ptr (strong scaling)", **res}
         del bp, bc, bb, bptr
 
