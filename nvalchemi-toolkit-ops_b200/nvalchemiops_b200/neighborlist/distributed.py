@@ -150,56 +150,6 @@ def _pack_shifts_word(shifts_own, targets_own):
         targets_own.copy_(torch.where(w >= 2**31, w - 2**32, w).to(torch.int32))      # the same 32 bits as an int32
 
 
-def _expand(neighbor_ptr, n_atoms, a0, a1, packed, edge, shifts):
-    if edge.is_cuda:
-        from .. import _lib
-
-        with torch.cuda.device(edge.device):
-            _lib.check(_lib.lib().nvnl_expand_gathered(ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, a0, a1,
-                                                       ctypes.c_void_p(packed.data_ptr()), ctypes.c_void_p(edge.data_ptr()),
-                                                       ctypes.c_void_p(shifts.data_ptr()),
-                                                       ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)),
-                       "nvnl_expand_gathered")
-    else:
-        counts = torch.diff(neighbor_ptr).long()
-        src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), counts)
-        p = packed.to(torch.int32)
-        full = torch.stack([(p & 3) - 1, ((p >> 2) & 3) - 1, ((p >> 4) & 3) - 1], dim=1).to(torch.int32)
-        lo, hi = int(neighbor_ptr[a0]), int(neighbor_ptr[a1])
-        keep_e, keep_s = edge[0, lo:hi].clone(), shifts[lo:hi].clone()
-        edge[0].copy_(src)
-        shifts.copy_(full)
-        edge[0, lo:hi] = keep_e
-        shifts[lo:hi] = keep_s
-
-
-def _expand_padded(neighbor_ptr, n_atoms, world, rank, atom_ranges, offs, pmax, t_dst, t_packed, edge, shifts):
-    """edge[1] for every pair, edge[0] / shifts for the other ranks' pairs, from the padded gathered staging buffers."""
-    if edge.is_cuda:
-        from .. import _lib
-
-        ab = (ctypes.c_int64 * (world + 1))(*([a for a, _ in atom_ranges] + [atom_ranges[-1][1]]))
-        pb = (ctypes.c_int64 * (world + 1))(*offs)
-        with torch.cuda.device(edge.device):
-            _lib.check(_lib.lib().nvnl_expand_padded(ctypes.c_void_p(neighbor_ptr.data_ptr()), n_atoms, world, rank, ab, pb, pmax,
-                                                     ctypes.c_void_p(t_dst.data_ptr()), ctypes.c_void_p(t_packed.data_ptr()),
-                                                     ctypes.c_void_p(edge[0].data_ptr()), ctypes.c_void_p(edge[1].data_ptr()),
-                                                     ctypes.c_void_p(shifts.data_ptr()),
-                                                     ctypes.c_void_p(torch.cuda.current_stream(edge.device).cuda_stream)),
-                       "nvnl_expand_padded")
-        return
-    counts = torch.diff(neighbor_ptr).long()
-    src = torch.repeat_interleave(torch.arange(n_atoms, dtype=torch.int32), counts)
-    for g in range(world):
-        lo, hi = offs[g], offs[g + 1]
-        edge[1, lo:hi] = t_dst[g * pmax: g * pmax + (hi - lo)]
-        if g == rank:
-            continue
-        pk = t_packed[g * pmax: g * pmax + (hi - lo)].to(torch.int32)
-        edge[0, lo:hi] = src[lo:hi]
-        shifts[lo:hi] = torch.stack([(pk & 3) - 1, ((pk >> 2) & 3) - 1, ((pk >> 4) & 3) - 1], dim=1).to(torch.int32)
-
-
 def _expand_chunk(neighbor_ptr, n_atoms, world, rank, begins, ends, pair_begins, counts, pmax, t_dst, t_packed, edge, shifts):
     """One chunk of the exchange: ``t_dst`` / ``t_packed`` are the chunk's world x pmax staging buffers; rank g's atoms of
     the chunk are [begins[g], ends[g]) and its ``counts[g]`` pairs start at ``pair_begins[g]``."""
